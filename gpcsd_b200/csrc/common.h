@@ -1,0 +1,17 @@
+// Shared host-side helpers of libgpcsd_b200.so: error reporting across the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/gpcsd_b200.h"
+
+int gp_fail(const char* msg);                 // records msg, returns 1
+int gp_fail_cuda(cudaError_t e, const char* what, int line);
+int gp_num_sms();
+
+#define GP_CUDA(expr)                                                  \
+  do {                                                                 \
+    cudaError_t _e = (expr);                                           \
+    if (_e != cudaSuccess) return gp_fail_cuda(_e, #expr, __LINE__);   \
+  } while (0)

@@ -1,0 +1,463 @@
+"""Device-resident GPCSD engine: orchestrates the C-ABI kernels of libgpcsd_b200.so for one model.
+
+Replaces the numpy/scipy/autograd arithmetic of the reference's ``loglik`` (gpcsd1d.py:113-128,
+gpcsd2d.py:136-151), of ``grad(obj_fun)`` (gpcsd1d.py:211, gpcsd2d.py:250) and of ``predict``
+(gpcsd1d.py:248-293, gpcsd2d.py:289-334).  PyTorch is used only for device memory, streams and
+``torch.distributed``; every flop of the path runs in the hand-written sm_100a kernels (plus cuSOLVER
+syevd for the two small eigendecompositions, as BASELINE.json's north_star allows).
+
+Data layout in HBM (all FP64, row-major, trial index fastest exactly like the reference's C-order
+``lfp[nx, nt, ntrials]``):
+    Y, Z, Bm : [nx][nt][ldn]   ldn = ntrials_local rounded up to 8 (64-byte rows, zero padded)
+    QsT, QtT : eigenvector matrices transposed (= cuSOLVER's column-major output), Qs, Qt row-major copies
+    rD       : [nx][ld(nt)] reciprocal Kronecker eigenvalues 1/(ls_i lt_j + sig2n_i)
+
+Trial sharding (torch.distributed): every rank holds a contiguous slab of trials; the small factors are
+replicated (recomputed deterministically on every rank); partial (loglik, gradient) vectors are summed
+with ONE all-reduce of P+1 doubles per evaluation.  ``predict`` needs no collective.
+"""
+import ctypes
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .parallel import TrialShard
+
+F64 = torch.float64
+
+
+def _even(n):
+    return (int(n) + 1) // 2 * 2
+
+
+def _ld8(n):
+    return (int(n) + 7) // 8 * 8
+
+
+@dataclass
+class HyperParams:
+    """Natural-unit hyperparameters read from a GPCSD1D/GPCSD2D object."""
+    R: float
+    ells: Tuple[float, ...]
+    temporal: List[Tuple[int, float, float]]          # (kind, ell, sigma2) in temporal_cov_list order
+    sig2n: Union[float, np.ndarray]                   # scalar or per spatial-eigen-index vector (util:54-57)
+    eps: float = 0.0
+
+    @property
+    def vector_noise(self):
+        return np.ndim(self.sig2n) > 0
+
+    def n_params(self):
+        return 1 + len(self.ells) + 2 * len(self.temporal) + (len(self.sig2n) if self.vector_noise else 1)
+
+
+class KronEngine:
+    """One model's geometry + LFP shard on one GPU."""
+
+    def __init__(self, dim, x, t, quad, device=None, group=None, jitter=None):
+        if not torch.cuda.is_available():
+            raise L.GpcsdLibraryError("gpcsd_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        L.load()
+        self.dim = int(dim)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.shard = TrialShard(group)
+        self.jitter = (1e-8 if dim == 1 else 1e-7) if jitter is None else jitter   # gpcsd1d.py:17 / gpcsd2d.py:16
+        self._ws = {}
+        self.set_geometry(x, t, quad)
+        self.Y = None
+        self.ntrials_total = 0
+        self.ntrials = 0
+        self.n_launches = 0
+
+    # ------------------------------------------------------------------ plumbing
+    def _dev(self, arr):
+        return torch.as_tensor(np.ascontiguousarray(arr, dtype=np.float64)).to(self.device)
+
+    def _buf(self, name, *shape, dtype=F64):
+        """Cached, zero-initialised device workspace."""
+        key = (name, tuple(int(s) for s in shape), dtype)
+        b = self._ws.get(key)
+        if b is None:
+            b = torch.zeros(tuple(int(s) for s in shape), dtype=dtype, device=self.device)
+            self._ws[key] = b
+        return b
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    # kernels of OURS launched per ABI call (cuSOLVER's own launches inside gpcsd_eigh are not counted)
+    _LAUNCHES = {"gpcsd_project_quad": 2, "gpcsd_wsyrk": 2, "gpcsd_eig_D": 2, "gpcsd_kt_grad": 2, "gpcsd_dot": 2}
+
+    def _call(self, name, *args):
+        self.n_launches += self._LAUNCHES.get(name, 1)
+        return L.call(name, *args)
+
+    @staticmethod
+    def _p(t, offset=0):
+        return t.data_ptr() + 8 * int(offset)
+
+    def gemm(self, transB, M, N, K, A, lda, sA, B, ldb, sB, C, ldc, sC, batch=1):
+        self._call("gpcsd_dgemm", int(transB), int(M), int(N), int(K), self._p(A), lda, sA, self._p(B), ldb, sB,
+                   self._p(C), ldc, sC, int(batch), self._stream())
+
+    # ------------------------------------------------------------------ geometry / data
+    def set_geometry(self, x, t, quad):
+        """x: (nx,1) [1-D] or (nx,2) [2-D]; t: (nt,1); quad: GL nodes/weights on [a,b] (covariances.py:22-27,
+        114-124).  Quadrature axes are padded to an even length with ZERO-weight nodes so every operand row
+        is 16-byte aligned; zero weights contribute exactly 0 to every quadrature sum."""
+        x = np.asarray(x, dtype=np.float64)
+        self.nx = x.shape[0]
+        self.t_host = np.asarray(t, dtype=np.float64).reshape(-1)
+        self.nt = self.t_host.shape[0]
+        self.t_dev = self._dev(self.t_host)
+        if self.dim == 1:
+            gx, gw = np.asarray(quad["gl_x"], dtype=np.float64), np.asarray(quad["gl_w"], dtype=np.float64)
+            if len(gx) % 2:
+                gx, gw = np.append(gx, gx[-1]), np.append(gw, 0.0)
+            self.G = len(gx)
+            self.gl_x, self.gl_w = self._dev(gx), self._dev(gw)
+            self.x_dev = self._dev(x.reshape(-1))
+        else:
+            g1, w1 = np.asarray(quad["gl_x1"], dtype=np.float64), np.asarray(quad["gl_w1"], dtype=np.float64)
+            g2, w2 = np.asarray(quad["gl_x2"], dtype=np.float64), np.asarray(quad["gl_w2"], dtype=np.float64)
+            if len(g2) % 2:
+                g2, w2 = np.append(g2, g2[-1]), np.append(w2, 0.0)
+            self.G1, self.G2 = len(g1), len(g2)
+            self.G = self.G1 * self.G2
+            self.gl_x1, self.gl_w1, self.gl_x2, self.gl_w2 = self._dev(g1), self._dev(w1), self._dev(g2), self._dev(w2)
+            self.x_dev = self._dev(x.reshape(self.nx, 2))
+        self.ldx = _even(self.nx)
+        self.ldt = _even(self.nt)
+
+    def set_lfp(self, lfp):
+        """Upload this rank's slab of trials.  lfp: host (nx, nt, ntrials) float64 (C order) or a CUDA tensor
+        of that shape; returns bytes copied host->device."""
+        if isinstance(lfp, torch.Tensor):
+            src = lfp if lfp.dim() == 3 else lfp.reshape(lfp.shape[0], lfp.shape[1], -1)
+            if src.dtype != F64:
+                raise TypeError("lfp tensor must be float64")
+        else:
+            src = torch.from_numpy(np.ascontiguousarray(np.atleast_3d(np.asarray(lfp, dtype=np.float64))))
+        ntot = src.shape[2]
+        if src.shape[0] != self.nx or src.shape[1] != self.nt:
+            raise ValueError("lfp shape %s does not match (nx=%d, nt=%d)" % (tuple(src.shape), self.nx, self.nt))
+        lo, hi = self.shard.bounds(ntot)
+        n = hi - lo
+        ldn = _ld8(max(n, 1))
+        if self.Y is None or self.Y.shape != (self.nx, self.nt, ldn):
+            self.Y = torch.zeros((self.nx, self.nt, ldn), dtype=F64, device=self.device)
+        elif ldn != n:
+            self.Y[:, :, n:].zero_()
+        slab = src[:, :, lo:hi]
+        if src.is_cuda:
+            self.Y[:, :, :n].copy_(slab)
+            nbytes = 0
+        else:
+            # pinned host tensors (torch.Tensor.pin_memory) make this a true async DMA
+            dst = self.Y if ldn == n else self.Y[:, :, :n]
+            dst.copy_(slab if (lo == 0 and hi == ntot) else slab.contiguous(), non_blocking=True)
+            nbytes = slab.numel() * 8
+        self.ntrials_total, self.ntrials, self.ldn = ntot, n, ldn
+        return nbytes
+
+    # ------------------------------------------------------------------ covariance construction
+    def _fwd_weights(self, pts_dev, npts, hp, want_dA, tag):
+        A = self._buf("A_" + tag, npts, self.G)
+        dA = self._buf("dA_" + tag, npts, self.G) if want_dA else None
+        if self.dim == 1:
+            self._call("gpcsd_fwd_weights_1d", npts, self._p(pts_dev), self.G, self._p(self.gl_x), self._p(self.gl_w),
+                       float(hp.R), self._p(A), self._p(dA) if want_dA else None, self.G, self._stream())
+        else:
+            self._call("gpcsd_fwd_weights_2d", npts, self._p(pts_dev), self.G1, self.G2, self._p(self.gl_x1),
+                       self._p(self.gl_w1), self._p(self.gl_x2), self._p(self.gl_w2), float(hp.R), float(hp.eps),
+                       self._p(A), self._p(dA) if want_dA else None, self.G, self._stream())
+        return A, dA
+
+    def _se(self, name, a, b, ell, deriv=0):
+        na, nb = a.shape[0], b.shape[0]
+        out = self._buf(name, na, _even(nb))
+        self._call("gpcsd_se_matrix", na, self._p(a), nb, self._p(b), float(ell), 1.0, int(deriv), self._p(out),
+                   _even(nb), self._stream())
+        return out
+
+    def _quad_kernels(self, hp, deriv_axis=None, tag=""):
+        """CSD SE kernel on the quadrature grid: 1-D -> [Kg]; 2-D -> Kronecker factors [K1, K2]
+        (covariances.py:89, 216: exp(-sq1/2l1^2) * exp(-sq2/2l2^2) on the x1-major product grid)."""
+        if self.dim == 1:
+            return [self._se("Kg" + tag, self.gl_x, self.gl_x, hp.ells[0], deriv=int(deriv_axis == 0))]
+        return [self._se("Kg1" + tag, self.gl_x1, self.gl_x1, hp.ells[0], deriv=int(deriv_axis == 0)),
+                self._se("Kg2" + tag, self.gl_x2, self.gl_x2, hp.ells[1], deriv=int(deriv_axis == 1))]
+
+    def _apply_quad_kernel(self, X, nrows, kern, out_name):
+        """out = X (nrows x G) * Kg, Kg given by _quad_kernels (dense 1-D, Kronecker 2-D)."""
+        out = self._buf(out_name, nrows, self.G)
+        if self.dim == 1:
+            Kg = kern[0]
+            self.gemm(0, nrows, self.G, self.G, X, self.G, 0, Kg, Kg.shape[1], 0, out, self.G, 0)
+            return out
+        K1, K2 = kern
+        G1, G2 = self.G1, self.G2
+        T = self._buf("kron_tmp", nrows, self.G)
+        # T[(i,a), b'] = sum_b X[(i,a), b] K2[b, b']
+        self.gemm(0, nrows * G1, G2, G2, X, G2, 0, K2, K2.shape[1], 0, T, G2, 0)
+        # out_i[a', b'] = sum_a K1[a', a] T_i[a, b']   (K1 symmetric), batched over rows i
+        self.gemm(0, G1, G2, G1, K1, K1.shape[1], 0, T, G2, self.G, out, G2, self.G, batch=nrows)
+        return out
+
+    def _spatial_cov(self, hp, jitter, want_grad):
+        """Ks = (A Kg) A^T (+ jitter I)   covariances.py:74-96 / 204-232."""
+        A, dA = self._fwd_weights(self.x_dev, self.nx, hp, want_grad, "x")
+        kern = self._quad_kernels(hp)
+        U = self._apply_quad_kernel(A, self.nx, kern, "U")
+        Ks = self._buf("Ks", self.nx, self.ldx)
+        self.gemm(1, self.nx, self.nx, self.G, U, self.G, 0, A, self.G, 0, Ks, self.ldx, 0)
+        if jitter:
+            self._call("gpcsd_add_diag", self.nx, self._p(Ks), self.ldx, float(self.jitter), self._stream())
+        return Ks, A, dA, U, kern
+
+    def _temporal_spec(self, temporal):
+        return (len(temporal), L.c_int_array([k for k, _, _ in temporal]), L.c_double_array([e for _, e, _ in temporal]),
+                L.c_double_array([s for _, _, s in temporal]))
+
+    def _temporal_cov(self, hp):
+        Kt = self._buf("Kt", self.nt, self.ldt)
+        ntc, kinds, ells, s2 = self._temporal_spec(hp.temporal)
+        self._call("gpcsd_kt_build", self.nt, self._p(self.t_dev), self.nt, self._p(self.t_dev), ntc, kinds, ells, s2,
+                   self._p(Kt), self.ldt, self._stream())
+        return Kt
+
+    def _eigh(self, K, n, ld, tag):
+        QT = self._buf("QT_" + tag, n, ld)
+        W = self._buf("W_" + tag, n)
+        nws = L.query("gpcsd_eigh_ws_doubles", n, ld)
+        ws = self._buf("eigws_" + tag, max(nws, 1))
+        info = self._buf("info_" + tag, 1, dtype=torch.int32)
+        self._call("gpcsd_eigh", n, self._p(K), ld, self._p(QT), ld, self._p(W), self._p(ws), nws, info.data_ptr(),
+                   self._stream())
+        return QT, W, info
+
+    def _factorize(self, hp, jitter, want_grad):
+        """Covariances -> eigen-factors -> 1/D and its reductions (comp_eig_D, utility_functions.py:44-64)."""
+        st = {}
+        st["Ks"], st["A"], st["dA"], st["U"], st["kern"] = self._spatial_cov(hp, jitter, want_grad)
+        st["Kt"] = self._temporal_cov(hp)
+        st["QsT"], st["ls"], st["info_s"] = self._eigh(st["Ks"], self.nx, self.ldx, "s")
+        st["QtT"], st["lt"], st["info_t"] = self._eigh(st["Kt"], self.nt, self.ldt, "t")
+        s_host = np.atleast_1d(np.asarray(hp.sig2n, dtype=np.float64))
+        if len(s_host) not in (1, self.nx):
+            raise ValueError("sig2n must be a scalar or have one entry per electrode")
+        st["s"] = self._dev(s_host)
+        st["rD"] = self._buf("rD", self.nx, self.ldt)
+        st["sums"] = self._buf("res", 64)            # [0:2]=quad,bsq  [2:4]=sum log D, sum 1/D  [4:]=gradient dots
+        st["rowA"], st["rowC"], st["rowL"] = self._buf("rowA", self.nx), self._buf("rowC", self.nx), self._buf("rowL", self.nx)
+        st["colB"] = self._buf("colB", self.nt)
+        self._call("gpcsd_eig_D", self.nx, self.nt, self._p(st["ls"]), self._p(st["lt"]), self._p(st["s"]), len(s_host),
+                   self._p(st["rD"]), self.ldt, self._p(st["sums"], 2), self._p(st["rowA"]), self._p(st["rowC"]),
+                   self._p(st["rowL"]), self._p(st["colB"]), self._stream())
+        return st
+
+    def _project(self, st):
+        """Z = Qs^T Y (all trials), then per spatial eigen-index A_i = Qt^T Z_i with the fused /D + quadratic
+        form epilogue (the hot loop gpcsd1d.py:124-126)."""
+        if self.Y is None:
+            raise RuntimeError("no LFP uploaded: call set_lfp first")
+        nx, nt, ldn = self.nx, self.nt, self.ldn
+        Z = self._buf("Z", nx, nt, ldn)
+        self.gemm(0, nx, nt * ldn, nx, st["QsT"], self.ldx, 0, self.Y, nt * ldn, 0, Z, nt * ldn, 0)
+        Bm = self._buf("Bm", nx, nt, ldn)
+        nws = L.query("gpcsd_project_quad_ws_doubles", nx, nt, max(self.ntrials, 1))
+        part = self._buf("quad_part", nws)
+        if self.ntrials > 0:
+            self._call("gpcsd_project_quad", nx, nt, self.ntrials, self._p(st["QtT"]), self.ldt, self._p(Z), ldn,
+                       self._p(st["rD"]), self.ldt, self._p(Bm), self._p(part), self._p(st["sums"], 0), self._stream())
+        else:
+            st["sums"][0:2].zero_()
+        st["Bm"] = Bm
+        return Bm
+
+    # ------------------------------------------------------------------ public evaluations
+    def _check_info(self, st):
+        bad = int(st["info_s"].item()) or int(st["info_t"].item())
+        if bad:
+            raise np.linalg.LinAlgError("Eigenvalues did not converge")
+
+    def loglik(self, hp):
+        """Marginal log-likelihood (gpcsd1d.py:113-128 / gpcsd2d.py:136-151); all-reduced over trial shards."""
+        st = self._factorize(hp, jitter=True, want_grad=False)
+        self._project(st)
+        res = st["sums"][:4].cpu().numpy()
+        self._check_info(st)
+        f = self.shard.det_fraction()
+        part = np.array([-0.5 * self.ntrials_total * f * res[2] - 0.5 * res[0]])
+        return float(self.shard.allreduce_sum(part, self.device)[0])
+
+    def loglik_grad(self, hp):
+        """(loglik, d loglik / d natural parameters) in the order R, ell(s), (ell_t, sigma2_t)..., sig2n[...]."""
+        nx, nt, ldn, N = self.nx, self.nt, self.ldn, self.ntrials
+        st = self._factorize(hp, jitter=True, want_grad=True)
+        Bm = self._project(st)
+        res = st["sums"]
+        stream = self._stream
+        f = self.shard.det_fraction()
+        ntot = float(self.ntrials_total)
+        vec = hp.vector_noise
+
+        # --- segment-weighted SYRKs over the trial batch
+        Mt = self._buf("Mt", nt, self.ldt)
+        Ms = self._buf("Ms", nx, self.ldx)
+        wst = self._buf("ws_syrk_t", max(L.query("gpcsd_wsyrk_ws_doubles", nt, nx, max(N, 1)), 2))
+        wss = self._buf("ws_syrk_s", max(L.query("gpcsd_wsyrk_ws_doubles", nx, nt, max(N, 1)), 2))
+        Ns = None
+        if N > 0:
+            self._call("gpcsd_wsyrk", nt, nx, N, self._p(Bm), ldn, nt * ldn, self._p(st["ls"]), self._p(Mt), self.ldt,
+                       self._p(wst), stream())
+            self._call("gpcsd_wsyrk", nx, nt, N, self._p(Bm), nt * ldn, ldn, self._p(st["lt"]), self._p(Ms), self.ldx,
+                       self._p(wss), stream())
+        else:
+            Mt.zero_()
+            Ms.zero_()
+        if vec:
+            Ns = self._buf("Ns", nx, self.ldx)
+            if N > 0:
+                self._call("gpcsd_wsyrk", nx, nt, N, self._p(Bm), nt * ldn, ldn, None, self._p(Ns), self.ldx,
+                           self._p(wss), stream())
+            else:
+                Ns.zero_()
+
+        # --- eigen-basis cores and rotation back:  G = Q X Q^T
+        Xs = self._buf("Xs", nx, self.ldx)
+        Xt = self._buf("Xt", nt, self.ldt)
+        self._call("gpcsd_grad_core", nx, self._p(Ms), self.ldx, self._p(Ns) if vec else None, self.ldx,
+                   self._p(st["ls"]), self._p(st["s"]) if vec else None, self._p(st["rowA"]), ntot, 1.0, f,
+                   self._p(Xs), self.ldx, stream())
+        self._call("gpcsd_grad_core", nt, self._p(Mt), self.ldt, None, 0, self._p(st["lt"]), None, self._p(st["colB"]),
+                   ntot, 1.0, f, self._p(Xt), self.ldt, stream())
+        Gs = self._rotate(Xs, st["QsT"], nx, self.ldx, "s")
+        Gt = self._rotate(Xt, st["QtT"], nt, self.ldt, "t")
+
+        # --- temporal hyperparameters: <Gt, dKt_k/d(ell_k, sigma2_k)>
+        ntc, kinds, ells, s2 = self._temporal_spec(hp.temporal)
+        wsk = self._buf("ws_ktgrad", L.query("gpcsd_kt_grad_ws_doubles", nt, ntc))
+        self._call("gpcsd_kt_grad", nt, self._p(self.t_dev), ntc, kinds, ells, s2, self._p(Gt), self.ldt, self._p(wsk),
+                   self._p(res, 8), stream())
+
+        # --- spatial hyperparameters.  With U = A Kg:  dL/dR = 2 <dA, Gs U>,  dL/dell_k = <A, (Gs A) dKg_k>
+        G = self.G
+        wsd = self._buf("ws_dot", L.query("gpcsd_dot_ws_doubles", nx * G))
+        GU = self._buf("GU", nx, G)
+        self.gemm(0, nx, G, nx, Gs, self.ldx, 0, st["U"], G, 0, GU, G, 0)
+        self._call("gpcsd_dot", nx, G, self._p(st["dA"]), G, self._p(GU), G, self._p(wsd), self._p(res, 4), stream())
+        GA = self._buf("GA", nx, G)
+        self.gemm(0, nx, G, nx, Gs, self.ldx, 0, st["A"], G, 0, GA, G, 0)
+        for k in range(len(hp.ells)):
+            dk = self._quad_kernels(hp, deriv_axis=k, tag="_d")
+            W = self._apply_quad_kernel(GA, nx, dk, "W")
+            self._call("gpcsd_dot", nx, G, self._p(st["A"]), G, self._p(W), G, self._p(wsd), self._p(res, 5 + k), stream())
+
+        # --- one device->host read, then the O(P) host assembly
+        pieces = [res[: 8 + 2 * ntc]]
+        if vec:
+            pieces += [st["rowC"], torch.diagonal(Ns[:, :nx])]
+        flat = torch.cat([p.reshape(-1) for p in pieces]).cpu().numpy()
+        self._check_info(st)
+        quad, bsq, slogD, srD = flat[0], flat[1], flat[2], flat[3]
+        ll = -0.5 * ntot * f * slogD - 0.5 * quad
+        g = [2.0 * flat[4]] + [flat[5 + k] for k in range(len(hp.ells))] + list(flat[8: 8 + 2 * ntc])
+        if vec:
+            off = 8 + 2 * ntc
+            rowC, dNs = flat[off: off + nx], flat[off + nx: off + 2 * nx]
+            g += list(-0.5 * ntot * f * rowC + 0.5 * dNs)
+        else:
+            g.append(-0.5 * ntot * f * srD + 0.5 * bsq)
+        out = self.shard.allreduce_sum(np.array([ll] + g, dtype=np.float64), self.device)
+        return float(out[0]), out[1:]
+
+    def _rotate(self, X, QT, n, ld, tag):
+        """G = Q X Q^T from QT = Q^T (row-major):  T1 = X QT ;  G = Q T1."""
+        Q = self._buf("Q_" + tag, n, ld)
+        self._call("gpcsd_transpose", n, n, self._p(QT), ld, self._p(Q), ld, self._stream())
+        T1 = self._buf("rot_tmp_" + tag, n, ld)
+        self.gemm(0, n, n, n, X, ld, 0, QT, ld, 0, T1, ld, 0)
+        Gm = self._buf("G_" + tag, n, ld)
+        self.gemm(0, n, n, n, Q, ld, 0, T1, ld, 0, Gm, ld, 0)
+        return Gm
+
+    def predict(self, hp, z, tstar, kind="csd", to_host=True):
+        """Posterior mean of CSD and/or LFP at (z, t*) per temporal component and summed
+        (gpcsd1d.py:248-293 / gpcsd2d.py:289-334), in Kronecker form:
+            out_k[:, :, r] = (Kc^T Qs) ((Qs^T Y_r Qt) / D) (Qt^T Kt*_k),   Kt*_k = Kt_k(t*, t)
+        No jitter on Ks (gpcsd1d.py:258).  Like the reference (mykron(..).T @ invy), requires len(t*) == len(t).
+        Returns {name: array (nz, nt*, ntrials_local)} for name in csd_pred, csd_pred_list[k], ..."""
+        nx, nt, ldn, N = self.nx, self.nt, self.ldn, self.ntrials
+        z = np.asarray(z, dtype=np.float64)
+        nz = z.shape[0]
+        ts = np.asarray(tstar, dtype=np.float64).reshape(-1)
+        if ts.shape[0] != nt:
+            raise ValueError("shapes (%d,%d) and (%d,%d) not aligned: dim 1 != dim 0"
+                             % (nz * nt, nx * ts.shape[0], nx * nt, self.ntrials_total))
+        st = self._factorize(hp, jitter=False, want_grad=False)
+        Bm = self._project(st)
+        Qs = self._buf("Q_s", nx, self.ldx)
+        Qt = self._buf("Q_t", nt, self.ldt)
+        self._call("gpcsd_transpose", nx, nx, self._p(st["QsT"]), self.ldx, self._p(Qs), self.ldx, self._stream())
+        self._call("gpcsd_transpose", nt, nt, self._p(st["QtT"]), self.ldt, self._p(Qt), self.ldt, self._stream())
+        ts_dev = self._dev(ts)
+        G = self.G
+        ldz = _even(nx)
+        results = {}
+        names = [n for n in ("csd", "lfp") if kind in ("both", n)]
+        if not names:
+            raise ValueError("type must be 'csd', 'lfp' or 'both'")
+        for name in names:
+            # KcT (nz x nx): transposed cross-covariance
+            KcT = self._buf("KcT", nz, ldz)
+            if name == "csd":
+                # Kphig^T = Kgz^T A^T, Kgz^T[z][g] (covariances.py:58-72 / 188-202)
+                KgzT = self._buf("KgzT", nz, G)
+                if self.dim == 1:
+                    zd = self._dev(z.reshape(-1))
+                    self._call("gpcsd_se_matrix", nz, self._p(zd), G, self._p(self.gl_x), float(hp.ells[0]), 1.0, 0,
+                               self._p(KgzT), G, self._stream())
+                else:
+                    zd = self._dev(z.reshape(nz, 2))
+                    self._call("gpcsd_se_grid_to_pts", self.G1, self.G2, self._p(self.gl_x1), self._p(self.gl_x2), nz,
+                               self._p(zd), float(hp.ells[0]), float(hp.ells[1]), self._p(KgzT), G, self._stream())
+                self.gemm(1, nz, nx, G, KgzT, G, 0, st["A"], G, 0, KcT, ldz, 0)
+            else:
+                # Kphi(xp=z)^T = A_z U^T   (covariances.py:91-95 / 224-231)
+                zd = self._dev(z.reshape(-1) if self.dim == 1 else z.reshape(nz, 2))
+                Az, _ = self._fwd_weights(zd, nz, hp, False, "z")
+                self.gemm(1, nz, nx, G, Az, G, 0, st["U"], G, 0, KcT, ldz, 0)
+            Ps = self._buf("Ps", nz, ldz)
+            self.gemm(0, nz, nx, nx, KcT, ldz, 0, Qs, self.ldx, 0, Ps, ldz, 0)
+            V = self._buf("V", nz, nt, ldn)
+            self.gemm(0, nz, nt * ldn, nx, Ps, ldz, 0, Bm, nt * ldn, 0, V, nt * ldn, 0)
+            parts = []
+            for k, (knd, ell, s2) in enumerate(hp.temporal):
+                ntc1, kinds, ells, s2s = self._temporal_spec([(knd, ell, s2)])
+                KtsT = self._buf("KtsT", nt, self.ldt)      # KtsT[j][j'] = k(t_j - t*_j') = Kt*_k[j'][j]
+                self._call("gpcsd_kt_build", nt, self._p(self.t_dev), nt, self._p(ts_dev), ntc1, kinds, ells, s2s,
+                           self._p(KtsT), self.ldt, self._stream())
+                Tk = self._buf("Tk", nt, self.ldt)           # Tk = Kt*_k^T Qt
+                self.gemm(0, nt, nt, nt, KtsT, self.ldt, 0, Qt, self.ldt, 0, Tk, self.ldt, 0)
+                out = torch.empty((nz, nt, ldn), dtype=F64, device=self.device)
+                self.gemm(0, nt, max(N, 1), nt, Tk, self.ldt, 0, V, ldn, nt * ldn, out, ldn, nt * ldn, batch=nz)
+                parts.append(out)
+            tot = torch.empty((nz, nt, ldn), dtype=F64, device=self.device)
+            ptrs = (ctypes.c_void_p * len(parts))(*[p.data_ptr() for p in parts])
+            self._call("gpcsd_sum_arrays", nz * nt * ldn, len(parts), ptrs, self._p(tot), self._stream())
+            results[name + "_pred"] = tot
+            results[name + "_pred_list"] = parts
+        self._check_info(st)
+        if not to_host:
+            return {k: ([p[:, :, :N] for p in v] if isinstance(v, list) else v[:, :, :N]) for k, v in results.items()}
+        host = {}
+        for k, v in results.items():
+            host[k] = [self._to_host(p, N) for p in v] if isinstance(v, list) else self._to_host(v, N)
+        return host
+
+    def _to_host(self, dev, N):
+        return np.ascontiguousarray(dev[:, :, :N].cpu().numpy())

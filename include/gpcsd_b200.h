@@ -1,0 +1,167 @@
+/*
+ * gpcsd_b200.h -- C ABI of the B200-native GPCSD hot path (libgpcsd_b200.so).
+ *
+ * The reference (natalieklein/gpcsd) is pure Python with no FFI; its boundary for this path is the
+ * Python object API (GPCSD1D/GPCSD2D.loglik / fit.obj_fun / predict and the covariance helpers).  The
+ * entry points below are what a ctypes binding inside those methods would call; each one names the
+ * reference code it replaces (paths relative to src/gpcsd/ of the reference).  INTEGRATION.md shows
+ * the binding.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes only.  All matrices are FP64, ROW-MAJOR, with an explicit
+ *    leading dimension `ld*` counted in doubles.  Device pointers unless the parameter name starts
+ *    with `h_` (host).  Leading dimensions and batch strides of GEMM operands must be EVEN (16-byte
+ *    rows) and base pointers 16-byte aligned; the Python host layer allocates that way.
+ *  - `stream` is a cudaStream_t passed as void*; every call is asynchronous on that stream and
+ *    performs no hidden allocation (workspaces are caller-provided; sizes from the *_ws_* queries).
+ *  - Return value: 0 on success, non-zero on error; gpcsd_last_error() returns a thread-local
+ *    message.  No C++ exception crosses the ABI.
+ *  - LFP layout (reference: `self.lfp`, shape (nx, nt, ntrials), C order => trial index fastest,
+ *    gpcsd1d.py:125,255): device array Y[nx][nt][ldn], ldn >= ntrials, ldn even.
+ */
+#ifndef GPCSD_B200_H
+#define GPCSD_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPCSD_B200_ABI_VERSION 1
+
+#define GPCSD_KIND_SE 0     /* GPCSDTemporalCovSE      covariances.py:240-271 */
+#define GPCSD_KIND_MATERN 1 /* GPCSDTemporalCovMatern  covariances.py:274-305 */
+
+int gpcsd_abi_version(void);
+const char* gpcsd_last_error(void);
+/* number of SMs of the current device (grid sizing is derived from it) */
+int gpcsd_num_sms(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * FP64 tensor-core (DMMA) strided-batched GEMM:  C_b = A_b (M x K) * op(B_b),  b = 0..batch-1
+ *   transB == 0 : B_b is K x N row-major (N contiguous)       -- replaces np.dot / np.matmul
+ *   transB == 1 : B_b is N x K row-major (K contiguous), C = A B^T
+ * Replaces every dense product on the path: Qs^T Y_r / (.) Qt of loglik (gpcsd1d.py:125,
+ * gpcsd2d.py:148), A Kg / (A Kg) A^T of compKphi (covariances.py:90,95,223,231), the cross-covariance
+ * products (covariances.py:71,201) and mykron(..).T @ invy of predict (gpcsd1d.py:279,283).
+ * ------------------------------------------------------------------------------------------- */
+int gpcsd_dgemm(int transB, int M, int N, int K,
+                const double* A, long lda, long strideA,
+                const double* B, long ldb, long strideB,
+                double* C, long ldc, long strideC,
+                int batch, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused Kronecker projection + quadratic form (hot loop gpcsd1d.py:124-126 / gpcsd2d.py:147-149):
+ * for every spatial eigen-index i (batch):  A_i = Qt^T Z_i  (nt x ntrials), Z = Qs^T Y already formed
+ * by gpcsd_dgemm;  epilogue  B_i = A_i * rD[i][:],  quad += sum A_i .* B_i,  bsq += sum B_i .* B_i.
+ *   QtT    : nt x nt, row-major Q^T  (== column-major eigenvector matrix as cuSOLVER returns it)
+ *   Z      : [nx][nt][ldn]            rD : [nx][ldrd] reciprocal of D_ij = ls_i lt_j + sig2n(_i)
+ *   Bout   : [nx][nt][ldn]  (= (Qs^T Y_r Qt) / D for all trials; input of the gradient and of predict)
+ *   partials: workspace of gpcsd_project_quad_ws_doubles(...) doubles; out2[0] = quad, out2[1] = bsq
+ * ------------------------------------------------------------------------------------------- */
+long gpcsd_project_quad_ws_doubles(int nx, int nt, int ntrials);
+int gpcsd_project_quad(int nx, int nt, int ntrials,
+                       const double* QtT, long ldq,
+                       const double* Z, long ldn,
+                       const double* rD, long ldrd,
+                       double* Bout, double* partials, double* out2, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Segment-weighted symmetric rank-k update (gradient of the quadratic form; replaces the autograd
+ * tape of gpcsd1d.py:211 / gpcsd2d.py:250 over the trial loop):
+ *     C (M x M) = sum_{seg=0}^{nseg-1} w[seg] * X_seg X_seg^T,   X_seg[m][k] = X[m*row_stride + seg*seg_stride + k],
+ *     k = 0..seglen-1.   w == NULL means all ones.
+ *   Mt = sum_i ls_i B_i^T-contraction : M = nt, row_stride = ldn,     nseg = nx, seg_stride = nt*ldn, w = ls
+ *   Ms = sum_j lt_j (...)             : M = nx, row_stride = nt*ldn,  nseg = nt, seg_stride = ldn,    w = lt
+ *   Ns = sum_j (...)                  : as Ms with w = NULL (per-electrode-noise mode only)
+ * Split-K over (seg, k) with per-CTA partial tiles in `ws` and a fixed-order second pass, so the result
+ * is deterministic (no atomics).  Both triangles of C are written.
+ * ------------------------------------------------------------------------------------------- */
+long gpcsd_wsyrk_ws_doubles(int M, int nseg, int seglen);
+int gpcsd_wsyrk(int M, int nseg, int seglen,
+                const double* X, long row_stride, long seg_stride,
+                const double* w, double* C, long ldc, double* ws, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Eigendecomposition of the small factors (np.linalg.eigh in comp_eig_D, utility_functions.py:58-59).
+ * cuSOLVER syevd on a copy; returns eigenvalues ascending in W and Q^T row-major (== column-major Q)
+ * in QT (n x n, leading dimension ldq).  `info` is a device int (0 = converged).
+ * ------------------------------------------------------------------------------------------- */
+long gpcsd_eigh_ws_doubles(int n, long ldq);
+int gpcsd_eigh(int n, const double* K, long ldk, double* QT, long ldq, double* W,
+               double* ws, long ws_doubles, int* info, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * D and its reductions (utility_functions.py:54-63; gpcsd1d.py:122):
+ *   D_ij = ls_i * lt_j + s_i  (s = sig2n[0] if n_sig2n == 1 else sig2n[i], i = ASCENDING spatial eigen-index)
+ *   rD[i][j] = 1 / D_ij ;  sums[0] = sum log D ;  sums[1] = sum 1/D
+ *   rowA[i] = sum_j lt_j / D_ij ; rowC[i] = sum_j 1 / D_ij ; rowL[i] = sum_j log D_ij ; colB[j] = sum_i ls_i / D_ij
+ * ------------------------------------------------------------------------------------------- */
+int gpcsd_eig_D(int nx, int nt, const double* ls, const double* lt, const double* sig2n, int n_sig2n,
+                double* rD, long ldrd, double* sums2, double* rowA, double* rowC, double* rowL, double* colB,
+                void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Forward-model quadrature weights  A = gl_w (.) b_fwd  and dA/dR.
+ *   1-D: b_fwd_1d(gl_x - x, R) forward_models.py:9-17 inside compKphi_1d covariances.py:86-88
+ *   2-D: b_fwd_2d(.., R, eps, w=delta_w) forward_models.py:42-54 inside compKphi_2d covariances.py:220-221;
+ *        quadrature node g = (g1, g2) of the x1-major product grid (utility_functions.py:22), g = g1*ngl2 + g2
+ * A, dA: [npts][ldg]; dA may be NULL.
+ * ------------------------------------------------------------------------------------------- */
+int gpcsd_fwd_weights_1d(int npts, const double* x, int G, const double* gl_x, const double* gl_w,
+                         double R, double* A, double* dA, long ldg, void* stream);
+int gpcsd_fwd_weights_2d(int npts, const double* pts /* [npts][2] */, int ngl1, int ngl2,
+                         const double* gl_x1, const double* gl_w1, const double* gl_x2, const double* gl_w2,
+                         double R, double eps, double* A, double* dA, long ldg, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Squared-exponential factor matrices:  out[i][j] = scale * exp(-0.5 ((a_i - b_j)/ell)^2)  (deriv == 0)
+ *                                        ... * (a_i - b_j)^2 / ell^3                        (deriv == 1)
+ * CSD kernel on the quadrature grid (covariances.py:89, 216 -- the 2-D kernel is the Kronecker product
+ * of two such factors on the product grid), CSD-CSD kernel (covariances.py:56,186), gl-to-z kernels of
+ * the cross-covariances (covariances.py:67,198).
+ * ------------------------------------------------------------------------------------------- */
+int gpcsd_se_matrix(int na, const double* a, int nb, const double* b, double ell, double scale, int deriv,
+                    double* out, long ld, void* stream);
+/* 2-D gl-to-z kernel, stored transposed: out[z][g] = exp(-.5((g1-z1)/ell1)^2) * exp(-.5((g2-z2)/ell2)^2),
+ * g = g1*ngl2 + g2  (covariances.py:198; ld >= ngl1*ngl2) */
+int gpcsd_se_grid_to_pts(int ngl1, int ngl2, const double* gl_x1, const double* gl_x2,
+                         int nz, const double* z /* [nz][2] */, double ell1, double ell2,
+                         double* out, long ld, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Temporal covariance  Kt[i][j] = sum_k sigma2_k f_k(t_i - tp_j)  (compute_Kt covariances.py:257-271,
+ * 291-305 summed as in gpcsd1d.py:118-120).  h_kind/h_ell/h_sigma2 are HOST arrays of length ntc (<= 8).
+ * ------------------------------------------------------------------------------------------- */
+int gpcsd_kt_build(int nt_rows, const double* t, int nt_cols, const double* tp, int ntc,
+                   const int* h_kind, const double* h_ell, const double* h_sigma2,
+                   double* Kt, long ld, void* stream);
+/* out[2k] = <G, dKt_k/d ell_k>, out[2k+1] = <G, dKt_k/d sigma2_k>;  G: nt x nt (ldg);
+ * ws: gpcsd_kt_grad_ws_doubles(nt, ntc) doubles. */
+long gpcsd_kt_grad_ws_doubles(int nt, int ntc);
+int gpcsd_kt_grad(int nt, const double* t, int ntc, const int* h_kind, const double* h_ell,
+                  const double* h_sigma2, const double* G, long ldg, double* ws, double* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Eigen-basis gradient cores (closed form of the reverse pass):
+ *   X[i][i'] = 0.5*M[i][i'] (+ 0.5*(s_i-s_i')/(l_i-l_i')*Nmat[i][i'] if Nmat != NULL), i != i'
+ *   X[i][i]  = -0.5*ntrials_total*rowsum[i] + 0.5*M[i][i]
+ * `scale_data` multiplies the data terms (M, Nmat) and `scale_det` the log-det term, so that trial-sharded
+ * ranks can form partial gradients (data terms local; log-det term once).
+ * ------------------------------------------------------------------------------------------- */
+int gpcsd_grad_core(int n, const double* Mmat, long ldm, const double* Nmat, long ldnm,
+                    const double* lam, const double* s, const double* rowsum, double ntrials_total,
+                    double scale_data, double scale_det, double* X, long ldx, void* stream);
+
+/* small helpers (all row-major, FP64) */
+int gpcsd_add_diag(int n, double* K, long ld, double v, void* stream);               /* + JITTER*I  gpcsd1d.py:117 */
+int gpcsd_transpose(int rows, int cols, const double* in, long ldi, double* out, long ldo, void* stream);
+long gpcsd_dot_ws_doubles(long n);
+int gpcsd_dot(int rows, int cols, const double* X, long ldx, const double* Y, long ldy, double* ws, double* out, void* stream);
+int gpcsd_sum_arrays(long n, int narr, const double* const* h_in, double* out, void* stream);   /* csd += csd_tmp gpcsd1d.py:281 */
+int gpcsd_sum_vec(long n, const double* in, double* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPCSD_B200_H */

@@ -228,26 +228,33 @@ class Model:
         return K
 
 
-def comp_eig_D(Ks, Kt, sig2n):
+def eigh_driver(driver):
+    """np.linalg.eigh stand-in using another LAPACK driver ('ev', 'evd', 'evr', 'evx'): used by tests to
+    measure the reference formula's own solver-to-solver spread."""
+    import scipy.linalg
+    return lambda K: scipy.linalg.eigh(K, driver=driver)
+
+
+def comp_eig_D(Ks, Kt, sig2n, eigh=np.linalg.eigh):
     """utility_functions.py:44-64 -- two eigh (ascending), D[i*nt+j] = ls_i*lt_j + sig2n(_i)."""
     nx, nt = Ks.shape[0], Kt.shape[0]
     if np.isscalar(sig2n) or np.ndim(sig2n) == 0:
         nvec = float(sig2n) * np.ones(nx * nt)
     else:
         nvec = np.repeat(np.asarray(sig2n, dtype=np.float64), nt)      # util:57: by spatial EIGEN index
-    lt, Qt = np.linalg.eigh(Kt)
-    ls, Qs = np.linalg.eigh(Ks)
+    lt, Qt = eigh(Kt)
+    ls, Qs = eigh(Ks)
     D = np.repeat(ls, nt) * np.tile(lt, nx) + nvec
     return Qs, Qt, D, ls, lt
 
 
-def loglik(model: Model, lfp):
+def loglik(model: Model, lfp, eigh=np.linalg.eigh):
     """gpcsd1d.py:113-128 / gpcsd2d.py:136-151 -- literal restatement, Python trial loop included."""
     lfp = np.atleast_3d(lfp)
     nx, nt, ntrials = lfp.shape
     Ks = model.Ks(jitter=True)
     Kt = model.Kt()
-    Qs, Qt, D, _, _ = comp_eig_D(Ks, Kt, model.sig2n)
+    Qs, Qt, D, _, _ = comp_eig_D(Ks, Kt, model.sig2n, eigh)
     logdet = -0.5 * ntrials * np.sum(np.log(D))
     quad = 0.0
     for r in range(ntrials):
@@ -363,7 +370,7 @@ def _dKs_contract(model: Model, G):
     return dR, [np.sum(H * dk) for dk in dKg]
 
 
-def loglik_and_grad(model: Model, lfp):
+def loglik_and_grad(model: Model, lfp, eigh=np.linalg.eigh):
     """loglik and d loglik / d(R, ells..., (ell_t, sigma2_t)..., sig2n[...]) in natural units.
 
     Derivation: with A_r = Qs^T Y_r Qt, D_ij = ls_i lt_j + s_i, B_r = A_r / D,
@@ -378,7 +385,7 @@ def loglik_and_grad(model: Model, lfp):
     nx, nt, N = lfp.shape
     Ks = model.Ks(jitter=True)
     Kt = model.Kt()
-    Qs, Qt, Dv, ls, lt = comp_eig_D(Ks, Kt, model.sig2n)
+    Qs, Qt, Dv, ls, lt = comp_eig_D(Ks, Kt, model.sig2n, eigh)
     D = Dv.reshape(nx, nt)
     vec_noise = not (np.isscalar(model.sig2n) or np.ndim(model.sig2n) == 0)
     s = np.asarray(model.sig2n, dtype=np.float64) if vec_noise else np.full(nx, float(model.sig2n))
@@ -476,7 +483,7 @@ def predict_dense(model: Model, lfp, z, tstar, kind="csd"):
     return out
 
 
-def predict_kron(model: Model, lfp, z, tstar, kind="csd"):
+def predict_kron(model: Model, lfp, z, tstar, kind="csd", eigh=np.linalg.eigh):
     """Same posterior mean in Kronecker form (never forms an (nx nt)^2 matrix):
     out_k[:, :, r] = (Kc^T Qs) ((Qs^T Y_r Qt) / D) (Qt^T Kt*_k)   with Kt*_k = Kt_k(t*, t) applied
     from the right exactly as ``mykron(Kc, Kt*).T @ invy`` does (needs len(t*) == len(t))."""
@@ -484,7 +491,7 @@ def predict_kron(model: Model, lfp, z, tstar, kind="csd"):
     nx, nt, N = lfp.shape
     if tstar.shape[0] != nt:
         raise ValueError("shapes (%d,%d) and (%d,%d) not aligned" % (z.shape[0] * nt, nx * tstar.shape[0], nx * nt, N))
-    Qs, Qt, D, _, _ = comp_eig_D(model.Ks(jitter=False), model.Kt(), model.sig2n)
+    Qs, Qt, D, _, _ = comp_eig_D(model.Ks(jitter=False), model.Kt(), model.sig2n, eigh)
     A = np.einsum("ia,ijr->ajr", Qs, lfp, optimize=True)
     A = np.einsum("ajr,jb->abr", A, Qt, optimize=True)
     B = A / D.reshape(nx, nt)[:, :, None]

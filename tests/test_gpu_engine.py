@@ -1,0 +1,162 @@
+"""End-to-end parity of the CUDA engine against the oracle and the reference-generated golden vectors.
+
+Tolerances (BASELINE.json north_star): relative 1e-9 on log-likelihood and gradient, 1e-8 on predicted
+CSD/LFP.  Inputs are model-matched synthetic draws."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import engine_from_oracle, relerr
+
+pytestmark = pytest.mark.gpu
+
+TOL_LL = 1e-9
+TOL_GRAD = 1e-9
+TOL_PRED = 1e-8
+
+
+def solver_spread(fn):
+    """Spread of the REFERENCE FORMULA's own result when only the LAPACK eigh driver changes
+    (syevd vs syevr vs syev): the floor below which "parity" is not defined."""
+    from oracle import gpcsd_oracle as O
+    vals = [np.atleast_1d(fn(O.eigh_driver(d))) for d in ("evd", "evr", "ev")]
+    ref = np.abs(vals[0])
+    return max(float(np.max(np.abs(v - vals[0]) / ref)) for v in vals[1:])
+
+
+def grad_tol(om, lfp):
+    from oracle import gpcsd_oracle as O
+    return max(TOL_GRAD, 10.0 * solver_spread(lambda e: O.loglik_and_grad(om, lfp, eigh=e)[1]))
+
+
+def _model_from_golden_1d(g):
+    from oracle import gpcsd_oracle as O
+    sp = O.Spatial1D(g["x"], float(g["a"]), float(g["b"]), int(g["ngl"]))
+    temporal = [(int(k), float(e), float(s)) for k, e, s in zip(g["t_kind"], g["t_ell"], g["t_sigma2"])]
+    sig = g["sig2n"]
+    sig = float(sig) if sig.ndim == 0 else np.array(sig)
+    return O.Model(1, sp, g["t"], float(g["R"]), (float(g["ell"]),), temporal, sig)
+
+
+def _model_from_golden_2d(g):
+    from oracle import gpcsd_oracle as O
+    sp = O.Spatial2D(g["x"], float(g["a1"]), float(g["b1"]), float(g["a2"]), float(g["b2"]), int(g["ngl1"]), int(g["ngl2"]))
+    temporal = [(int(k), float(e), float(s)) for k, e, s in zip(g["t_kind"], g["t_ell"], g["t_sigma2"])]
+    return O.Model(2, sp, g["t"], float(g["R"]), (float(g["ell1"]), float(g["ell2"])), temporal, float(g["sig2n"]), float(g["eps"]))
+
+
+@pytest.mark.parametrize("name", ["gpcsd1d_cfg1", "gpcsd1d_lownoise", "gpcsd1d_vecnoise"])
+def test_loglik_matches_reference_golden_1d(cuda_lib, golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    om = _model_from_golden_1d(g)
+    eng, hp = engine_from_oracle(om, g["lfp"])
+    ll = eng.loglik(hp)
+    assert abs(ll - float(g["loglik"])) / abs(float(g["loglik"])) < TOL_LL
+
+
+def test_loglik_matches_reference_golden_2d(cuda_lib, golden_dir):
+    g = np.load(os.path.join(golden_dir, "gpcsd2d_small.npz"))
+    om = _model_from_golden_2d(g)
+    eng, hp = engine_from_oracle(om, g["lfp"])
+    ll = eng.loglik(hp)
+    assert abs(ll - float(g["loglik"])) / abs(float(g["loglik"])) < TOL_LL
+
+
+@pytest.mark.parametrize("name", ["gpcsd1d_cfg1", "gpcsd1d_lownoise"])
+def test_grad_matches_oracle_and_reference_fd_1d(cuda_lib, golden_dir, name):
+    from oracle import gpcsd_oracle as O
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    om = _model_from_golden_1d(g)
+    eng, hp = engine_from_oracle(om, g["lfp"])
+    ll, grad = eng.loglik_grad(hp)
+    ll_o, grad_o = O.loglik_and_grad(om, g["lfp"])
+    assert abs(ll - ll_o) / abs(ll_o) < TOL_LL
+    # 1e-9, or 10x the reference formula's own LAPACK-driver spread where that is larger (the sig2n
+    # component at sig2n = 1e-4 cancels two 4e7-sized terms down to 3e3)
+    assert np.max(np.abs(grad - grad_o) / np.abs(grad_o)) < grad_tol(om, g["lfp"])
+    # FD of the reference's own loglik: limited by FD truncation/roundoff, not by us
+    fd = g["grad_fd_natural"]
+    assert np.max(np.abs(grad - fd) / np.maximum(np.abs(fd), 1e-3 * np.max(np.abs(fd)))) < 1e-4
+
+
+def test_grad_at_perturbed_point_vs_torch_autograd(cuda_lib, golden_dir):
+    """Gradient evaluation point theta_true + 0.1 N(0,1); checker = torch autograd through eigh (the
+    published reverse-mode algorithm the reference's autograd.grad implements)."""
+    from oracle import gpcsd_oracle as O
+    from oracle.oracle_torch import loglik_and_grad_torch
+    g = np.load(os.path.join(golden_dir, "gpcsd1d_cfg1.npz"))
+    om = _model_from_golden_1d(g)
+    v = g["pert_natural"]
+    om2 = O.Model(1, om.spatial, om.t, float(v[0]), (float(v[1]),), [(0, float(v[2]), float(v[3])), (1, float(v[4]), float(v[5]))], float(v[6]))
+    eng, hp = engine_from_oracle(om2, g["lfp"])
+    ll, grad = eng.loglik_grad(hp)
+    assert abs(ll - float(g["pert_loglik"])) / abs(float(g["pert_loglik"])) < TOL_LL
+    ll_t, grad_t = loglik_and_grad_torch(om2, g["lfp"])
+    assert np.max(np.abs(grad - grad_t) / np.abs(grad_t)) < TOL_GRAD
+
+
+def test_grad_2d(cuda_lib, golden_dir):
+    from oracle import gpcsd_oracle as O
+    g = np.load(os.path.join(golden_dir, "gpcsd2d_small.npz"))
+    om = _model_from_golden_2d(g)
+    eng, hp = engine_from_oracle(om, g["lfp"])
+    ll, grad = eng.loglik_grad(hp)
+    ll_o, grad_o = O.loglik_and_grad(om, g["lfp"])
+    assert abs(ll - ll_o) / abs(ll_o) < TOL_LL
+    assert np.max(np.abs(grad - grad_o) / np.abs(grad_o)) < TOL_GRAD
+
+
+def test_grad_vector_noise_kernel_level(cuda_lib, golden_dir):
+    """Per-electrode noise enters by spatial EIGEN index (util:54-57) so loglik depends on eigenvector
+    identity; parity is checked against the oracle's closed form (same formula, numpy eigh)."""
+    from oracle import gpcsd_oracle as O
+    g = np.load(os.path.join(golden_dir, "gpcsd1d_vecnoise.npz"))
+    om = _model_from_golden_1d(g)
+    eng, hp = engine_from_oracle(om, g["lfp"])
+    ll, grad = eng.loglik_grad(hp)
+    ll_o, grad_o = O.loglik_and_grad(om, g["lfp"])
+    assert len(grad) == 6 + 24
+    assert abs(ll - ll_o) / abs(ll_o) < 1e-8
+    # eigenvector-identity conditioning: looser gate, stated
+    assert np.max(np.abs(grad - grad_o) / np.maximum(np.abs(grad_o), 1e-6 * np.max(np.abs(grad_o)))) < 1e-4
+
+
+@pytest.mark.parametrize("name,is2d", [("gpcsd1d_cfg1", False), ("gpcsd1d_lownoise", False), ("gpcsd2d_small", True)])
+def test_predict_matches_oracle_and_golden(cuda_lib, golden_dir, name, is2d):
+    from oracle import gpcsd_oracle as O
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    om = _model_from_golden_2d(g) if is2d else _model_from_golden_1d(g)
+    eng, hp = engine_from_oracle(om, g["lfp"])
+    out = eng.predict(hp, g["z"], g["t"], "both")
+    ref = O.predict_kron(om, g["lfp"], g["z"], g["t"], "both")
+    npred = g["csd_pred"].shape[2]
+    for key in ("csd_pred", "lfp_pred"):
+        assert out[key].shape == ref[key].shape
+        assert relerr(out[key], ref[key]) < TOL_PRED
+        for k in range(2):
+            assert relerr(out[key + "_list"][k], ref[key + "_list"][k]) < TOL_PRED
+        # reference's dense (nx nt)^2 inverse: its own conditioning limits agreement
+        assert relerr(out[key][:, :, :npred], g[key]) < 1e-6
+        assert relerr(out[key + "_list"][1][:, :, :npred], g[key + "_1"]) < 1e-6
+
+
+def test_predict_requires_matching_time_grid(cuda_lib, golden_dir):
+    g = np.load(os.path.join(golden_dir, "gpcsd1d_lownoise.npz"))
+    om = _model_from_golden_1d(g)
+    eng, hp = engine_from_oracle(om, g["lfp"])
+    with pytest.raises(ValueError):
+        eng.predict(hp, g["z"], g["t"][:-1], "csd")
+
+
+def test_single_trial_and_ragged_trial_counts(cuda_lib):
+    from oracle import gpcsd_oracle as O, synth
+    x, t = synth.geometry_1d(24, 33)
+    om = synth.model_1d(x, t)
+    for N in (1, 7, 129):
+        lfp = synth.matched_lfp(om, N, 50 + N)
+        eng, hp = engine_from_oracle(om, lfp)
+        ll, grad = eng.loglik_grad(hp)
+        ll_o, grad_o = O.loglik_and_grad(om, lfp)
+        assert abs(ll - ll_o) / abs(ll_o) < TOL_LL
+        assert np.max(np.abs(grad - grad_o) / np.abs(grad_o)) < TOL_GRAD

@@ -1,0 +1,263 @@
+"""Kernel-level parity of the C-ABI entry points against numpy / the oracle pieces (-m gpu)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import relerr
+
+pytestmark = pytest.mark.gpu
+F64 = torch.float64
+
+
+def _ld(n):
+    return (n + 1) // 2 * 2
+
+
+def _dev(a, ld=None):
+    """row-major matrix -> device buffer with even leading dimension; returns (tensor, ld)."""
+    a = np.atleast_2d(np.asarray(a, dtype=np.float64))
+    ld = _ld(a.shape[1]) if ld is None else ld
+    buf = torch.zeros((a.shape[0], ld), dtype=F64, device="cuda")
+    buf[:, : a.shape[1]] = torch.from_numpy(a).cuda()
+    return buf, ld
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+@pytest.mark.parametrize("M,N,K,batch", [(128, 128, 16, 1), (500, 2000, 500, 3), (24, 1003, 24, 1), (7, 50, 5, 2),
+                                          (33, 65, 17, 2), (384, 777, 384, 1), (130, 258, 131, 1), (1, 9, 300, 1)])
+@pytest.mark.parametrize("transB", [0, 1])
+def test_dgemm(cuda_lib, M, N, K, batch, transB):
+    from gpcsd_b200 import _lib as L
+    rng = np.random.default_rng(M * 7 + N + K + transB)
+    lda, ldb, ldc = _ld(K), _ld(K if transB else N), _ld(N)
+    A = torch.zeros((batch, M, lda), dtype=F64, device="cuda")
+    B = torch.zeros((batch, N if transB else K, ldb), dtype=F64, device="cuda")
+    C = torch.full((batch, M, ldc), 7.0, dtype=F64, device="cuda")
+    Ah = rng.standard_normal((batch, M, K))
+    Bh = rng.standard_normal((batch, N, K) if transB else (batch, K, N))
+    A[:, :, :K] = torch.from_numpy(Ah).cuda()
+    B[:, :, : Bh.shape[2]] = torch.from_numpy(Bh).cuda()
+    L.call("gpcsd_dgemm", transB, M, N, K, A.data_ptr(), lda, M * lda, B.data_ptr(), ldb, B.shape[1] * ldb,
+           C.data_ptr(), ldc, M * ldc, batch, _stream())
+    torch.cuda.synchronize()
+    ref = np.einsum("bmk,bnk->bmn", Ah, Bh) if transB else np.einsum("bmk,bkn->bmn", Ah, Bh)
+    got = C[:, :, :N].cpu().numpy()
+    assert relerr(got, ref) < 1e-13
+    if ldc > N:  # padding column untouched
+        assert torch.all(C[:, :, N:] == 7.0)
+
+
+def test_dgemm_broadcast_A_and_strided_view(cuda_lib):
+    """strideA == 0 (shared small matrix) and B viewed as [nx][nt*ldn] exactly as the engine uses it."""
+    from gpcsd_b200 import _lib as L
+    rng = np.random.default_rng(3)
+    nx, nt, ldn = 5, 37, 24
+    Q = rng.standard_normal((nt, nt))
+    Y = rng.standard_normal((nx, nt, ldn))
+    Qd, ldq = _dev(Q)
+    Yd = torch.from_numpy(Y).cuda()
+    Cd = torch.zeros_like(Yd)
+    L.call("gpcsd_dgemm", 0, nt, ldn, nt, Qd.data_ptr(), ldq, 0, Yd.data_ptr(), ldn, nt * ldn, Cd.data_ptr(), ldn,
+           nt * ldn, nx, _stream())
+    assert relerr(Cd.cpu().numpy(), np.einsum("ab,ibr->iar", Q, Y)) < 1e-13
+
+
+@pytest.mark.parametrize("nx,nt,N", [(24, 50, 50), (6, 130, 257), (3, 20, 1), (40, 33, 17)])
+def test_project_quad(cuda_lib, nx, nt, N):
+    from gpcsd_b200 import _lib as L
+    rng = np.random.default_rng(nx + nt + N)
+    ldn = (N + 7) // 8 * 8
+    QtT = rng.standard_normal((nt, nt))
+    Z = np.zeros((nx, nt, ldn))
+    Z[:, :, :N] = rng.standard_normal((nx, nt, N))
+    rD = rng.uniform(0.5, 2.0, (nx, nt))
+    Qd, ldq = _dev(QtT)
+    rDd, ldrd = _dev(rD)
+    Zd = torch.from_numpy(Z).cuda()
+    Bd = torch.zeros_like(Zd)
+    part = torch.zeros(L.query("gpcsd_project_quad_ws_doubles", nx, nt, N), dtype=F64, device="cuda")
+    out2 = torch.zeros(2, dtype=F64, device="cuda")
+    L.call("gpcsd_project_quad", nx, nt, N, Qd.data_ptr(), ldq, Zd.data_ptr(), ldn, rDd.data_ptr(), ldrd,
+           Bd.data_ptr(), part.data_ptr(), out2.data_ptr(), _stream())
+    A = np.einsum("ab,ibr->iar", QtT, Z[:, :, :N])
+    Bm = A * rD[:, :, None]
+    assert relerr(Bd[:, :, :N].cpu().numpy(), Bm) < 1e-13
+    o = out2.cpu().numpy()
+    assert abs(o[0] - np.sum(A * Bm)) / np.sum(A * Bm) < 1e-13
+    assert abs(o[1] - np.sum(Bm * Bm)) / np.sum(Bm * Bm) < 1e-13
+
+
+@pytest.mark.parametrize("nx,nt,N", [(24, 50, 50), (5, 140, 300), (130, 9, 33), (3, 3, 1)])
+@pytest.mark.parametrize("weighted", [True, False])
+def test_wsyrk_both_orientations(cuda_lib, nx, nt, N, weighted):
+    from gpcsd_b200 import _lib as L
+    rng = np.random.default_rng(nx * 3 + nt + N)
+    ldn = (N + 7) // 8 * 8
+    Bm = np.zeros((nx, nt, ldn))
+    Bm[:, :, :N] = rng.standard_normal((nx, nt, N))
+    Bm[:, :, N:] = 99.0  # garbage in the padding must be ignored
+    ls, lt = rng.standard_normal(nx), rng.standard_normal(nt)
+    Bd = torch.from_numpy(Bm).cuda()
+    lsd, ltd = torch.from_numpy(ls).cuda(), torch.from_numpy(lt).cuda()
+    B = Bm[:, :, :N]
+    # Mt: M = nt, segments = nx
+    ldt = _ld(nt)
+    Mt = torch.zeros((nt, ldt), dtype=F64, device="cuda")
+    ws = torch.zeros(L.query("gpcsd_wsyrk_ws_doubles", nt, nx, N), dtype=F64, device="cuda")
+    L.call("gpcsd_wsyrk", nt, nx, N, Bd.data_ptr(), ldn, nt * ldn, lsd.data_ptr() if weighted else None, Mt.data_ptr(),
+           ldt, ws.data_ptr(), _stream())
+    ref = np.einsum("ajr,a,akr->jk", B, ls if weighted else np.ones(nx), B)
+    assert relerr(Mt[:, :nt].cpu().numpy(), ref) < 1e-12
+    # Ms: M = nx, segments = nt
+    ldx = _ld(nx)
+    Ms = torch.zeros((nx, ldx), dtype=F64, device="cuda")
+    ws = torch.zeros(L.query("gpcsd_wsyrk_ws_doubles", nx, nt, N), dtype=F64, device="cuda")
+    L.call("gpcsd_wsyrk", nx, nt, N, Bd.data_ptr(), nt * ldn, ldn, ltd.data_ptr() if weighted else None, Ms.data_ptr(),
+           ldx, ws.data_ptr(), _stream())
+    ref = np.einsum("ajr,j,bjr->ab", B, lt if weighted else np.ones(nt), B)
+    assert relerr(Ms[:, :nx].cpu().numpy(), ref) < 1e-12
+
+
+@pytest.mark.parametrize("n", [5, 24, 100, 251])
+def test_eigh(cuda_lib, n):
+    from gpcsd_b200 import _lib as L
+    rng = np.random.default_rng(n)
+    K = rng.standard_normal((n, n))
+    K = K @ K.T
+    Kd, ld = _dev(K)
+    QT = torch.zeros((n, ld), dtype=F64, device="cuda")
+    W = torch.zeros(n, dtype=F64, device="cuda")
+    nws = L.query("gpcsd_eigh_ws_doubles", n, ld)
+    ws = torch.zeros(max(nws, 1), dtype=F64, device="cuda")
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    L.call("gpcsd_eigh", n, Kd.data_ptr(), ld, QT.data_ptr(), ld, W.data_ptr(), ws.data_ptr(), nws, info.data_ptr(), _stream())
+    assert int(info.item()) == 0
+    w = W.cpu().numpy()
+    Q = QT[:, :n].cpu().numpy().T
+    assert np.all(np.diff(w) >= 0)
+    assert relerr(w, np.linalg.eigvalsh(K)) < 1e-12
+    assert relerr((Q * w) @ Q.T, K) < 1e-12
+    assert relerr(Q.T @ Q, np.eye(n)) < 1e-12
+
+
+@pytest.mark.parametrize("vec", [False, True])
+def test_eig_D(cuda_lib, vec):
+    from gpcsd_b200 import _lib as L
+    rng = np.random.default_rng(1)
+    nx, nt = 24, 77
+    ls, lt = np.sort(rng.uniform(0, 5, nx)), np.sort(rng.uniform(0, 2, nt))
+    s = rng.uniform(0.1, 0.3, nx) if vec else np.array([0.2])
+    ldrd = _ld(nt)
+    rD = torch.zeros((nx, ldrd), dtype=F64, device="cuda")
+    sums, rowA, rowC, rowL = (torch.zeros(k, dtype=F64, device="cuda") for k in (2, nx, nx, nx))
+    colB = torch.zeros(nt, dtype=F64, device="cuda")
+    d = lambda a: torch.from_numpy(a).cuda()
+    lsd, ltd, sd = d(ls), d(lt), d(s)
+    L.call("gpcsd_eig_D", nx, nt, lsd.data_ptr(), ltd.data_ptr(), sd.data_ptr(), len(s), rD.data_ptr(), ldrd,
+           sums.data_ptr(), rowA.data_ptr(), rowC.data_ptr(), rowL.data_ptr(), colB.data_ptr(), _stream())
+    D = ls[:, None] * lt[None, :] + (s[:, None] if vec else s[0])
+    assert relerr(rD[:, :nt].cpu().numpy(), 1 / D) < 1e-14
+    assert relerr(sums.cpu().numpy(), [np.sum(np.log(D)), np.sum(1 / D)]) < 1e-13
+    assert relerr(rowA.cpu().numpy(), (lt[None, :] / D).sum(1)) < 1e-13
+    assert relerr(rowC.cpu().numpy(), (1 / D).sum(1)) < 1e-13
+    assert relerr(rowL.cpu().numpy(), np.log(D).sum(1)) < 1e-13
+    assert relerr(colB.cpu().numpy(), (ls[:, None] / D).sum(0)) < 1e-13
+
+
+def test_covariance_builders_match_oracle(cuda_lib):
+    from gpcsd_b200 import _lib as L
+    from oracle import gpcsd_oracle as O
+    rng = np.random.default_rng(2)
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+    # 1-D forward weights + SE matrices
+    x = np.linspace(0, 2300, 24)
+    gx, gw = O.gauss_legendre(-200.0, 2600.0, 100)
+    A = torch.zeros((24, 100), dtype=F64, device="cuda")
+    dA = torch.zeros_like(A)
+    xd, gxd, gwd = d(x), d(gx), d(gw)
+    L.call("gpcsd_fwd_weights_1d", 24, xd.data_ptr(), 100, gxd.data_ptr(), gwd.data_ptr(), 137.0, A.data_ptr(),
+           dA.data_ptr(), 100, _stream())
+    ref = gw[None, :] * O.b_fwd_1d(gx[None, :] - x[:, None], 137.0)
+    assert relerr(A.cpu().numpy(), ref) < 1e-14
+    h = 1e-3
+    fd = gw[None, :] * (O.b_fwd_1d(gx[None, :] - x[:, None], 137.0 + h) - O.b_fwd_1d(gx[None, :] - x[:, None], 137.0 - h)) / (2 * h)
+    assert relerr(dA.cpu().numpy(), fd) < 1e-7
+    Kg = torch.zeros((100, 100), dtype=F64, device="cuda")
+    L.call("gpcsd_se_matrix", 100, gxd.data_ptr(), 100, gxd.data_ptr(), 200.0, 1.0, 0, Kg.data_ptr(), 100, _stream())
+    assert relerr(Kg.cpu().numpy(), np.exp(-0.5 * np.square((gx[:, None] - gx[None, :]) / 200.0))) < 1e-14
+    L.call("gpcsd_se_matrix", 100, gxd.data_ptr(), 100, gxd.data_ptr(), 200.0, 1.0, 1, Kg.data_ptr(), 100, _stream())
+    dd = gx[:, None] - gx[None, :]
+    assert relerr(Kg.cpu().numpy(), np.exp(-0.5 * np.square(dd / 200.0)) * dd ** 2 / 200.0 ** 3) < 1e-13
+    # 2-D forward weights
+    pts = rng.uniform(0, 50, (7, 2))
+    g1, w1 = O.gauss_legendre(0.0, 48.0, 6)
+    g2, w2 = O.gauss_legendre(0.0, 220.0, 10)
+    sp = O.Spatial2D(pts, 0.0, 48.0, 0.0, 220.0, 6, 10)
+    A2 = torch.zeros((7, 60), dtype=F64, device="cuda")
+    dA2 = torch.zeros_like(A2)
+    pd_, g1d, w1d, g2d, w2d = d(pts), d(g1), d(w1), d(g2), d(w2)
+    L.call("gpcsd_fwd_weights_2d", 7, pd_.data_ptr(), 6, 10, g1d.data_ptr(), w1d.data_ptr(), g2d.data_ptr(),
+           w2d.data_ptr(), 60.0, 20.0, A2.data_ptr(), dA2.data_ptr(), 60, _stream())
+    ref2 = sp.w_prod[None, :] * O.b_fwd_2d(sp.delta_w(pts), 60.0, 20.0)
+    assert relerr(A2.cpu().numpy(), ref2) < 1e-14
+    fd2 = sp.w_prod[None, :] * (O.b_fwd_2d(sp.delta_w(pts), 60.0 + h, 20.0) - O.b_fwd_2d(sp.delta_w(pts), 60.0 - h, 20.0)) / (2 * h)
+    assert relerr(dA2.cpu().numpy(), fd2) < 1e-7
+    # grid-to-points kernel (transposed storage)
+    z = rng.uniform(0, 50, (5, 2))
+    out = torch.zeros((5, 60), dtype=F64, device="cuda")
+    zd = d(z)
+    L.call("gpcsd_se_grid_to_pts", 6, 10, g1d.data_ptr(), g2d.data_ptr(), 5, zd.data_ptr(), 30.0, 70.0, out.data_ptr(), 60, _stream())
+    refz = (np.exp(-0.5 * np.square((sp.grid1[:, None] - z[:, 0][None, :]) / 30.0))
+            * np.exp(-0.5 * np.square((sp.grid2[:, None] - z[:, 1][None, :]) / 70.0)))
+    assert relerr(out.cpu().numpy(), refz.T) < 1e-14
+    # temporal covariance, rectangular
+    t, tp = np.linspace(0, 49, 50), np.linspace(0.5, 30, 31)
+    Kt = torch.zeros((50, 32), dtype=F64, device="cuda")
+    td, tpd = d(t), d(tp)
+    L.call("gpcsd_kt_build", 50, td.data_ptr(), 31, tpd.data_ptr(), 2, L.c_int_array([0, 1]), L.c_double_array([20.0, 5.0]),
+           L.c_double_array([0.5, 0.7]), Kt.data_ptr(), 32, _stream())
+    ref = O.compute_Kt(0, 20.0, 0.5, t, tp) + O.compute_Kt(1, 5.0, 0.7, t, tp)
+    assert relerr(Kt[:, :31].cpu().numpy(), ref) < 1e-14
+
+
+def test_kt_grad_and_small_helpers(cuda_lib):
+    from gpcsd_b200 import _lib as L
+    from oracle import gpcsd_oracle as O
+    rng = np.random.default_rng(4)
+    nt = 61
+    t = np.sort(rng.uniform(0, 80, nt))
+    G = rng.standard_normal((nt, nt))
+    Gd, ldg = _dev(G)
+    td = torch.from_numpy(t).cuda()
+    ws = torch.zeros(L.query("gpcsd_kt_grad_ws_doubles", nt, 2), dtype=F64, device="cuda")
+    out = torch.zeros(4, dtype=F64, device="cuda")
+    L.call("gpcsd_kt_grad", nt, td.data_ptr(), 2, L.c_int_array([0, 1]), L.c_double_array([20.0, 5.0]),
+           L.c_double_array([0.5, 0.7]), Gd.data_ptr(), ldg, ws.data_ptr(), out.data_ptr(), _stream())
+    dist = t[:, None] - t[None, :]
+    Kse, Km = O.compute_Kt(0, 20.0, 0.5, t), O.compute_Kt(1, 5.0, 0.7, t)
+    ref = [np.sum(G * Kse * dist ** 2 / 20.0 ** 3), np.sum(G * Kse) / 0.5, np.sum(G * Km * np.abs(dist) / 25.0), np.sum(G * Km) / 0.7]
+    assert relerr(out.cpu().numpy(), ref) < 1e-12
+    # transpose / add_diag / dot / sum_arrays
+    X = rng.standard_normal((13, 40))
+    Xd, ldx = _dev(X)
+    XT = torch.zeros((40, 14), dtype=F64, device="cuda")
+    L.call("gpcsd_transpose", 13, 40, Xd.data_ptr(), ldx, XT.data_ptr(), 14, _stream())
+    assert np.array_equal(XT[:, :13].cpu().numpy(), X.T)
+    Yh = rng.standard_normal((13, 40))
+    Yd, ldy = _dev(Yh)
+    wsd = torch.zeros(L.query("gpcsd_dot_ws_doubles", 13 * 40), dtype=F64, device="cuda")
+    o1 = torch.zeros(1, dtype=F64, device="cuda")
+    L.call("gpcsd_dot", 13, 40, Xd.data_ptr(), ldx, Yd.data_ptr(), ldy, wsd.data_ptr(), o1.data_ptr(), _stream())
+    assert abs(o1.item() - np.sum(X * Yh)) < 1e-12 * np.sum(np.abs(X * Yh))
+    K = torch.zeros((6, 6), dtype=F64, device="cuda")
+    L.call("gpcsd_add_diag", 6, K.data_ptr(), 6, 1e-8, _stream())
+    assert np.array_equal(K.cpu().numpy(), 1e-8 * np.eye(6))
+    import ctypes
+    a, b = torch.from_numpy(rng.standard_normal(1000)).cuda(), torch.from_numpy(rng.standard_normal(1000)).cuda()
+    o = torch.zeros(1000, dtype=F64, device="cuda")
+    ptrs = (ctypes.c_void_p * 2)(a.data_ptr(), b.data_ptr())
+    L.call("gpcsd_sum_arrays", 1000, 2, ptrs, o.data_ptr(), _stream())
+    assert np.array_equal(o.cpu().numpy(), (a + b).cpu().numpy())
