@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""bench.py -- GPCSD loglik+grad throughput on B200 (BASELINE.json metric, configs[1]).
+
+Workload (configs[1]): GPCSD1D auditory-shaped synthetic LFP -- 2 probes x 24 channels, 500 time points
+(1 ms grid), 2000 trials per probe per GPU, integration bounds a=-200, b=2600, ngl=100, temporal list
+[SE, Matern-1/2], per-electrode noise (P = 30 hyperparameters), set up like
+auditory_lfp/fit_gpcsd_baseline.py:80-89 of the reference.  A STEP is one marginal log-likelihood +
+hyperparameter-gradient evaluation for EACH of the two probes (2 evals); hyperparameters change every
+step (theta_true + 0.1 N(0,1), the L-BFGS access pattern).  The unit "eval" is one loglik+grad over one
+24 x 500 x 2000 trial block.
+
+  value : device-resident -- each probe's LFP block already sits in HBM (how fit() runs: data uploaded
+          once, thousands of evaluations).  Everything else is inside the timed region: covariance build,
+          both eigendecompositions, projections, gradient SYRKs, device->host read of (ll, grad), host
+          assembly, and the all-reduce at N > 1.
+  e2e   : the same evaluations through the public API (GPCSD1D.update_lfp + GPCSD1D.obj_fun_and_grad) with
+          the LFP block copied from PINNED HOST memory every step and the result read back.
+Multi-GPU (torchrun, one rank per GPU): weak scaling -- every rank holds its own 2000-trial slab per probe,
+the model sees 2000*N trials, one all-reduce of P+1 doubles per evaluation; value = N * 2 * K / time.
+
+`--impl reference` times the CPU restatement of the reference algorithm (oracle/, numpy + BLAS threads)
+on a bounded sample of the same workload on the box's host cores (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NX, NT, NTRIALS, NGL = 24, 500, 2000, 100
+A_LO, B_HI = -200.0, 2600.0
+NPROBES = 2
+METRIC = "gpcsd_loglik_grad_evals_per_s"
+UNIT = "evals/s"
+
+
+def true_hyper(probe):
+    """theta_true of SURVEY.md 8d (sim_from_gp_1D.py:41-47 family), per-electrode noise 1e-2*exp(.3 N(0,1))."""
+    rng = np.random.default_rng(2000 + probe)
+    return dict(R=100.0, ell=200.0, se=(20.0, 0.5), matern=(5.0, 0.7), sig2n=1e-2 * np.exp(0.3 * rng.standard_normal(NX)))
+
+
+def geometry():
+    x = np.linspace(0.0, 2300.0, NX)[:, None]
+    t = np.arange(NT, dtype=np.float64)[:, None]
+    return x, t
+
+
+# ----------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on host cores
+# ----------------------------------------------------------------------------------------------------
+def cpu_eval_seconds(sample_trials, reps=1):
+    """Time the CPU restatement (oracle.gpcsd_oracle.loglik_and_grad: the reference's covariance build,
+    two LAPACK eigh, Kronecker projection of every trial and the closed-form gradient) on a bounded sample
+    of one probe block.  Returns (seconds per evaluation of the sample, cores)."""
+    from oracle import gpcsd_oracle as O
+    from oracle import synth
+    x, t = geometry()
+    th = true_hyper(0)
+    om = synth.model_1d(x, t, a=A_LO, b=B_HI, ngl=NGL, sig2n=th["sig2n"])
+    rng = np.random.default_rng(7)
+    lfp = rng.standard_normal((NX, NT, sample_trials))
+    O.loglik_and_grad(om, lfp[:, :, : max(8, sample_trials // 8)])   # warm BLAS threads
+    ts = []
+    for r in range(reps):
+        om_r = synth.perturbed(om, 100 + r)
+        t0 = time.perf_counter()
+        O.loglik_and_grad(om_r, lfp)
+        ts.append(time.perf_counter() - t0)
+    return float(np.median(ts)), os.cpu_count()
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    sample = 500
+    per_step = []
+    for _ in range(args.warmup):
+        cpu_eval_seconds(sample)
+    for _ in range(args.steps):
+        # one step = NPROBES evals of a full block; measured on a quarter block per probe and scaled
+        s, cores = cpu_eval_seconds(sample)
+        per_step.append(s * (NTRIALS / sample) * NPROBES)
+    ms = 1e3 * float(np.mean(per_step))
+    value = NPROBES / (ms * 1e-3)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                             "sample": "oracle loglik_and_grad (numpy/LAPACK restatement of loglik + closed-form "
+                                       "gradient; HIPS autograd not installable) on 24x500x%d trials, time scaled x%d "
+                                       "to a 2000-trial block" % (sample, NTRIALS // sample)},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus):
+    return {"workload": "BASELINE.json configs[1]: GPCSD1D auditory-shaped, 2 probes x 24 ch x 500 t x 2000 trials per GPU, "
+                        "per-electrode noise (P=30), a=-200 b=2600 ngl=100, loglik+grad",
+            "eval_unit": "one loglik+grad over a 24x500x2000 trial block", "trials_per_gpu_per_probe": NTRIALS,
+            "global_trials_per_probe": NTRIALS * n_gpus, "parallelism": "trial-shard x%d, 1 allreduce of P+1 f64 per eval" % n_gpus,
+            "cache": "working set per step 2 x (Y+Z+B) = 1.15 GB >> 126 MB L2 (inputs larger than L2)"}
+
+
+# ----------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------
+def make_models(device, world, torch):
+    """Two GPCSD1D models (one per probe) set up like fit_gpcsd_baseline.py:80-89, with model-matched
+    synthetic LFP generated on the device (generator only; not part of the measured path)."""
+    from gpcsd_b200.covariances import GPCSD1DSpatialCovSE, GPCSDTemporalCovMatern, GPCSDTemporalCovSE
+    from gpcsd_b200.gpcsd1d import GPCSD1D
+    from gpcsd_b200.priors import GPCSDHalfNormalPrior
+    x, t = geometry()
+    rank = int(os.environ.get("RANK", "0"))
+    models = []
+    for probe in range(NPROBES):
+        np.random.seed(10 + probe)
+        th = true_hyper(probe)
+        spatial_cov = GPCSD1DSpatialCovSE(x, a=A_LO, b=B_HI, ngl=NGL)
+        se, mat = GPCSDTemporalCovSE(t), GPCSDTemporalCovMatern(t)
+        se.params['ell']['prior'].set_params(30.0, 100.0)
+        mat.params['ell']['prior'].set_params(1.0, 20.0)
+        sig_pri = [GPCSDHalfNormalPrior(0.1) for _ in range(NX)]
+        placeholder = np.zeros((NX, NT, 1))
+        m = GPCSD1D(placeholder, x, t, a=A_LO, b=B_HI, ngl=NGL, spatial_cov=spatial_cov, temporal_cov_list=[se, mat],
+                    sig2n_prior=sig_pri, distributed=(world > 1))
+        m.lfp_is_local = world > 1
+        m.R['value'] = th["R"]
+        spatial_cov.params['ell']['value'] = th["ell"]
+        Ks = spatial_cov.compKphi_1d(th["R"])
+        scale = np.trace(Ks) / NX                      # unit-scale LFP
+        se.params['ell']['value'], se.params['sigma2']['value'] = th["se"][0], th["se"][1] / scale
+        mat.params['ell']['value'], mat.params['sigma2']['value'] = th["matern"][0], th["matern"][1] / scale
+        m.sig2n['value'] = th["sig2n"].copy()
+        # model-matched draw  Y_r = Ls Z_r Lt^T + sqrt(sig2n) E_r  (torch on the device: data generator only)
+        Kt = se.compute_Kt() + mat.compute_Kt()
+        g = torch.Generator(device=device)
+        g.manual_seed(1000 * (probe + 1) + rank)
+        ls, Qs = np.linalg.eigh(Ks + 1e-8 * np.eye(NX))
+        lt, Qt = np.linalg.eigh(Kt)
+        Ls = torch.from_numpy(Qs * np.sqrt(np.maximum(ls, 0))).to(device)
+        Lt = torch.from_numpy(Qt * np.sqrt(np.maximum(lt, 0))).to(device)
+        Z = torch.randn((NX, NT, NTRIALS), dtype=torch.float64, device=device, generator=g)
+        Y = torch.einsum("ia,ajr->ijr", Ls, Z)
+        Y = torch.einsum("ijr,bj->ibr", Y, Lt)
+        Y += float(np.sqrt(np.mean(th["sig2n"]))) * torch.randn(Y.shape, dtype=torch.float64, device=device, generator=g)
+        host = torch.empty((NX, NT, NTRIALS), dtype=torch.float64).pin_memory()
+        host.copy_(Y)
+        del Z, Y
+        m.lfp = host.numpy()                           # numpy view of PINNED memory
+        m._invalidate_lfp()
+        models.append(m)
+    return models
+
+
+def theta_sequence(model, n, seed):
+    """Log-space hyperparameter vectors theta_true + 0.1 N(0,1), one per step."""
+    rng = np.random.default_rng(seed)
+    vals = [model.R['value'] / 100.0, model.spatial_cov.params['ell']['value'] / 100.0]
+    for tc in model.temporal_cov_list:
+        vals += [tc.params['ell']['value'], tc.params['sigma2']['value']]
+    vals += list(model.sig2n['value'])
+    t0 = np.log(np.array(vals, dtype=np.float64))
+    return [t0 + 0.1 * rng.standard_normal(t0.shape) for _ in range(n)]
+
+
+def measure_fp64_peak(torch, device):
+    """cuBLAS DGEMM 4096^3, best of 5 (MEASURED_PEAKS.json carries HBM and bf16 only)."""
+    n = 4096
+    a = torch.randn(n, n, dtype=torch.float64, device=device)
+    b = torch.randn(n, n, dtype=torch.float64, device=device)
+    best = 1e9
+    for i in range(7):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        a @ b
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            best = min(best, e0.elapsed_time(e1))
+    del a, b
+    return 2.0 * n ** 3 / (best * 1e-3) * 1e-12
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    import __graft_entry__ as ge
+    ge.ensure_built()
+
+    models = make_models(device, world, torch)
+    K, W = args.steps, max(args.warmup, 3)
+    thetas = [theta_sequence(m, 2 * (K + W), 500 + p) for p, m in enumerate(models)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, nsteps, offset):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in range(nsteps):
+            fn(offset + s)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tt = torch.tensor([ms], dtype=torch.float64, device=device)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        return ms
+
+    last = {}
+
+    def step_resident(s):
+        for p, m in enumerate(models):
+            last[p] = m.obj_fun_and_grad(thetas[p][s])
+
+    def step_e2e(s):
+        for p, m in enumerate(models):
+            m.update_lfp(m.lfp, m.t)                       # forces the host->device copy of the pinned block
+            last[p] = m.obj_fun_and_grad(thetas[p][s])
+
+    # ---- device-resident arm ("value")
+    for m in models:
+        m._get_engine()                                     # upload once
+    timed(step_resident, W, 0)
+    if args.profile_step:
+        # one steady-state step between cudaProfilerStart/Stop for `ncu --profile-from-start off`
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step_resident(W)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        if rank == 0:
+            print(json.dumps({"profile_step": "done"}))
+        return
+    engines = [m._get_engine() for m in models]
+    for e in engines:
+        e.timers = {"gpcsd_project_quad": [], "gpcsd_wsyrk": [], "gpcsd_eigh": [], "gpcsd_dgemm": []}
+        e.n_launches = 0
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(step_resident, K, W)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = sum(e.n_launches for e in engines)
+    kt = {}
+    for name in engines[0].timers:
+        d = [a.elapsed_time(b) for e in engines for (a, b) in e.timers[name]]
+        kt[name] = (float(np.mean(d)) if d else 0.0, len(d))
+    for e in engines:
+        e.timers = None
+    # ---- end-to-end arm
+    timed(step_e2e, W, K + W)
+    ms_e2e = timed(step_e2e, K, K + 2 * W)
+
+    evals_per_step = NPROBES * world
+    value = evals_per_step * K / (ms_total * 1e-3)
+    e2e_value = evals_per_step * K / (ms_e2e * 1e-3)
+    P = 6 + NX
+    if rank == 0:
+        peak = measure_fp64_peak(torch, device)
+        algo_flops = 2.0 * NX * NT * NT * NTRIALS            # projection Qt^T Z_i for all i: SURVEY.md 8d
+        dur_ms = kt["gpcsd_project_quad"][0]
+        achieved = algo_flops / (dur_ms * 1e-3) * 1e-12 if dur_ms > 0 else None
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("project_quad_dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": workload_config(world),
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K,
+                        "h2d_bytes_per_step": NPROBES * NX * NT * NTRIALS * 8 + NPROBES * 0,
+                        "d2h_bytes_per_step": NPROBES * (8 + 2 * 2 + 2 * NX) * 8,
+                        "api": "GPCSD1D.update_lfp(pinned lfp) + GPCSD1D.obj_fun_and_grad(tparams)"},
+                "gpu_launches": launches,
+                "roofline": {"bound": "tensor", "kernel": "dmma_gemm_kernel<128,128,64,32,4,NN,EPI_QUAD> (gpcsd_project_quad)",
+                             "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                             "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                             "algorithmic_flops_per_launch": algo_flops, "avg_launch_ms": dur_ms,
+                             "peak_source": "in-run cuBLAS DGEMM 4096^3 best-of-5 (FP64; MEASURED_PEAKS.json has only "
+                                            "HBM and bf16); DMMA issue-rate microbenchmark: 37.0 TFLOP/s"},
+                "kernel_ms": {k: {"avg_ms": v[0], "calls": v[1]} for k, v in kt.items()},
+                "last_nll": [float(last[p][0]) for p in range(NPROBES)]}
+        if world == 1 and not args.no_cpu_baseline:
+            sample = 500
+            secs, cores = cpu_eval_seconds(sample, reps=3)
+            full = secs * NTRIALS / sample
+            line["cpu_baseline"] = {"value": 1.0 / full, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "oracle loglik_and_grad (numpy/LAPACK restatement; closed-form gradient) on "
+                                              "24x500x%d trials, median of 3, time scaled x%d to a 2000-trial block" % (sample, NTRIALS // sample)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-step", action="store_true", help="run warm-up then ONE step inside cudaProfilerStart/Stop")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args, int(os.environ.get("RANK", "0")))
+        return
+    run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,235 @@
+"""Shared implementation of the GPCSD1D / GPCSD2D model classes on top of the CUDA engine.
+
+The public surface (constructor arguments, attribute names, hyperparameter dictionaries, method names
+and side effects) follows the reference classes (gpcsd1d.py:19-309, gpcsd2d.py:18-360); the arithmetic
+is delegated to ``engine.KronEngine``.  Dimension-specific pieces (parameter names, bounds, quadrature)
+live in the two subclasses.
+"""
+import numpy as np
+import scipy.optimize
+from tqdm import tqdm
+
+from . import devops
+from .engine import HyperParams, KronEngine
+
+np.seterr(all='ignore')  # gpcsd1d.py:7 -- NaN/inf propagate as values
+
+
+def _is_scalar(v):
+    return np.isscalar(v) or np.ndim(v) == 0
+
+
+class GPCSDModelBase:
+    DIM = None
+    JITTER = None
+    SPATIAL_ELL_KEYS = ()       # ('ell',) or ('ell1', 'ell2')
+    DEFAULT_MAXITER = 1000
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _quadrature(self):
+        raise NotImplementedError
+
+    def _get_engine(self):
+        eng = getattr(self, "_engine", None)
+        geom_key = (id(self.x), id(self.t), id(self.spatial_cov))
+        if eng is None or self._engine_geom != geom_key:
+            eng = KronEngine(self.DIM, self.x, self.t, self._quadrature(), group=getattr(self, "_group", None),
+                             jitter=self.JITTER)
+            self._engine, self._engine_geom, self._engine_lfp = eng, geom_key, None
+        if self._engine_lfp is not self.lfp:
+            eng.set_lfp(self.lfp, local=getattr(self, "lfp_is_local", False))
+            self._engine_lfp = self.lfp
+        return eng
+
+    def _invalidate_lfp(self):
+        """Force a fresh host->device upload at the next evaluation (called by update_lfp)."""
+        self._engine_lfp = None
+
+    def _hyperparams(self):
+        sig = self.sig2n['value']
+        sig = float(sig) if _is_scalar(sig) else np.asarray(sig, dtype=np.float64)
+        return HyperParams(
+            R=float(self.R['value']),
+            ells=tuple(float(self.spatial_cov.params[k]['value']) for k in self.SPATIAL_ELL_KEYS),
+            temporal=[(tc.KIND, float(tc.params['ell']['value']), float(tc.params['sigma2']['value']))
+                      for tc in self.temporal_cov_list],
+            sig2n=sig, eps=float(getattr(self, "eps", 0.0) or 0.0))
+
+    # ------------------------------------------------------------------ parameter (de)serialisation
+    def _temporal_lists(self):
+        return ([tc.params['ell']['value'] for tc in self.temporal_cov_list],
+                [tc.params['sigma2']['value'] for tc in self.temporal_cov_list])
+
+    def _restore_temporal(self, params):
+        if len(self.temporal_cov_list) != len(params['temporal_ell_list']):
+            print('different number of temporal covariance functions! stopping.')
+            return
+        for i, tc in enumerate(self.temporal_cov_list):
+            tc.params['ell']['value'] = params['temporal_ell_list'][i]
+            tc.params['sigma2']['value'] = params['temporal_sigma2_list'][i]
+
+    def _str_temporal(self):
+        s = ""
+        for i, tc in enumerate(self.temporal_cov_list):
+            s += "Temporal covariance %d class name: %s\n" % (i + 1, type(tc).__name__)
+            s += "Temporal covariance %d ell prior: %s\n" % (i + 1, str(tc.params['ell']['prior']))
+            s += "Temporal covariance %d ell value %0.4g\n" % (i + 1, tc.params['ell']['value'])
+            s += "Temporal covariance %d sigma2 prior: %s\n" % (i + 1, str(tc.params['sigma2']['prior']))
+            s += "Temporal covariance %d sigma2 value %0.4g\n" % (i + 1, tc.params['sigma2']['value'])
+        return s
+
+    # ------------------------------------------------------------------ likelihood
+    def loglik(self):
+        """Marginal log-likelihood of all trials at the current hyperparameters
+        (gpcsd1d.py:113-128 / gpcsd2d.py:136-151)."""
+        return np.float64(self._get_engine().loglik(self._hyperparams()))
+
+    def loglik_and_grad(self):
+        """(loglik, gradient w.r.t. R, spatial ell(s), (ell_t, sigma2_t) per temporal kernel, sig2n[...])
+        in natural units -- one fused device evaluation (replaces loglik + autograd.grad)."""
+        return self._get_engine().loglik_grad(self._hyperparams())
+
+    # ------------------------------------------------------------------ fit objective in log space
+    def _param_slots(self):
+        """[(dict, scale)] in the reference's tparams order (gpcsd1d.py:160-174 / gpcsd2d.py:185-199):
+        value = exp(tparam) * scale."""
+        slots = [(self.R, 100.0)] + [(self.spatial_cov.params[k], 100.0) for k in self.SPATIAL_ELL_KEYS]
+        for tc in self.temporal_cov_list:
+            slots += [(tc.params['ell'], 1.0), (tc.params['sigma2'], 1.0)]
+        return slots
+
+    def _noise_is_scalar(self):
+        return _is_scalar(self.sig2n['value'])
+
+    def _bounds(self):
+        b = [(np.log(d['min'] / sc), np.log(d['max'] / sc)) for d, sc in self._param_slots()]
+        if self._noise_is_scalar():
+            b.append((np.log(self.sig2n['min']), np.log(self.sig2n['max'])))
+        else:
+            b += [(np.log(lo), np.log(hi)) for lo, hi in zip(self.sig2n['min'], self.sig2n['max'])]
+        return b
+
+    def _set_tparams(self, tparams, fix_R):
+        slots = self._param_slots()
+        for k, (d, sc) in enumerate(slots):
+            if k == 0 and fix_R:
+                continue
+            d['value'] = np.exp(tparams[k]) * sc
+        p = len(slots)
+        self.sig2n['value'] = np.exp(tparams[p]) if self._noise_is_scalar() else np.exp(np.asarray(tparams[p:]))
+
+    def _sample_tparams0(self, fix_R):
+        """Random start from the priors, same draw order as gpcsd1d.py:194-208."""
+        t0 = []
+        for k, (d, sc) in enumerate(self._param_slots()):
+            v = d['value'] if (k == 0 and fix_R) else d['prior'].sample()
+            t0.append(np.log(v) - np.log(sc))
+        if self._noise_is_scalar():
+            t0.append(np.log(self.sig2n['prior'].sample()))
+        else:
+            t0 += [np.log(p.sample()) for p in self.sig2n['prior']]
+        return np.array(t0)
+
+    def _prior_terms(self):
+        """(sum of lpdf, d lpdf / d value per tparams slot) at the current values (gpcsd1d.py:177-186)."""
+        vals, pris = [], []
+        for d, _ in self._param_slots():
+            vals.append(d['value'])
+            pris.append(d['prior'])
+        if self._noise_is_scalar():
+            vals.append(self.sig2n['value'])
+            pris.append(self.sig2n['prior'])
+        else:
+            vals += list(self.sig2n['value'])
+            pris += list(self.sig2n['prior'])
+        lp = 0.0
+        for p, v in zip(pris, vals):
+            lp = lp + p.lpdf(v)
+        dlp = np.array([p.dlpdf(v) if v > 0 else 0.0 for p, v in zip(pris, vals)])
+        return lp, dlp, np.array(vals, dtype=np.float64)
+
+    def obj_fun(self, tparams, fix_R=False):
+        """Negative log posterior at log-space ``tparams``; writes the values into the model like the
+        reference's closure (gpcsd1d.py:153-191)."""
+        self._set_tparams(tparams, fix_R)
+        lp, _, _ = self._prior_terms()
+        try:
+            llik = self.loglik()
+        except np.linalg.LinAlgError:
+            if self.DIM == 1:
+                raise
+            llik = -np.inf                                             # gpcsd2d.py:215-219
+        return -1.0 * (llik + lp)
+
+    def obj_fun_and_grad(self, tparams, fix_R=False):
+        """(nll, d nll / d tparams): the pair scipy's L-BFGS-B consumes (jac=True)."""
+        self._set_tparams(tparams, fix_R)
+        lp, dlp, vals = self._prior_terms()
+        try:
+            ll, g = self.loglik_and_grad()
+        except np.linalg.LinAlgError:
+            if self.DIM == 1:
+                raise
+            return np.inf, np.zeros(len(vals))
+        grad = -(np.asarray(g) + dlp) * vals                           # chain rule of value = exp(tparam) * scale
+        if fix_R:
+            grad[0] = 0.0
+        return -1.0 * (ll + lp), grad
+
+    # ------------------------------------------------------------------ fit
+    def _fit(self, n_restarts, method, fix_R, verbose, options):
+        bounds = self._bounds()
+        nll_values, params, term_msg = [], [], []
+        for _ in tqdm(range(n_restarts), desc="Restarts"):
+            tparams0 = self._sample_tparams0(fix_R)
+            try:
+                res = scipy.optimize.minimize(lambda tp: self.obj_fun_and_grad(tp, fix_R), tparams0, jac=True,
+                                              method=method, options=options, bounds=bounds)
+                nll_values.append(res.fun)
+                params.append(res.x)
+                term_msg.append(res.message)
+            except (ValueError, np.linalg.LinAlgError) as e:
+                print(e)
+                if self.DIM == 2:
+                    print('\nrestarting optimization...')
+        nll_values = np.array(nll_values)
+        if len(nll_values) < 1:
+            print('problem with optimization!')
+            return
+        finite = np.isfinite(nll_values)
+        best_ind = np.argmin(nll_values[finite])
+        params = [p for p, ok in zip(params, finite) if ok]
+        if verbose:
+            print('\nNeg log lik values across different initializations:')
+            print(nll_values)
+            print('Best index termination message')
+            print(term_msg[best_ind])
+        self._set_tparams(params[best_ind], fix_R)
+
+    # ------------------------------------------------------------------ prediction
+    def predict(self, z, t, type="csd"):
+        """Posterior mean CSD and/or LFP at locations ``z`` and times ``t``; results are stored as attributes
+        csd_pred, csd_pred_list, lfp_pred, lfp_pred_list, t_pred, x_pred (gpcsd1d.py:248-293)."""
+        out = self._get_engine().predict(self._hyperparams(), z, t, kind=type)
+        if type == "both" or type == "csd":
+            self.csd_pred_list = out["csd_pred_list"]
+            self.csd_pred = out["csd_pred"]
+        if type == "both" or type == "lfp":
+            self.lfp_pred_list = out["lfp_pred_list"]
+            self.lfp_pred = out["lfp_pred"]
+        self.t_pred = t
+        self.x_pred = z
+
+    # ------------------------------------------------------------------ prior sampling helpers
+    def _kt_total(self):
+        nt = self.t.shape[0]
+        Kt = np.zeros((nt, nt))
+        for tc in self.temporal_cov_list:
+            Kt += tc.compute_Kt()
+        return Kt
+
+    @staticmethod
+    def _sample_trials(Ls, Lt, rand):
+        """out[:, :, r] = Ls rand[:, :, r] Lt^T for every trial, as two device GEMMs over the trial-fastest
+        layout (replaces the per-trial loop of gpcsd1d.py:307-308)."""
+        return devops.sandwich(Ls, rand, Lt)

@@ -71,6 +71,7 @@ class KronEngine:
         self.ntrials_total = 0
         self.ntrials = 0
         self.n_launches = 0
+        self.timers = None      # {abi_name: [(start_event, end_event), ...]} when bench.py profiles a kernel
 
     # ------------------------------------------------------------------ plumbing
     def _dev(self, arr):
@@ -93,7 +94,16 @@ class KronEngine:
 
     def _call(self, name, *args):
         self.n_launches += self._LAUNCHES.get(name, 1)
-        return L.call(name, *args)
+        timers = self.timers.get(name) if self.timers else None
+        if timers is None:
+            return L.call(name, *args)
+        # bench.py roofline: CUDA events on the launching stream around this ABI call
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = L.call(name, *args)
+        e1.record()
+        timers.append((e0, e1))
+        return rc
 
     @staticmethod
     def _p(t, offset=0):
@@ -132,9 +142,12 @@ class KronEngine:
         self.ldx = _even(self.nx)
         self.ldt = _even(self.nt)
 
-    def set_lfp(self, lfp):
-        """Upload this rank's slab of trials.  lfp: host (nx, nt, ntrials) float64 (C order) or a CUDA tensor
-        of that shape; returns bytes copied host->device."""
+    def set_lfp(self, lfp, local=False):
+        """Upload this rank's slab of trials.  lfp: host (nx, nt, ntrials) float64 (C order; numpy array or
+        torch tensor, pinned memory makes the copy an async DMA) or a CUDA tensor of that shape.
+        local=False: ``lfp`` holds ALL trials and this rank takes its contiguous slab;
+        local=True : ``lfp`` already is this rank's slab (the global trial count is all-reduced).
+        Returns the bytes copied host->device."""
         if isinstance(lfp, torch.Tensor):
             src = lfp if lfp.dim() == 3 else lfp.reshape(lfp.shape[0], lfp.shape[1], -1)
             if src.dtype != F64:
@@ -144,7 +157,11 @@ class KronEngine:
         ntot = src.shape[2]
         if src.shape[0] != self.nx or src.shape[1] != self.nt:
             raise ValueError("lfp shape %s does not match (nx=%d, nt=%d)" % (tuple(src.shape), self.nx, self.nt))
-        lo, hi = self.shard.bounds(ntot)
+        if local:
+            lo, hi = 0, ntot
+            ntot = int(round(self.shard.allreduce_sum(np.array([float(ntot)]), self.device)[0]))
+        else:
+            lo, hi = self.shard.bounds(ntot)
         n = hi - lo
         ldn = _ld8(max(n, 1))
         if self.Y is None or self.Y.shape != (self.nx, self.nt, ldn):
@@ -158,7 +175,7 @@ class KronEngine:
         else:
             # pinned host tensors (torch.Tensor.pin_memory) make this a true async DMA
             dst = self.Y if ldn == n else self.Y[:, :, :n]
-            dst.copy_(slab if (lo == 0 and hi == ntot) else slab.contiguous(), non_blocking=True)
+            dst.copy_(slab if slab.is_contiguous() else slab.contiguous(), non_blocking=True)
             nbytes = slab.numel() * 8
         self.ntrials_total, self.ntrials, self.ldn = ntot, n, ldn
         return nbytes

@@ -1,0 +1,52 @@
+"""Forward-model weight functions and CSD->LFP trapezoid operators -- API mirror of
+``gpcsd.forward_models`` (forward_models.py:9-81).
+
+``b_fwd_1d`` / ``b_fwd_2d`` are the weight functions the covariance kernels fuse on the GPU
+(gpcsd_fwd_weights_{1d,2d}); the host versions here serve callers that use them directly.
+``fwd_model_1d`` / ``fwd_model_2d`` (synthetic-data generators) are restated as
+ONE weight-matrix product each instead of the reference's Python double loop over time x location.
+"""
+import numpy as np
+
+
+def b_fwd_1d(r, R):
+    """sqrt((r/R)^2 + 1) - sqrt((r/R)^2)  (forward_models.py:9-17)."""
+    q = np.square(np.divide(r, R))
+    return np.sqrt(q + 1) - np.sqrt(q)
+
+
+def _trapz_weights(x):
+    x = np.asarray(x, dtype=np.float64).reshape(-1)
+    w = np.zeros_like(x)
+    d = np.diff(x)
+    w[:-1] += 0.5 * d
+    w[1:] += 0.5 * d
+    return w
+
+
+def fwd_model_1d(arr, x, z, R, varsigma=1):
+    """LFP at z from CSD ``arr`` (nx, nt) sampled at x: R/(2 varsigma) * trapz_x b(z_i - x) arr[:, t]
+    (forward_models.py:20-39)."""
+    x = np.asarray(x, dtype=np.float64).reshape(-1)
+    z = np.asarray(z, dtype=np.float64).reshape(-1)
+    W = b_fwd_1d(z[:, None] - x[None, :], R) * _trapz_weights(x)[None, :]
+    return R / (2 * varsigma) * (W @ np.asarray(arr, dtype=np.float64))
+
+
+def b_fwd_2d(delta1, delta2, R, eps, w=None):
+    """log(R+eps+sqrt((R+eps)^2+w^2)) - log(eps+sqrt(eps^2+w^2)), w = |delta| (forward_models.py:42-54)."""
+    if w is None:
+        w = np.array(np.sqrt(np.square(delta1) + np.square(delta2)))
+    return np.log(R + eps + np.sqrt((R + eps) ** 2 + w ** 2)) - np.log(eps + np.sqrt(eps ** 2 + w ** 2))
+
+
+def fwd_model_2d(arr, x1, x2, z, R, eps, varsigma=1):
+    """LFP at z (nz, 2) from CSD ``arr`` (nx1, nx2, nt) on the grid x1 x x2: double trapezoid of
+    b_fwd_2d * arr (forward_models.py:57-81; the 1/(4 pi varsigma) factor is omitted there too)."""
+    x1 = np.asarray(x1, dtype=np.float64).reshape(-1)
+    x2 = np.asarray(x2, dtype=np.float64).reshape(-1)
+    z = np.asarray(z, dtype=np.float64)
+    arr = np.asarray(arr, dtype=np.float64)
+    wt = b_fwd_2d(z[:, 0][:, None, None] - x1[None, :, None], z[:, 1][:, None, None] - x2[None, None, :], R, eps)
+    wt = wt * _trapz_weights(x1)[None, :, None] * _trapz_weights(x2)[None, None, :]
+    return np.einsum("zab,abt->zt", wt, arr, optimize=True)

@@ -17,12 +17,14 @@ def shard_bounds(ntrials, rank, world):
 
 
 class TrialShard:
+    """group: None/False -> single process (no sharding); True -> the default process group;
+    otherwise a torch.distributed process group."""
+
     def __init__(self, group=None):
-        self.group = group
-        self.enabled = group is not None or (dist.is_available() and dist.is_initialized() and group is not False)
-        if group is False:
-            self.enabled = False
-            self.group = None
+        self.enabled = group is not None and group is not False
+        if self.enabled and not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("trial sharding requested but torch.distributed is not initialised")
+        self.group = None if (group is True or not self.enabled) else group
         self.rank = dist.get_rank(self.group) if self.enabled else 0
         self.world = dist.get_world_size(self.group) if self.enabled else 1
 

@@ -389,17 +389,19 @@ def loglik_and_grad(model: Model, lfp, eigh=np.linalg.eigh):
     D = Dv.reshape(nx, nt)
     vec_noise = not (np.isscalar(model.sig2n) or np.ndim(model.sig2n) == 0)
     s = np.asarray(model.sig2n, dtype=np.float64) if vec_noise else np.full(nx, float(model.sig2n))
-    A = np.einsum("ia,ijr->ajr", Qs, lfp, optimize=True)
-    A = np.einsum("ajr,jb->abr", A, Qt, optimize=True)
+    A = (Qs.T @ lfp.reshape(nx, nt * N)).reshape(nx, nt, N)
+    A = np.matmul(Qt.T[None, :, :], A)                                           # A_a = Qt^T Z_a
     B = A / D[:, :, None]
     ll = float(-0.5 * N * np.sum(np.log(D)) - 0.5 * np.sum(A * B))
     Bsq = np.sum(B * B, axis=2)
     Dbar = -0.5 * N / D + 0.5 * Bsq
-    Ms = np.einsum("ajr,j,bjr->ab", B, lt, B, optimize=True)
-    Mt = np.einsum("ajr,a,akr->jk", B, ls, B, optimize=True)
+    B2 = B.reshape(nx, nt * N)
+    Ms = (B * lt[None, :, None]).reshape(nx, nt * N) @ B2.T                      # sum_{j,r} lt_j B_ajr B_bjr
+    Bt = np.ascontiguousarray(B.transpose(1, 0, 2)).reshape(nt, nx * N)
+    Mt = (Bt.reshape(nt, nx, N) * ls[None, :, None]).reshape(nt, nx * N) @ Bt.T  # sum_{a,r} ls_a B_ajr B_akr
     Xs = 0.5 * Ms
     if vec_noise:
-        Ns = np.einsum("ajr,bjr->ab", B, B, optimize=True)
+        Ns = B2 @ B2.T
         dl = ls[:, None] - ls[None, :]
         ds = s[:, None] - s[None, :]
         with np.errstate(divide="ignore", invalid="ignore"):

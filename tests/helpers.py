@@ -2,7 +2,7 @@
 import numpy as np
 
 
-def engine_from_oracle(om, lfp=None, group=False):
+def engine_from_oracle(om, lfp=None, group=None):
     from gpcsd_b200.engine import HyperParams, KronEngine
     sp = om.spatial
     if om.dim == 1:
