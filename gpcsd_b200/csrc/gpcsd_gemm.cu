@@ -60,13 +60,21 @@ __global__ void __launch_bounds__(NTHREADS, MINB) dmma_gemm_kernel(GemmArgs p) {
 #pragma unroll
     for (int j = 0; j < WN / 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+  KMajorLoader<BM> ldA;
+  ldA.init(A, p.lda, rowsA, p.A);
+  KMajorLoader<BN> ldBk;
+  NMajorLoader<BN> ldBn;
+  if (BT)
+    ldBk.init(B, p.ldb, (int)(colsB > BN ? BN : colsB), p.B);
+  else
+    ldBn.init(B, p.ldb, colsB, p.B);
   auto load_stage = [&](int st, int kb) {
     const long k0 = (long)kb * BK;
-    load_kmajor_tile<BM>(sA + st * L::A_STAGE, A + k0, p.lda, rowsA, p.K - k0, p.A);
+    ldA.load(sA + st * L::A_STAGE, k0, p.K - k0);
     if (BT)
-      load_kmajor_tile<BN>(sB + st * L::B_STAGE, B + k0, p.ldb, (int)(colsB > BN ? BN : colsB), p.K - k0, p.B);
+      ldBk.load(sB + st * L::B_STAGE, k0, p.K - k0);
     else
-      load_nmajor_tile<BN>(sB + st * L::B_STAGE, B + k0 * p.ldb, p.ldb, p.K - k0, colsB, p.B);
+      ldBn.load(sB + st * L::B_STAGE, k0, p.K - k0);
   };
 
 #pragma unroll
@@ -232,12 +240,15 @@ __global__ void __launch_bounds__(NTHREADS, MINB) wsyrk_kernel(SyrkArgs p) {
 #pragma unroll
     for (int j = 0; j < WN / 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+  KMajorLoader<BMN> ldA, ldB;
+  ldA.init(XA, p.row_stride, rowsA, p.X);
+  ldB.init(XB, p.row_stride, rowsB, p.X);
   auto load_stage = [&](int st, long f) {
     const int seg = (int)(f / p.kbps);
     const long k0 = (long)(f - (long)seg * p.kbps) * BK;
     const long off = (long)seg * p.seg_stride + k0;
-    load_kmajor_tile<BMN>(sA + st * STAGE, XA + off, p.row_stride, rowsA, p.seglen - k0, p.X);
-    if (!diag) load_kmajor_tile<BMN>(sB + st * STAGE, XB + off, p.row_stride, rowsB, p.seglen - k0, p.X);
+    ldA.load(sA + st * STAGE, off, p.seglen - k0);
+    if (!diag) ldB.load(sB + st * STAGE, off, p.seglen - k0);
   };
 
 #pragma unroll
@@ -296,15 +307,125 @@ __global__ void wsyrk_reduce_kernel(const double* __restrict__ ws, int nsplit, i
   }
 }
 
+// ---- M <= 32: register-only variant ---------------------------------------------------------------
+// One diagonal tile only, so the B fragment of MMA column-tile j IS the A fragment of row-tile j: lane (g,q)
+// loads X[8i+g][k + 2q .. 2q+1] with one LDG.128 per row-tile and feeds two DMMAs (k-slots {0,2,4,6} and
+// {1,3,5,7} -- any k permutation is legal as long as both operands use it).  Nothing is staged in shared
+// memory; the kernel is HBM-bound (6 flop/byte) and keeps 4 chunks x MT LDG.128 in flight per lane.
+template <int MT>
+__global__ void __launch_bounds__(NTHREADS, 2) wsyrk_small_kernel(SyrkArgs p) {
+  extern __shared__ __align__(16) double red[];  // [8 warps][32*32]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, q = lane & 3;
+  const long cps = (p.seglen + 7) / 8;
+  const long total = (long)p.nseg * cps;
+  const long nwarps = (long)gridDim.x * (NTHREADS / 32), wg = (long)blockIdx.x * (NTHREADS / 32) + warp;
+  long c = total * wg / nwarps;
+  const long c1 = total * (wg + 1) / nwarps;
+  long seg = c / cps, kc = c - seg * cps;
+
+  double acc[MT][MT][2];
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int j = 0; j < MT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  const double* rowp[MT];
+  bool rowok[MT];
+#pragma unroll
+  for (int i = 0; i < MT; ++i) {
+    rowok[i] = (8 * i + g) < p.M;
+    rowp[i] = p.X + (long)(rowok[i] ? 8 * i + g : 0) * p.row_stride + 2 * q;
+  }
+  constexpr int U = 4;
+  while (c < c1) {
+    double2 v[U][MT];
+    double wv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool live = (c + u) < c1;
+      const long k = kc * 8 + 2 * q;
+      const long off = seg * p.seg_stride + kc * 8;
+      wv[u] = (live && p.w) ? __ldg(p.w + seg) : 1.0;
+#pragma unroll
+      for (int i = 0; i < MT; ++i) {
+        double2 t = make_double2(0.0, 0.0);
+        if (live && rowok[i]) {
+          if (k + 1 < p.seglen)
+            t = __ldg(reinterpret_cast<const double2*>(rowp[i] + off));
+          else if (k < p.seglen)
+            t.x = __ldg(rowp[i] + off);
+        }
+        v[u][i] = t;
+      }
+      if (++kc == cps) {
+        kc = 0;
+        ++seg;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+#pragma unroll
+      for (int i = 0; i < MT; ++i) {
+        const double a0 = v[u][i].x * wv[u], a1 = v[u][i].y * wv[u];
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+          dmma884(acc[i][j][0], acc[i][j][1], a0, v[u][j].x);
+          dmma884(acc[i][j][0], acc[i][j][1], a1, v[u][j].y);
+        }
+      }
+    }
+    c += U;
+  }
+  // cross-warp reduction (fixed order) -> one 32x32 partial per CTA; only lower 8x8 tiles are meaningful
+  double* mine = red + warp * 1024;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double2 o = make_double2(0.0, 0.0);
+      if (i < MT && j <= i && j < MT) o = make_double2(acc[i < MT ? i : 0][j < MT ? j : 0][0], acc[i < MT ? i : 0][j < MT ? j : 0][1]);
+      *reinterpret_cast<double2*>(mine + (8 * i + g) * 32 + 8 * j + 2 * q) = o;
+    }
+  __syncthreads();
+  double* out = p.ws + (long)blockIdx.x * 1024;
+  for (int e = tid; e < 1024; e += NTHREADS) {
+    double sacc = 0.0;
+#pragma unroll
+    for (int w8 = 0; w8 < NTHREADS / 32; ++w8) sacc += red[w8 * 1024 + e];
+    out[e] = sacc;
+  }
+}
+
+__global__ void wsyrk_small_reduce_kernel(const double* __restrict__ ws, int nparts, int M, double* __restrict__ C,
+                                          long ldc) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 1024) return;
+  const int r = e >> 5, cc = e & 31;
+  if (r >= M || cc >= M) return;
+  const int es = ((r >> 3) >= (cc >> 3)) ? e : (cc * 32 + r);  // upper tiles: mirror of the computed lower tile
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int pidx = 0;
+  for (; pidx + 4 <= nparts; pidx += 4) {
+    s0 += ws[(long)pidx * 1024 + es];
+    s1 += ws[(long)(pidx + 1) * 1024 + es];
+    s2 += ws[(long)(pidx + 2) * 1024 + es];
+    s3 += ws[(long)(pidx + 3) * 1024 + es];
+  }
+  for (; pidx < nparts; ++pidx) s0 += ws[(long)pidx * 1024 + es];
+  C[(long)r * ldc + cc] = (s0 + s1) + (s2 + s3);
+}
+
+static int syrk_small_ctas() { return 2 * gp_num_sms(); }
+
 static int syrk_plan(int M, int nseg, int seglen, int& bmn, int& tiles_1d, int& kbps, long& total_kb, int& nsplit) {
   bmn = (M <= 32) ? 32 : 128;
   tiles_1d = (M + bmn - 1) / bmn;
   const long ntiles = (long)tiles_1d * (tiles_1d + 1) / 2;
   kbps = (seglen + BK - 1) / BK;
   total_kb = (long)nseg * kbps;
-  const int sms = gp_num_sms();
-  const long ctas_target = (bmn == 32) ? 6L * sms : 2L * sms;
-  long ns = (ctas_target + ntiles - 1) / ntiles;
+  // whole waves: ntiles * nsplit <= 2 CTAs-worth per SM (1 resident CTA/SM -> 2 full waves, no ragged tail)
+  long ns = (2L * gp_num_sms()) / ntiles;
   const long min_kb = 8;  // at least 8 k-blocks per split
   if (ns > total_kb / min_kb) ns = total_kb / min_kb;
   if (ns < 1) ns = 1;
@@ -355,6 +476,7 @@ long gpcsd_wsyrk_ws_doubles(int M, int nseg, int seglen) {
   int bmn, t1, kbps, nsplit;
   long total;
   syrk_plan(M, nseg, seglen, bmn, t1, kbps, total, nsplit);
+  if (bmn == 32) return (long)syrk_small_ctas() * 1024;
   return (long)nsplit * ((long)t1 * (t1 + 1) / 2) * bmn * bmn;
 }
 
@@ -372,14 +494,24 @@ int gpcsd_wsyrk(int M, int nseg, int seglen, const double* X, long row_stride, l
   const long ntiles = (long)p.tiles_1d * (p.tiles_1d + 1) / 2;
   dim3 grid((unsigned)ntiles, (unsigned)p.nsplit);
   if (bmn == 32) {
-    constexpr int STAGES = 6;
-    const size_t bytes = (size_t)2 * STAGES * 32 * KMAJ_LD * sizeof(double);
-    auto kern = wsyrk_kernel<32, 8, 16, STAGES, 4>;
+    const int mt = (M + 7) / 8, nct = syrk_small_ctas();
+    const size_t bytes = (size_t)(NTHREADS / 32) * 1024 * sizeof(double);
     static bool attr = false;
-    if (!attr) { GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)); attr = true; }
-    kern<<<grid, NTHREADS, bytes, st>>>(p);
+    if (!attr) {
+      GP_CUDA(cudaFuncSetAttribute(wsyrk_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+      GP_CUDA(cudaFuncSetAttribute(wsyrk_small_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+      GP_CUDA(cudaFuncSetAttribute(wsyrk_small_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+      GP_CUDA(cudaFuncSetAttribute(wsyrk_small_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+      attr = true;
+    }
+    switch (mt) {
+      case 1: wsyrk_small_kernel<1><<<nct, NTHREADS, bytes, st>>>(p); break;
+      case 2: wsyrk_small_kernel<2><<<nct, NTHREADS, bytes, st>>>(p); break;
+      case 3: wsyrk_small_kernel<3><<<nct, NTHREADS, bytes, st>>>(p); break;
+      default: wsyrk_small_kernel<4><<<nct, NTHREADS, bytes, st>>>(p); break;
+    }
     GP_CUDA(cudaGetLastError());
-    wsyrk_reduce_kernel<32><<<dim3(4, (unsigned)ntiles), 256, 0, st>>>(ws, p.nsplit, p.tiles_1d, M, C, ldc);
+    wsyrk_small_reduce_kernel<<<4, 256, 0, st>>>(ws, nct, M, C, ldc);
   } else {
     constexpr int STAGES = 4;
     const size_t bytes = (size_t)2 * STAGES * 128 * KMAJ_LD * sizeof(double);

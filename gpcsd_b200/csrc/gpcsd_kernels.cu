@@ -282,7 +282,9 @@ static int dot_blocks(long n) {
 // ------------------------------------------------------------------------------------------------
 // cuSOLVER
 // ------------------------------------------------------------------------------------------------
-static cusolverDnHandle_t g_solver = nullptr;
+// one handle per host thread: evaluations of independent models may run concurrently on separate
+// streams / threads (multi-start restarts, the two probes of the auditory configuration)
+static thread_local cusolverDnHandle_t g_solver = nullptr;
 static int solver_handle(cusolverDnHandle_t* h) {
   if (!g_solver) {
     cusolverStatus_t s = cusolverDnCreate(&g_solver);
