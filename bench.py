@@ -162,7 +162,7 @@ def workload_config(n_gpus):
 # ----------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------
-def make_models(device, world, torch):
+def make_models(device, world, torch, groups=None):
     """Two GPCSD1D models (one per probe) set up like fit_gpcsd_baseline.py:80-89, with model-matched
     synthetic LFP generated on the device (generator only; not part of the measured path)."""
     from gpcsd_b200.covariances import GPCSD1DSpatialCovSE, GPCSDTemporalCovMatern, GPCSDTemporalCovSE
@@ -181,7 +181,7 @@ def make_models(device, world, torch):
         sig_pri = [GPCSDHalfNormalPrior(0.1) for _ in range(NX)]
         placeholder = np.zeros((NX, NT, 1))
         m = GPCSD1D(placeholder, x, t, a=A_LO, b=B_HI, ngl=NGL, spatial_cov=spatial_cov, temporal_cov_list=[se, mat],
-                    sig2n_prior=sig_pri, distributed=(world > 1))
+                    sig2n_prior=sig_pri, distributed=(groups[probe] if world > 1 else False))
         m.lfp_is_local = world > 1
         m.R['value'] = th["R"]
         spatial_cov.params['ell']['value'] = th["ell"]
@@ -251,11 +251,15 @@ def run_gpu(args):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+        import datetime
+        dist.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(seconds=180))
     import __graft_entry__ as ge
     ge.ensure_built()
 
-    models = make_models(device, world, torch)
+    # one communicator per probe: the two probes' evaluations run on separate host threads, and collectives
+    # issued from different threads on ONE communicator could be ordered differently on different ranks
+    groups = [dist.new_group(ranks=list(range(world))) for _ in range(NPROBES)] if world > 1 else None
+    models = make_models(device, world, torch, groups)
     K, W = args.steps, max(args.warmup, 3)
     thetas = [theta_sequence(m, 2 * (K + W), 500 + p) for p, m in enumerate(models)]
 
@@ -317,7 +321,8 @@ def run_gpu(args):
     torch.cuda.synchronize()
     timed(step_resident, W, 0)
     if args.profile_step:
-        # one steady-state step between cudaProfilerStart/Stop for `ncu --profile-from-start off`
+        # one steady-state SERIAL step between cudaProfilerStart/Stop for `ncu --profile-from-start off`
+        args.serial = True
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
         step_resident(W)
@@ -327,21 +332,30 @@ def run_gpu(args):
             print(json.dumps({"profile_step": "done"}))
         return
     engines = [m._get_engine() for m in models]
-    for e in engines:
-        e.timers = {"gpcsd_project_quad": [], "gpcsd_wsyrk": [], "gpcsd_eigh": [], "gpcsd_dgemm": []}
-        e.n_launches = 0
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    # pass 1 (headline): the two probes evaluated concurrently
+    for e in engines:
+        e.n_launches = 0
     ms_total = timed(step_resident, K, W)
-    clocks = sampler.stop() if rank == 0 else None
     launches = sum(e.n_launches for e in engines)
+    # pass 2: same K steps with the probes one after the other and CUDA events around the dominant kernels
+    # (per-kernel durations are only meaningful without a second stream competing for the SMs)
+    concurrent = not args.serial
+    args.serial = True
+    timed(step_resident, 2, 0)                              # warm the main thread's cuSOLVER handle
+    for e in engines:
+        e.timers = {"gpcsd_project_quad": [], "gpcsd_wsyrk": [], "gpcsd_eigh": [], "gpcsd_dgemm": []}
+    ms_serial = timed(step_resident, K, W)
+    clocks = sampler.stop() if rank == 0 else None
     kt = {}
     for name in engines[0].timers:
         d = [a.elapsed_time(b) for e in engines for (a, b) in e.timers[name]]
         kt[name] = (float(np.mean(d)) if d else 0.0, len(d))
     for e in engines:
         e.timers = None
+    args.serial = not concurrent
     # ---- end-to-end arm
     timed(step_e2e, W, K + W)
     ms_e2e = timed(step_e2e, K, K + 2 * W)
@@ -363,7 +377,8 @@ def run_gpu(args):
             except Exception:
                 traffic = None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms_total / K, "value_serial": evals_per_step * K / (ms_serial * 1e-3),
+                "ms_per_step_serial": ms_serial / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": workload_config(world),
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K,
@@ -375,6 +390,7 @@ def run_gpu(args):
                              "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                              "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                              "algorithmic_flops_per_launch": algo_flops, "avg_launch_ms": dur_ms,
+                             "timed_in": "serial pass (value_serial): CUDA events on the launching stream around every launch",
                              "peak_source": "in-run cuBLAS DGEMM 4096^3 best-of-5 (FP64; MEASURED_PEAKS.json has only "
                                             "HBM and bf16); DMMA issue-rate microbenchmark: 37.0 TFLOP/s"},
                 "kernel_ms": {k: {"avg_ms": v[0], "calls": v[1]} for k, v in kt.items()},

@@ -179,6 +179,9 @@ class GPCSDModelBase:
     # ------------------------------------------------------------------ fit
     def _fit(self, n_restarts, method, fix_R, verbose, options):
         bounds = self._bounds()
+        options = dict(options)
+        if method == 'L-BFGS-B' and not options.get('disp', False):
+            options.pop('disp', None)       # the reference passes disp=False; newer scipy warns on the key
         nll_values, params, term_msg = [], [], []
         for _ in tqdm(range(n_restarts), desc="Restarts"):
             tparams0 = self._sample_tparams0(fix_R)

@@ -1,0 +1,158 @@
+"""Drop-in API on the GPU (-m gpu): the reference-facing classes produce the reference's numbers."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import relerr
+from test_gpu_engine import _model_from_golden_1d, _model_from_golden_2d, grad_tol
+
+pytestmark = pytest.mark.gpu
+
+
+def _api_model_1d(g, vec=False):
+    from gpcsd_b200.covariances import GPCSDTemporalCovMatern, GPCSDTemporalCovSE
+    from gpcsd_b200.gpcsd1d import GPCSD1D
+    from gpcsd_b200.priors import GPCSDHalfNormalPrior
+    np.random.seed(0)
+    pri = [GPCSDHalfNormalPrior(0.1) for _ in range(24)] if vec else None
+    m = GPCSD1D(g["lfp"], g["x"], g["t"], temporal_cov_list=[GPCSDTemporalCovSE(g["t"]), GPCSDTemporalCovMatern(g["t"])],
+                sig2n_prior=pri)
+    m.R['value'] = float(g["R"])
+    m.spatial_cov.params['ell']['value'] = float(g["ell"])
+    for tc, e, s in zip(m.temporal_cov_list, g["t_ell"], g["t_sigma2"]):
+        tc.params['ell']['value'], tc.params['sigma2']['value'] = float(e), float(s)
+    m.sig2n['value'] = np.array(g["sig2n"]) if vec else float(g["sig2n"])
+    return m
+
+
+def _api_model_2d(g):
+    from gpcsd_b200.gpcsd2d import GPCSD2D
+    np.random.seed(0)
+    m = GPCSD2D(g["lfp"], g["x"], g["t"], ngl1=int(g["ngl1"]), ngl2=int(g["ngl2"]), eps=float(g["eps"]))
+    m.R['value'] = float(g["R"])
+    m.spatial_cov.params['ell1']['value'], m.spatial_cov.params['ell2']['value'] = float(g["ell1"]), float(g["ell2"])
+    for tc, e, s in zip(m.temporal_cov_list, g["t_ell"], g["t_sigma2"]):
+        tc.params['ell']['value'], tc.params['sigma2']['value'] = float(e), float(s)
+    m.sig2n['value'] = float(g["sig2n"])
+    return m
+
+
+@pytest.mark.parametrize("name,vec", [("gpcsd1d_cfg1", False), ("gpcsd1d_vecnoise", True)])
+def test_gpcsd1d_api_against_reference_golden(cuda_lib, golden_dir, name, vec):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    m = _api_model_1d(g, vec)
+    ll = m.loglik()
+    assert abs(float(ll) - float(g["loglik"])) < 1e-9 * abs(float(g["loglik"]))
+    # covariance helper API (device kernels, host arrays out) vs reference matrices
+    sc = m.spatial_cov
+    assert relerr(sc.compKphi_1d(float(g["R"])), g["Ks"]) < 1e-12
+    assert relerr(sc.compKphig_1d(g["z"], float(g["R"])), g["Kphig"]) < 1e-12
+    assert relerr(sc.compKphi_1d(float(g["R"]), xp=g["z"]), g["Kphi_z"]) < 1e-12
+    assert relerr(sc.compute_Ks(), g["Ks_csd"]) < 1e-14
+    assert relerr(m.temporal_cov_list[0].compute_Kt(), g["Kt_se"]) < 1e-14
+    assert relerr(m.temporal_cov_list[1].compute_Kt(), g["Kt_matern"]) < 1e-14
+    z, tt = g["z"], g["t"]
+    m.predict(z, tt, type="both")
+    npred = g["csd_pred"].shape[2]
+    assert m.csd_pred.shape == (22, g["t"].shape[0], g["lfp"].shape[2]) and len(m.csd_pred_list) == 2
+    assert m.x_pred is z and m.t_pred is tt
+    for key in ("csd_pred", "lfp_pred"):
+        assert relerr(getattr(m, key)[:, :, :npred], g[key]) < 1e-6      # vs the reference's dense inverse
+    m.predict(g["z"], g["t"])                                             # default type="csd"
+    assert relerr(m.csd_pred[:, :, :npred], g["csd_pred"]) < 1e-6
+
+
+def test_gpcsd2d_api_against_reference_golden(cuda_lib, golden_dir):
+    g = np.load(os.path.join(golden_dir, "gpcsd2d_small.npz"))
+    m = _api_model_2d(g)
+    assert abs(float(m.loglik()) - float(g["loglik"])) < 1e-9 * abs(float(g["loglik"]))
+    sc = m.spatial_cov
+    assert relerr(sc.compKphi_2d(float(g["R"]), float(g["eps"])), g["Ks"]) < 1e-12
+    assert relerr(sc.compKphig_2d(g["z"], float(g["R"]), float(g["eps"])), g["Kphig"]) < 1e-12
+    assert relerr(sc.compKphi_2d(float(g["R"]), float(g["eps"]), xp=g["z"]), g["Kphi_z"]) < 1e-12
+    assert relerr(sc.compute_Ks(), g["Ks_csd"]) < 1e-14
+    m.predict(g["z"], g["t"], type="both")
+    for key in ("csd_pred", "lfp_pred"):
+        assert relerr(getattr(m, key), g[key]) < 1e-6
+        assert relerr(getattr(m, key + "_list")[0], g[key + "_0"]) < 1e-6
+
+
+def test_obj_fun_and_grad_matches_oracle_objective(cuda_lib, golden_dir):
+    """nll and its log-space gradient (priors + exp transforms, gpcsd1d.py:153-191) vs the oracle's."""
+    from oracle import gpcsd_oracle as O, synth
+    g = np.load(os.path.join(golden_dir, "gpcsd1d_cfg1.npz"))
+    m = _api_model_1d(g)
+    om = _model_from_golden_1d(g)
+    pri = synth.default_priors(om)
+    tp = O.pack_tparams(om) + 0.05
+    f, gr = m.obj_fun_and_grad(tp)
+    f_o, gr_o = O.obj_and_grad(om, g["lfp"], tp, pri)
+    assert abs(f - f_o) < 1e-9 * abs(f_o)
+    assert np.max(np.abs(gr - gr_o) / np.maximum(np.abs(gr_o), 1e-9 * np.max(np.abs(gr_o)))) < 1e-8
+    assert abs(m.obj_fun(tp) - f_o) < 1e-9 * abs(f_o)
+    f2, gr2 = m.obj_fun_and_grad(tp, fix_R=True)
+    assert gr2[0] == 0.0
+
+
+def test_fit_recovers_and_improves(cuda_lib):
+    """fit(): multi-start bounded L-BFGS-B driven by the fused CUDA objective+gradient; the MAP objective
+    at the fitted parameters must be no worse than at the data-generating parameters."""
+    from gpcsd_b200.gpcsd1d import GPCSD1D
+    from oracle import gpcsd_oracle as O, synth
+    x, t = synth.geometry_1d(24, 40)
+    om = synth.model_1d(x, t, sig2n=1e-2)
+    lfp = synth.matched_lfp(om, 30, 11)
+    np.random.seed(2)
+    m = GPCSD1D(lfp, x, t)
+    tp_true = O.pack_tparams(om)
+    f_true = m.obj_fun(tp_true)
+    m.fit(n_restarts=2, options={'maxiter': 60, 'disp': False, 'gtol': 1e-5, 'ftol': 1e7 * np.finfo(float).eps})
+    tp_fit = np.log(np.array([m.R['value'] / 100, m.spatial_cov.params['ell']['value'] / 100] +
+                             [v for tc in m.temporal_cov_list for v in (tc.params['ell']['value'], tc.params['sigma2']['value'])] +
+                             [m.sig2n['value']]))
+    f_fit = m.obj_fun(tp_fit)
+    assert np.isfinite(f_fit) and f_fit <= f_true + 1e-6 * abs(f_true)
+    assert 0.3 * 1e-2 < m.sig2n['value'] < 3e-2            # noise variance is well identified
+
+
+def test_sample_prior_and_comp_eig_D(cuda_lib):
+    from gpcsd_b200.gpcsd1d import GPCSD1D
+    from gpcsd_b200.utility_functions import comp_eig_D
+    from oracle import gpcsd_oracle as O
+    np.random.seed(3)
+    x = np.linspace(0, 2300, 24)[:, None]
+    t = np.linspace(0, 30, 31)[:, None]
+    m = GPCSD1D(np.zeros((24, 31, 1)), x, t)
+    m.spatial_cov.params['ell']['value'] = 300.0
+    np.random.seed(7)
+    csd = m.sample_prior(5)
+    assert csd.shape == (24, 31, 5) and np.all(np.isfinite(csd))
+    # same draws through the reference's formula on the host
+    Kt = sum(O.compute_Kt(tc.KIND, tc.params['ell']['value'], tc.params['sigma2']['value'], t) for tc in m.temporal_cov_list)
+    Lt = np.linalg.cholesky(Kt)
+    Ls = np.linalg.cholesky(O.compute_Ks_1d(x, 300.0) + 1e-8 * np.eye(24))
+    np.random.seed(7)
+    ref = np.stack([Ls @ np.random.normal(0, 1, (24, 31)) @ Lt.T for _ in range(5)], axis=2)
+    # cond(Ks_csd + 1e-8 I) ~ 1e8: round-off level differences in Ks are amplified by the Cholesky factor
+    assert relerr(csd, ref) < 1e-7
+    rng = np.random.default_rng(0)
+    Ks = rng.standard_normal((9, 9)); Ks = Ks @ Ks.T
+    Kt2 = rng.standard_normal((13, 13)); Kt2 = Kt2 @ Kt2.T
+    sv = rng.uniform(0.1, 0.4, 9)
+    for sig in (0.3, sv):
+        Qs, Qt, D = comp_eig_D(Ks, Kt2, sig)
+        _, _, D_o, ls, lt = O.comp_eig_D(Ks, Kt2, sig)
+        assert relerr(D, D_o) < 1e-12 and D.shape == (9 * 13,)
+        assert relerr((Qs * ls) @ Qs.T, Ks) < 1e-12 and relerr((Qt * lt) @ Qt.T, Kt2) < 1e-12
+
+
+def test_update_lfp_reuploads(cuda_lib, golden_dir):
+    g = np.load(os.path.join(golden_dir, "gpcsd1d_lownoise.npz"))
+    m = _api_model_1d(g)
+    ll1 = float(m.loglik())
+    m.update_lfp(2.0 * g["lfp"], g["t"])
+    ll2 = float(m.loglik())
+    assert abs(ll1 - float(g["loglik"])) < 1e-9 * abs(ll1) and ll2 != ll1
+    m.update_lfp(g["lfp"], g["t"])
+    assert abs(float(m.loglik()) - ll1) < 1e-12 * abs(ll1)
