@@ -5,6 +5,14 @@
 
 namespace gpcsd {
 
+// gpcsd_tma.cu: persistent TMA + mbarrier warp-specialised kernels (M > 32)
+int tma_gemm(int transB, int M, int N, int K, const double* A, long lda, long sA, const double* B, long ldb, long sB,
+             double* C, long ldc, long sC, int batch, const double* rD, long ldrd, double* partials, int epi_quad,
+             cudaStream_t st);
+int tma_gemm_ctas(int M, int N, int batch);
+int tma_wsyrk(int M, int nseg, int seglen, const double* X, long row_stride, long seg_stride, const double* w, double* C,
+              long ldc, double* ws, int nsplit, int tiles_1d, int kbps, long total_kb, cudaStream_t st);
+
 struct GemmArgs {
   const double* A;
   const double* B;
@@ -189,8 +197,9 @@ static int dispatch_gemm(GemmArgs& p, int transB, int batch, cudaStream_t st) {
     if (transB) return launch_gemm<32, 128, 32, 16, 3, true, EPI, 2>(p, batch, st);
     return launch_gemm<32, 128, 32, 16, 3, false, EPI, 2>(p, batch, st);
   }
-  if (transB) return launch_gemm<128, 128, 64, 32, 4, true, EPI, 1>(p, batch, st);
-  return launch_gemm<128, 128, 64, 32, 4, false, EPI, 1>(p, batch, st);
+  if (batch > 65535) return gp_fail("gemm batch too large");
+  return tma_gemm(transB, p.M, p.N, p.K, p.A, p.lda, p.sA, p.B, p.ldb, p.sB, p.C, p.ldc, p.sC, batch, p.rD, p.ldrd,
+                  p.partials, EPI == EPI_QUAD, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -451,9 +460,9 @@ int gpcsd_dgemm(int transB, int M, int N, int K, const double* A, long lda, long
 }
 
 static long project_quad_ctas(int nx, int nt, int ntrials) {
-  const int bm = (nt <= 32) ? 32 : 128;
-  const long mt = (nt + bm - 1) / bm, ntl = ((long)ntrials + 127) / 128;
-  return mt * ntl * nx;
+  if (nt > 32) return tma_gemm_ctas(nt, ntrials, nx);   // persistent kernel: one partial pair per CTA
+  const long ntl = ((long)ntrials + 127) / 128;
+  return ntl * nx;
 }
 
 long gpcsd_project_quad_ws_doubles(int nx, int nt, int ntrials) { return 2 * project_quad_ctas(nx, nt, ntrials) + 2; }
@@ -513,14 +522,7 @@ int gpcsd_wsyrk(int M, int nseg, int seglen, const double* X, long row_stride, l
     GP_CUDA(cudaGetLastError());
     wsyrk_small_reduce_kernel<<<4, 256, 0, st>>>(ws, nct, M, C, ldc);
   } else {
-    constexpr int STAGES = 4;
-    const size_t bytes = (size_t)2 * STAGES * 128 * KMAJ_LD * sizeof(double);
-    auto kern = wsyrk_kernel<128, 64, 32, STAGES, 1>;
-    static bool attr = false;
-    if (!attr) { GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)); attr = true; }
-    kern<<<grid, NTHREADS, bytes, st>>>(p);
-    GP_CUDA(cudaGetLastError());
-    wsyrk_reduce_kernel<128><<<dim3(64, (unsigned)ntiles), 256, 0, st>>>(ws, p.nsplit, p.tiles_1d, M, C, ldc);
+    return tma_wsyrk(M, nseg, seglen, X, row_stride, seg_stride, w, C, ldc, ws, p.nsplit, p.tiles_1d, p.kbps, p.total_kb, st);
   }
   GP_CUDA(cudaGetLastError());
   return 0;

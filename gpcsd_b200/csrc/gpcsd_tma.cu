@@ -1,0 +1,514 @@
+// Persistent, warp-specialised FP64 DMMA GEMM / weighted SYRK for sm_100a with TMA-staged tiles.
+//
+//   warp 8      : producer -- one elected lane issues cp.async.bulk.tensor (TMA) loads into a ring of
+//                 128B-swizzled shared-memory stages, signalled through mbarriers (full / empty)
+//   warps 0..7  : consumers -- LDS + DMMA.8x8x4 on a 128x128 CTA tile (warp tile 64x32), no CTA-wide barrier
+//                 in the main loop; epilogue of tile i overlaps the producer's prefetch of tile i+1
+//   grid        : one CTA per SM, static round-robin over tiles (m-tiles fastest so the CTAs sharing a B
+//                 column panel run together and the panel is fetched from HBM once)
+//
+// Shared-memory layout (SWIZZLE_128B, box inner extent = 16 doubles = 128 B):
+//   K-major tile [rows][16 k]:  element (r, k) at  r*128 + (((k>>1) ^ (r&7)) << 4) + (k&1)*8
+//   N-major tile = 8 boxes [16 k][16 n]: element (k, n) at (n>>4)*2048 + k*128 + ((((n&15)>>1) ^ (k&7)) << 4) + (n&1)*8
+// Fragment mapping (lane = 4g + q), chosen so that every shared-memory wavefront is conflict-free:
+//   * MMA k-slot q of k-step kk reads memory k = 8*(kk>>1) + 2q + (kk&1)   (any k permutation is legal as long
+//     as A and B agree): a K-major operand then needs ONE LDS.128 per row-tile for two k-steps (kk even -> .x,
+//     kk odd -> .y), an N-major operand one LDS.64 per (column-tile, k-step);
+//   * MMA row/column index g of a K-major operand reads memory row 8*tile + perm(g), perm(g) = (g>>1) + 4*(g&1),
+//     so the 8 lanes of each LDS.128 quarter-warp touch rows {0,4} / {1,5} / {2,6} / {3,7} (mod 8) -> 8 distinct
+//     16-byte chunks after the XOR swizzle.
+#include <cuda.h>
+
+#include "common.h"
+#include "dmma_gemm.cuh"
+
+namespace gpcsd {
+
+constexpr int T_BM = 128, T_BN = 128, T_WM = 64, T_WN = 32;
+constexpr int T_STAGES = 6;
+constexpr int T_CONSUMERS = 8;                       // consumer warps
+constexpr int T_THREADS = 32 * (T_CONSUMERS + 1);    // + 1 producer warp
+constexpr int T_TILE_BYTES = T_BM * BK * 8;          // 16 KiB per operand per stage
+constexpr int T_STAGE_BYTES = 2 * T_TILE_BYTES;
+constexpr size_t T_SMEM_BYTES = (size_t)T_STAGES * T_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra.uni WAIT_DONE;\n"
+      "bra.uni WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ double2 lds128(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ double lds64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ int perm8(int g) { return (g >> 1) + 4 * (g & 1); }
+
+// one 16-deep k-block of a 64x32 warp tile.
+//   aBase/bBase: shared-memory byte addresses of the stage's A / B tiles
+//   B_KMAJOR: B tile stored [n rows][16 k] (NT / SYRK) else 8 boxes [16 k][16 n] (NN)
+template <bool B_KMAJOR, bool SCALE_A>
+__device__ __forceinline__ void tma_mma_kblock(uint32_t aBase, uint32_t bBase, double (&acc)[8][4][2], int wm, int wn, int g,
+                                               int q, double ascale) {
+  const int pg = perm8(g);
+  // (row & 7) == pg for every row tile (rows advance by 8), so the swizzle XOR term is loop-invariant
+  const uint32_t aRow = aBase + (wm * T_WM + pg) * 128;
+  const uint32_t bRow = bBase + (wn * T_WN + pg) * 128;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {  // k-step pairs (2h, 2h+1)
+    const uint32_t kch = (uint32_t)(((4 * h + q) ^ pg) << 4);
+    double b0[4], b1[4];
+    if (B_KMAJOR) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double2 t = lds128(bRow + j * 1024 + kch);
+        b0[j] = t.x;
+        b1[j] = t.y;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = wn * T_WN + 8 * j + g;
+        const uint32_t box = bBase + (n >> 4) * 2048 + (n & 1) * 8;
+        const int c = (n & 15) >> 1;
+        const int k0 = 8 * h + 2 * q, k1 = k0 + 1;
+        b0[j] = lds64(box + k0 * 128 + ((c ^ (k0 & 7)) << 4));
+        b1[j] = lds64(box + k1 * 128 + ((c ^ (k1 & 7)) << 4));
+      }
+    }
+#pragma unroll
+    for (int ih = 0; ih < 2; ++ih) {  // two halves of the 8 row tiles: keeps only 4 A fragments live
+      double2 af[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        af[i] = lds128(aRow + (4 * ih + i) * 1024 + kch);
+        if (SCALE_A) {
+          af[i].x *= ascale;
+          af[i].y *= ascale;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[4 * ih + i][j][0], acc[4 * ih + i][j][1], af[i].x, b0[j]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[4 * ih + i][j][0], acc[4 * ih + i][j][1], af[i].y, b1[j]);
+    }
+  }
+}
+
+struct TmaGemmArgs {
+  double* C;
+  long ldc, sC;
+  int M, N, K, batch;
+  int m_tiles, n_tiles;
+  int a_batched;      // 0: A shared by all batches
+  const double* rD;   // EPI_QUAD
+  long ldrd;
+  double* partials;   // [gridDim.x][2]
+};
+
+constexpr int TEPI_STORE = 0, TEPI_QUAD = 1;
+
+__device__ __forceinline__ void pipeline_setup(uint8_t*& tiles, uint64_t*& full, uint64_t*& empty) {
+  extern __shared__ uint8_t raw_smem[];
+  const uintptr_t base = (reinterpret_cast<uintptr_t>(raw_smem) + 1023) & ~uintptr_t(1023);
+  tiles = reinterpret_cast<uint8_t*>(base);
+  full = reinterpret_cast<uint64_t*>(tiles + (size_t)T_STAGES * T_STAGE_BYTES);
+  empty = full + T_STAGES;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < T_STAGES; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, T_CONSUMERS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+}
+
+// C_b = A_b * op(B_b): persistent tiles, TMA producer + 8 DMMA consumer warps.
+template <bool BT, int EPI>
+__global__ void __launch_bounds__(T_THREADS, 1)
+    tma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TmaGemmArgs p) {
+  uint8_t* tiles;
+  uint64_t *full, *empty;
+  pipeline_setup(tiles, full, empty);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = (p.K + BK - 1) / BK;
+  const long ntiles = (long)p.m_tiles * p.n_tiles * p.batch;
+
+  if (warp == T_CONSUMERS) {
+    // ------------------------------------------------------------------ producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int mt = (int)(t % p.m_tiles);
+        const long r = t / p.m_tiles;
+        const int nt_ = (int)(r % p.n_tiles), b = (int)(r / p.n_tiles);
+        const int m0 = mt * T_BM, n0 = nt_ * T_BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % T_STAGES;
+          mbar_wait(empty + s, ((it / T_STAGES) & 1) ^ 1);
+          mbar_expect_tx(full + s, T_STAGE_BYTES);
+          uint8_t* sa = tiles + (size_t)s * T_STAGE_BYTES;
+          uint8_t* sb = sa + T_TILE_BYTES;
+          tma_load_3d(sa, &tmA, full + s, kb * BK, m0, p.a_batched ? b : 0);
+          if (BT) {
+            tma_load_3d(sb, &tmB, full + s, kb * BK, n0, b);
+          } else {
+#pragma unroll
+            for (int x = 0; x < 8; ++x) tma_load_3d(sb + x * 2048, &tmB, full + s, n0 + 16 * x, kb * BK, b);
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------- consumers
+  const int g = lane >> 2, q = lane & 3;
+  const int wm = warp & 1, wn = warp >> 1;   // 2 x 4 warps of 64 x 32
+  const int pg = perm8(g);
+  double quad = 0.0, bsq = 0.0;
+  uint32_t it = 0;
+  for (long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int mt = (int)(t % p.m_tiles);
+    const long r = t / p.m_tiles;
+    const int nt_ = (int)(r % p.n_tiles), b = (int)(r / p.n_tiles);
+    const int m0 = mt * T_BM, n0 = nt_ * T_BN;
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int kb = 0; kb < nkb; ++kb, ++it) {
+      const int s = it % T_STAGES;
+      mbar_wait(full + s, (it / T_STAGES) & 1);
+      const uint32_t sa = smem_u32(tiles + (size_t)s * T_STAGE_BYTES);
+      tma_mma_kblock<BT, false>(sa, sa + T_TILE_BYTES, acc, wm, wn, g, q, 1.0);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + s);
+    }
+    // epilogue (overlaps the producer's prefetch of the next tile)
+    double* C = p.C + (long)b * p.sC;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int m = m0 + wm * T_WM + 8 * i + pg;
+      if (m >= p.M) continue;
+      double rr = 1.0;
+      if (EPI == TEPI_QUAD) rr = __ldg(p.rD + (long)b * p.ldrd + m);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        double v0 = acc[i][j][0], v1 = acc[i][j][1];
+        if (EPI == TEPI_QUAD) {
+          v0 *= rr;
+          v1 *= rr;
+        }
+        if (BT) {
+          const long na = (long)n0 + wn * T_WN + 8 * j + q, nb = na + 4;
+          if (na < p.N) C[(long)m * p.ldc + na] = v0;
+          if (nb < p.N) C[(long)m * p.ldc + nb] = v1;
+        } else {
+          const long n = (long)n0 + wn * T_WN + 8 * j + 2 * q;
+          if (n >= p.N) continue;
+          const bool two = (n + 1 < p.N);
+          if (EPI == TEPI_QUAD) {
+            quad += acc[i][j][0] * v0;
+            bsq += v0 * v0;
+            if (two) {
+              quad += acc[i][j][1] * v1;
+              bsq += v1 * v1;
+            }
+          }
+          double* dst = C + (long)m * p.ldc + n;
+          if (two)
+            *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+          else
+            *dst = v0;
+        }
+      }
+    }
+  }
+  if (EPI == TEPI_QUAD) {
+    // consumer-only reduction (named barrier 1, 256 threads): fixed order -> deterministic
+    __shared__ double red[2][T_CONSUMERS];
+    quad = warp_sum(quad);
+    bsq = warp_sum(bsq);
+    if (lane == 0) {
+      red[0][warp] = quad;
+      red[1][warp] = bsq;
+    }
+    asm volatile("bar.sync 1, %0;\n" ::"n"(32 * T_CONSUMERS) : "memory");
+    if (threadIdx.x == 0) {
+      double s0 = 0.0, s1 = 0.0;
+      for (int w = 0; w < T_CONSUMERS; ++w) {
+        s0 += red[0][w];
+        s1 += red[1][w];
+      }
+      p.partials[2 * blockIdx.x] = s0;
+      p.partials[2 * blockIdx.x + 1] = s1;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// segment-weighted split-K SYRK (lower-triangular 128x128 tiles), X viewed as the 3-D tensor {k, row, seg}
+// ------------------------------------------------------------------------------------------------
+struct TmaSyrkArgs {
+  const double* w;
+  int M, nseg, seglen;
+  int kbps;       // k-blocks per segment
+  long total_kb;  // nseg * kbps
+  int nsplit, tiles_1d;
+  int seg_middle; // tensor-map dim order {k, seg, row} instead of {k, row, seg}
+  double* ws;     // [nsplit][ntiles][128*128] in fragment order
+};
+
+__global__ void __launch_bounds__(T_THREADS, 1)
+    tma_wsyrk_kernel(const __grid_constant__ CUtensorMap tmX, TmaSyrkArgs p) {
+  uint8_t* tiles;
+  uint64_t *full, *empty;
+  pipeline_setup(tiles, full, empty);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int t = blockIdx.x, tm = 0;
+  while ((tm + 1) * (tm + 2) / 2 <= t) ++tm;
+  const int tn = t - tm * (tm + 1) / 2;
+  const bool diag = (tm == tn);
+  const int split = blockIdx.y;
+  const long f0 = p.total_kb * split / p.nsplit, f1 = p.total_kb * (split + 1) / p.nsplit;
+  const int nkb = (int)(f1 - f0);
+
+  if (warp == T_CONSUMERS) {
+    if (lane == 0) {
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % T_STAGES;
+        const long f = f0 + it;
+        const int seg = (int)(f / p.kbps);
+        const int k0 = (int)(f - (long)seg * p.kbps) * BK;
+        mbar_wait(empty + s, ((it / T_STAGES) & 1) ^ 1);
+        mbar_expect_tx(full + s, diag ? T_TILE_BYTES : T_STAGE_BYTES);
+        uint8_t* sa = tiles + (size_t)s * T_STAGE_BYTES;
+        if (p.seg_middle) {
+          tma_load_3d(sa, &tmX, full + s, k0, seg, tm * T_BM);
+          if (!diag) tma_load_3d(sa + T_TILE_BYTES, &tmX, full + s, k0, seg, tn * T_BN);
+        } else {
+          tma_load_3d(sa, &tmX, full + s, k0, tm * T_BM, seg);
+          if (!diag) tma_load_3d(sa + T_TILE_BYTES, &tmX, full + s, k0, tn * T_BN, seg);
+        }
+      }
+    }
+    return;
+  }
+  const int g = lane >> 2, q = lane & 3;
+  const int wm = warp & 1, wn = warp >> 1;
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  for (int it = 0; it < nkb; ++it) {
+    const int s = it % T_STAGES;
+    const double wgt = p.w ? __ldg(p.w + (f0 + it) / p.kbps) : 1.0;
+    mbar_wait(full + s, (it / T_STAGES) & 1);
+    const uint32_t sa = smem_u32(tiles + (size_t)s * T_STAGE_BYTES);
+    if (p.w)
+      tma_mma_kblock<true, true>(sa, diag ? sa : sa + T_TILE_BYTES, acc, wm, wn, g, q, wgt);
+    else
+      tma_mma_kblock<true, false>(sa, diag ? sa : sa + T_TILE_BYTES, acc, wm, wn, g, q, 1.0);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + s);
+  }
+  // partial tile in fragment order: fully coalesced double2 stores
+  const long ntiles = (long)p.tiles_1d * (p.tiles_1d + 1) / 2;
+  double* out = p.ws + ((long)split * ntiles + t) * (T_BM * T_BN);
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<double2*>(out + ((((warp * 8 + i) * 4 + j) * 32 + lane) << 1)) = make_double2(acc[i][j][0], acc[i][j][1]);
+}
+
+// sum the split-K partials in fixed order, un-permute the fragment layout, mirror the upper triangle
+__global__ void tma_wsyrk_reduce_kernel(const double* __restrict__ ws, int nsplit, int tiles_1d, int M,
+                                        double* __restrict__ C, long ldc) {
+  const long ntiles = (long)tiles_1d * (tiles_1d + 1) / 2;
+  const int t = blockIdx.y;
+  int tm = 0;
+  while ((tm + 1) * (tm + 2) / 2 <= t) ++tm;
+  const int tn = t - tm * (tm + 1) / 2;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;  // fragment-order element index
+  if (e >= T_BM * T_BN) return;
+  const int v = e & 1, lane = (e >> 1) & 31, j = (e >> 6) & 3, i = (e >> 8) & 7, warp = e >> 11;
+  const int g = lane >> 2, q = lane & 3, wm = warp & 1, wn = warp >> 1;
+  const int r = wm * T_WM + 8 * i + perm8(g), c = wn * T_WN + 8 * j + q + 4 * v;
+  const int m = tm * T_BM + r, n = tn * T_BN + c;
+  if (m >= M || n >= M) return;
+  double s0 = 0.0, s1 = 0.0;
+  int sp = 0;
+  for (; sp + 2 <= nsplit; sp += 2) {
+    s0 += ws[((long)sp * ntiles + t) * (T_BM * T_BN) + e];
+    s1 += ws[((long)(sp + 1) * ntiles + t) * (T_BM * T_BN) + e];
+  }
+  if (sp < nsplit) s0 += ws[((long)sp * ntiles + t) * (T_BM * T_BN) + e];
+  const double s = s0 + s1;
+  C[(long)m * ldc + n] = s;
+  if (tm != tn) C[(long)n * ldc + m] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: tensor-map encoding through the driver entry point (no link-time dependency on libcuda)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 3-D FP64 tensor map: dims {d0 (contiguous), d1, d2}, element strides {s1, s2}, box {b0, b1, b2}; 128B swizzle,
+// zero fill for out-of-range box elements (this is what handles every M / N / K / segment edge).
+static int make_map3(CUtensorMap* m, const double* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1, uint64_t s2,
+                     uint32_t b0, uint32_t b1, uint32_t b2) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return gp_fail("cuTensorMapEncodeTiled entry point not available");
+  if (d1 == 0) d1 = 1;
+  if (d2 == 0) d2 = 1;
+  if (s1 == 0) s1 = (d0 + 1) & ~1ull;                       // unused stride (d1 == 1): any legal value
+  if (s2 == 0) s2 = s1 * d1;                                 // unused stride (d2 == 1)
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {s1 * 8, s2 * 8};
+  cuuint32_t box[3] = {b0, b1, b2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[200];
+    snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed (%d): dims %llu %llu %llu strides %llu %llu", (int)r,
+             (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, (unsigned long long)s1,
+             (unsigned long long)s2);
+    return gp_fail(buf);
+  }
+  return 0;
+}
+
+template <bool BT, int EPI>
+static int launch_tma_gemm(const CUtensorMap& tA, const CUtensorMap& tB, TmaGemmArgs& p, cudaStream_t st) {
+  auto kern = tma_gemm_kernel<BT, EPI>;
+  static bool attr = false;
+  if (!attr) {
+    GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_SMEM_BYTES));
+    attr = true;
+  }
+  const long ntiles = (long)p.m_tiles * p.n_tiles * p.batch;
+  const long grid = ntiles < gp_num_sms() ? ntiles : gp_num_sms();
+  kern<<<(unsigned)grid, T_THREADS, T_SMEM_BYTES, st>>>(tA, tB, p);
+  GP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int tma_gemm_ctas(int M, int N, int batch) {
+  const long ntiles = (long)((M + T_BM - 1) / T_BM) * ((N + T_BN - 1) / T_BN) * batch;
+  return (int)(ntiles < gp_num_sms() ? ntiles : gp_num_sms());
+}
+
+// C_b = A_b op(B_b); epi_quad != 0 fuses the /D + quadratic-form epilogue.  Returns 0 on success.
+int tma_gemm(int transB, int M, int N, int K, const double* A, long lda, long sA, const double* B, long ldb, long sB,
+             double* C, long ldc, long sC, int batch, const double* rD, long ldrd, double* partials, int epi_quad,
+             cudaStream_t st) {
+  CUtensorMap tA, tB;
+  const bool a_batched = (sA != 0 && batch > 1);
+  if (int e = make_map3(&tA, A, K, M, a_batched ? batch : 1, lda, a_batched ? sA : 0, BK, T_BM, 1)) return e;
+  const long sBe = (batch > 1) ? sB : 0;
+  if (transB) {
+    if (int e = make_map3(&tB, B, K, N, batch, ldb, sBe, BK, T_BN, 1)) return e;
+  } else {
+    if (int e = make_map3(&tB, B, N, K, batch, ldb, sBe, 16, BK, 1)) return e;
+  }
+  TmaGemmArgs p{};
+  p.C = C; p.ldc = ldc; p.sC = sC;
+  p.M = M; p.N = N; p.K = K; p.batch = batch;
+  p.m_tiles = (M + T_BM - 1) / T_BM;
+  p.n_tiles = (N + T_BN - 1) / T_BN;
+  p.a_batched = a_batched ? 1 : 0;
+  p.rD = rD; p.ldrd = ldrd; p.partials = partials;
+  if (epi_quad) return launch_tma_gemm<false, TEPI_QUAD>(tA, tB, p, st);
+  if (transB) return launch_tma_gemm<true, TEPI_STORE>(tA, tB, p, st);
+  return launch_tma_gemm<false, TEPI_STORE>(tA, tB, p, st);
+}
+
+int tma_wsyrk(int M, int nseg, int seglen, const double* X, long row_stride, long seg_stride, const double* w, double* C,
+              long ldc, double* ws, int nsplit, int tiles_1d, int kbps, long total_kb, cudaStream_t st) {
+  CUtensorMap tX;
+  // X[m][seg][k] = X + m*row_stride + seg*seg_stride + k.  Outer tensor dims are ordered by increasing stride
+  // (seg_middle: {k, seg, row}; else {k, row, seg}); the box is 16 k x 128 rows x 1 segment either way, so the
+  // shared-memory image is always [128 rows][16 k].
+  const bool seg_middle = (nseg > 1) && (seg_stride < row_stride);
+  if (seg_middle) {
+    if (int e = make_map3(&tX, X, seglen, nseg, M, seg_stride, row_stride, BK, 1, T_BM)) return e;
+  } else {
+    if (int e = make_map3(&tX, X, seglen, M, nseg, row_stride, nseg > 1 ? seg_stride : 0, BK, T_BM, 1)) return e;
+  }
+  TmaSyrkArgs p{};
+  p.w = w; p.M = M; p.nseg = nseg; p.seglen = seglen;
+  p.kbps = kbps; p.total_kb = total_kb; p.nsplit = nsplit; p.tiles_1d = tiles_1d; p.ws = ws;
+  p.seg_middle = seg_middle ? 1 : 0;
+  static bool attr = false;
+  if (!attr) {
+    GP_CUDA(cudaFuncSetAttribute(tma_wsyrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_SMEM_BYTES));
+    attr = true;
+  }
+  const long ntiles = (long)tiles_1d * (tiles_1d + 1) / 2;
+  tma_wsyrk_kernel<<<dim3((unsigned)ntiles, (unsigned)nsplit), T_THREADS, T_SMEM_BYTES, st>>>(tX, p);
+  GP_CUDA(cudaGetLastError());
+  tma_wsyrk_reduce_kernel<<<dim3(T_BM * T_BN / 256, (unsigned)ntiles), 256, 0, st>>>(ws, nsplit, tiles_1d, M, C, ldc);
+  GP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace gpcsd
