@@ -24,10 +24,18 @@
 
 namespace gpcsd {
 
-constexpr int T_BM = 128, T_BN = 128, T_WM = 64, T_WN = 32;
+#ifndef GPCSD_TMA_CONSUMERS
+#define GPCSD_TMA_CONSUMERS 8
+#endif
+constexpr int T_BM = 128, T_BN = 128, T_WN = 32;
 constexpr int T_STAGES = 6;
-constexpr int T_CONSUMERS = 8;                       // consumer warps
-constexpr int T_THREADS = 32 * (T_CONSUMERS + 1);    // + 1 producer warp
+constexpr int T_CONSUMERS = GPCSD_TMA_CONSUMERS;     // consumer warps: 8 (64x32 warp tiles) or 16 (32x32)
+constexpr int T_WARPS_M = T_CONSUMERS / 4;           // warp grid T_WARPS_M x 4
+constexpr int T_WM = T_BM / T_WARPS_M;
+constexpr int T_MT = T_WM / 8;                       // 8-row MMA tiles per warp
+constexpr int T_PRODUCER_WARPS = 4;                  // one warpgroup (setmaxnreg works per warpgroup); warp 0 issues TMA
+constexpr int T_THREADS = 32 * (T_CONSUMERS + T_PRODUCER_WARPS);
+constexpr int T_REGS_PRODUCER = 40, T_REGS_CONSUMER = 232;   // 128*40 + 256*232 = 64512 <= 65536 registers
 constexpr int T_TILE_BYTES = T_BM * BK * 8;          // 16 KiB per operand per stage
 constexpr int T_STAGE_BYTES = 2 * T_TILE_BYTES;
 constexpr size_t T_SMEM_BYTES = (size_t)T_STAGES * T_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -77,12 +85,16 @@ __device__ __forceinline__ double lds64(uint32_t addr) {
   return v;
 }
 __device__ __forceinline__ int perm8(int g) { return (g >> 1) + 4 * (g & 1); }
+template <int N>
+__device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(N)); }
 
 // one 16-deep k-block of a 64x32 warp tile.
 //   aBase/bBase: shared-memory byte addresses of the stage's A / B tiles
 //   B_KMAJOR: B tile stored [n rows][16 k] (NT / SYRK) else 8 boxes [16 k][16 n] (NN)
 template <bool B_KMAJOR, bool SCALE_A>
-__device__ __forceinline__ void tma_mma_kblock(uint32_t aBase, uint32_t bBase, double (&acc)[8][4][2], int wm, int wn, int g,
+__device__ __forceinline__ void tma_mma_kblock(uint32_t aBase, uint32_t bBase, double (&acc)[T_MT][4][2], int wm, int wn, int g,
                                                int q, double ascale) {
   const int pg = perm8(g);
   // (row & 7) == pg for every row tile (rows advance by 8), so the swizzle XOR term is loop-invariant
@@ -111,7 +123,7 @@ __device__ __forceinline__ void tma_mma_kblock(uint32_t aBase, uint32_t bBase, d
       }
     }
 #pragma unroll
-    for (int ih = 0; ih < 2; ++ih) {  // two halves of the 8 row tiles: keeps only 4 A fragments live
+    for (int ih = 0; ih < T_MT / 4; ++ih) {  // 4 row tiles at a time: keeps only 4 A fragments live
       double2 af[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -169,13 +181,14 @@ __global__ void __launch_bounds__(T_THREADS, 1)
   uint8_t* tiles;
   uint64_t *full, *empty;
   pipeline_setup(tiles, full, empty);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31;
   const int nkb = (p.K + BK - 1) / BK;
   const long ntiles = (long)p.m_tiles * p.n_tiles * p.batch;
 
-  if (warp == T_CONSUMERS) {
-    // ------------------------------------------------------------------ producer
-    if (lane == 0) {
+  if (threadIdx.x < 32 * T_PRODUCER_WARPS) {
+    // ------------------------------------------------------------------ producer warpgroup
+    reg_dealloc<T_REGS_PRODUCER>();
+    if (threadIdx.x == 0) {
       uint32_t it = 0;
       for (long t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int mt = (int)(t % p.m_tiles);
@@ -201,9 +214,11 @@ __global__ void __launch_bounds__(T_THREADS, 1)
     return;
   }
 
-  // -------------------------------------------------------------------- consumers
+  // -------------------------------------------------------------------- consumers (2 warpgroups)
+  reg_alloc<T_REGS_CONSUMER>();
+  const int warp = (threadIdx.x >> 5) - T_PRODUCER_WARPS;
   const int g = lane >> 2, q = lane & 3;
-  const int wm = warp & 1, wn = warp >> 1;   // 2 x 4 warps of 64 x 32
+  const int wm = warp % T_WARPS_M, wn = warp / T_WARPS_M;
   const int pg = perm8(g);
   double quad = 0.0, bsq = 0.0;
   uint32_t it = 0;
@@ -212,9 +227,9 @@ __global__ void __launch_bounds__(T_THREADS, 1)
     const long r = t / p.m_tiles;
     const int nt_ = (int)(r % p.n_tiles), b = (int)(r / p.n_tiles);
     const int m0 = mt * T_BM, n0 = nt_ * T_BN;
-    double acc[8][4][2];
+    double acc[T_MT][4][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < T_MT; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     for (int kb = 0; kb < nkb; ++kb, ++it) {
@@ -228,7 +243,7 @@ __global__ void __launch_bounds__(T_THREADS, 1)
     // epilogue (overlaps the producer's prefetch of the next tile)
     double* C = p.C + (long)b * p.sC;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < T_MT; ++i) {
       const int m = m0 + wm * T_WM + 8 * i + pg;
       if (m >= p.M) continue;
       double rr = 1.0;
@@ -275,7 +290,7 @@ __global__ void __launch_bounds__(T_THREADS, 1)
       red[1][warp] = bsq;
     }
     asm volatile("bar.sync 1, %0;\n" ::"n"(32 * T_CONSUMERS) : "memory");
-    if (threadIdx.x == 0) {
+    if (warp == 0 && lane == 0) {
       double s0 = 0.0, s1 = 0.0;
       for (int w = 0; w < T_CONSUMERS; ++w) {
         s0 += red[0][w];
@@ -305,7 +320,7 @@ __global__ void __launch_bounds__(T_THREADS, 1)
   uint8_t* tiles;
   uint64_t *full, *empty;
   pipeline_setup(tiles, full, empty);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31;
   int t = blockIdx.x, tm = 0;
   while ((tm + 1) * (tm + 2) / 2 <= t) ++tm;
   const int tn = t - tm * (tm + 1) / 2;
@@ -314,8 +329,9 @@ __global__ void __launch_bounds__(T_THREADS, 1)
   const long f0 = p.total_kb * split / p.nsplit, f1 = p.total_kb * (split + 1) / p.nsplit;
   const int nkb = (int)(f1 - f0);
 
-  if (warp == T_CONSUMERS) {
-    if (lane == 0) {
+  if (threadIdx.x < 32 * T_PRODUCER_WARPS) {
+    reg_dealloc<T_REGS_PRODUCER>();
+    if (threadIdx.x == 0) {
       for (int it = 0; it < nkb; ++it) {
         const int s = it % T_STAGES;
         const long f = f0 + it;
@@ -335,11 +351,13 @@ __global__ void __launch_bounds__(T_THREADS, 1)
     }
     return;
   }
+  reg_alloc<T_REGS_CONSUMER>();
+  const int warp = (threadIdx.x >> 5) - T_PRODUCER_WARPS;
   const int g = lane >> 2, q = lane & 3;
-  const int wm = warp & 1, wn = warp >> 1;
-  double acc[8][4][2];
+  const int wm = warp % T_WARPS_M, wn = warp / T_WARPS_M;
+  double acc[T_MT][4][2];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < T_MT; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
   for (int it = 0; it < nkb; ++it) {
@@ -358,10 +376,10 @@ __global__ void __launch_bounds__(T_THREADS, 1)
   const long ntiles = (long)p.tiles_1d * (p.tiles_1d + 1) / 2;
   double* out = p.ws + ((long)split * ntiles + t) * (T_BM * T_BN);
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < T_MT; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      *reinterpret_cast<double2*>(out + ((((warp * 8 + i) * 4 + j) * 32 + lane) << 1)) = make_double2(acc[i][j][0], acc[i][j][1]);
+      *reinterpret_cast<double2*>(out + ((((warp * T_MT + i) * 4 + j) * 32 + lane) << 1)) = make_double2(acc[i][j][0], acc[i][j][1]);
 }
 
 // sum the split-K partials in fixed order, un-permute the fragment layout, mirror the upper triangle
@@ -374,8 +392,8 @@ __global__ void tma_wsyrk_reduce_kernel(const double* __restrict__ ws, int nspli
   const int tn = t - tm * (tm + 1) / 2;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;  // fragment-order element index
   if (e >= T_BM * T_BN) return;
-  const int v = e & 1, lane = (e >> 1) & 31, j = (e >> 6) & 3, i = (e >> 8) & 7, warp = e >> 11;
-  const int g = lane >> 2, q = lane & 3, wm = warp & 1, wn = warp >> 1;
+  const int v = e & 1, lane = (e >> 1) & 31, j = (e >> 6) & 3, i = (e >> 8) % T_MT, warp = (e >> 8) / T_MT;
+  const int g = lane >> 2, q = lane & 3, wm = warp % T_WARPS_M, wn = warp / T_WARPS_M;
   const int r = wm * T_WM + 8 * i + perm8(g), c = wn * T_WN + 8 * j + q + 4 * v;
   const int m = tm * T_BM + r, n = tn * T_BN + c;
   if (m >= M || n >= M) return;
