@@ -282,19 +282,84 @@ static int dot_blocks(long n) {
 // ------------------------------------------------------------------------------------------------
 // cuSOLVER
 // ------------------------------------------------------------------------------------------------
-// one handle per host thread: evaluations of independent models may run concurrently on separate
-// streams / threads (multi-start restarts, the two probes of the auditory configuration)
-static thread_local cusolverDnHandle_t g_solver = nullptr;
-static int solver_handle(cusolverDnHandle_t* h) {
-  if (!g_solver) {
-    cusolverStatus_t s = cusolverDnCreate(&g_solver);
-    if (s != CUSOLVER_STATUS_SUCCESS) {
-      g_solver = nullptr;
-      return gp_fail("cusolverDnCreate failed");
+// One handle per (host thread, stream): independent eigenproblems run concurrently -- the two factors of one
+// model on side streams, independent models on separate host threads -- and a cuSOLVER handle (with the cuBLAS
+// workspace inside it) must not be shared by work in flight on two streams.
+struct SolverSlot {
+  cudaStream_t stream;
+  cusolverDnHandle_t handle;
+};
+static thread_local SolverSlot g_slots[8];
+static thread_local int g_nslots = 0;
+static int solver_handle(cusolverDnHandle_t* h, cudaStream_t st = nullptr) {
+  for (int i = 0; i < g_nslots; ++i)
+    if (g_slots[i].stream == st) {
+      *h = g_slots[i].handle;
+      return 0;
     }
+  if (g_nslots == 8) {  // recycle the oldest slot
+    cusolverDnDestroy(g_slots[0].handle);
+    for (int i = 1; i < 8; ++i) g_slots[i - 1] = g_slots[i];
+    g_nslots = 7;
   }
-  *h = g_solver;
+  cusolverDnHandle_t nh = nullptr;
+  if (cusolverDnCreate(&nh) != CUSOLVER_STATUS_SUCCESS) return gp_fail("cusolverDnCreate failed");
+  if (cusolverDnSetStream(nh, st) != CUSOLVER_STATUS_SUCCESS) return gp_fail("cusolverDnSetStream failed");
+  g_slots[g_nslots].stream = st;
+  g_slots[g_nslots].handle = nh;
+  ++g_nslots;
+  *h = nh;
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// centrosymmetric split (Cantoni & Butler 1976).  A symmetric Toeplitz matrix -- any stationary temporal
+// kernel on a uniform time grid -- satisfies J K J = K, so its eigenvectors are symmetric ([u; Ju]/sqrt2, or
+// [u; sqrt2 a; Ju]/sqrt2 for odd n) or skew-symmetric ([v; -Jv]/sqrt2):  the n x n eigenproblem splits
+// EXACTLY into two independent half-size ones, S = K11 + K12 J (bordered for odd n) and A = K11 - K12 J.
+// ------------------------------------------------------------------------------------------------
+__global__ void centro_split_kernel(int n, const double* __restrict__ K, long ldk, double* __restrict__ S, long lds,
+                                    double* __restrict__ A, long lda) {
+  const int m = n / 2, odd = n & 1, ms = m + odd;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)ms * ms) return;
+  const int i = (int)(idx / ms), j = (int)(idx % ms);
+  const double r2 = 1.4142135623730951;
+  if (i < m && j < m) {
+    const double a = K[(long)i * ldk + j], b = K[(long)i * ldk + (n - 1 - j)];
+    S[(long)i * lds + j] = a + b;
+    A[(long)i * lda + j] = a - b;
+  } else if (i == m && j == m) {
+    S[(long)i * lds + j] = K[(long)m * ldk + m];
+  } else {  // odd border
+    const int r = (i == m) ? j : i;
+    S[(long)i * lds + j] = r2 * K[(long)r * ldk + m];
+  }
+}
+
+// QT rows = eigenvectors of K: first ms rows from the symmetric block (UsT, ms x ms), then m rows from the skew
+// block (UaT, m x m); W = [Ws, Wa] (not sorted: the Kronecker sums do not depend on the order).
+__global__ void centro_assemble_kernel(int n, const double* __restrict__ UsT, long lds, const double* __restrict__ Ws,
+                                       const double* __restrict__ UaT, long lda, const double* __restrict__ Wa,
+                                       double* __restrict__ QT, long ldq, double* __restrict__ W) {
+  const int m = n / 2, odd = n & 1, ms = m + odd;
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)n * n) return;
+  const int a = (int)(idx / n), c = (int)(idx % n);
+  const double h = 0.70710678118654752;
+  double v;
+  if (a < ms) {
+    if (c < m) v = h * UsT[(long)a * lds + c];
+    else if (odd && c == m) v = UsT[(long)a * lds + m];
+    else v = h * UsT[(long)a * lds + (n - 1 - c)];
+  } else {
+    const int b = a - ms;
+    if (c < m) v = h * UaT[(long)b * lda + c];
+    else if (odd && c == m) v = 0.0;
+    else v = -h * UaT[(long)b * lda + (n - 1 - c)];
+  }
+  QT[(long)a * ldq + c] = v;
+  if (c == 0) W[a] = (a < ms) ? Ws[a] : Wa[a - ms];
 }
 
 __global__ void copy_matrix_kernel(int n, const double* __restrict__ in, long ldi, double* __restrict__ out, long ldo) {
@@ -467,12 +532,26 @@ long gpcsd_eigh_ws_doubles(int n, long ldq) {
   return (long)lwork;
 }
 
+int gpcsd_centro_split(int n, const double* K, long ldk, double* S, long lds, double* A, long lda, void* stream) {
+  if (n < 2) return gp_fail("centro_split: n must be >= 2");
+  const long ms = n / 2 + (n & 1);
+  centro_split_kernel<<<GRID1D(ms * ms), 0, (cudaStream_t)stream>>>(n, K, ldk, S, lds, A, lda);
+  GP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int gpcsd_centro_assemble(int n, const double* UsT, long lds, const double* Ws, const double* UaT, long lda,
+                          const double* Wa, double* QT, long ldq, double* W, void* stream) {
+  centro_assemble_kernel<<<GRID1D((long)n * n), 0, (cudaStream_t)stream>>>(n, UsT, lds, Ws, UaT, lda, Wa, QT, ldq, W);
+  GP_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int gpcsd_eigh(int n, const double* K, long ldk, double* QT, long ldq, double* W, double* ws, long ws_doubles, int* info,
                void* stream) {
   cusolverDnHandle_t h;
-  if (int e = solver_handle(&h)) return e;
   cudaStream_t st = (cudaStream_t)stream;
-  if (cusolverDnSetStream(h, st) != CUSOLVER_STATUS_SUCCESS) return gp_fail("cusolverDnSetStream failed");
+  if (int e = solver_handle(&h, st)) return e;
   copy_matrix_kernel<<<GRID1D((long)n * n), 0, st>>>(n, K, ldk, QT, ldq);
   GP_CUDA(cudaGetLastError());
   // K symmetric: row-major == column-major on input; output eigenvectors are the COLUMNS of a column-major

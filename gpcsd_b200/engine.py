@@ -71,6 +71,7 @@ class KronEngine:
         self.ntrials_total = 0
         self.ntrials = 0
         self.n_launches = 0
+        self._sides = None
         self.timers = None      # {abi_name: [(start_event, end_event), ...]} when bench.py profiles a kernel
 
     # ------------------------------------------------------------------ plumbing
@@ -123,6 +124,10 @@ class KronEngine:
         self.t_host = np.asarray(t, dtype=np.float64).reshape(-1)
         self.nt = self.t_host.shape[0]
         self.t_dev = self._dev(self.t_host)
+        # uniform to floating-point rounding (linspace / arange grids): then every stationary Kt is Toeplitz
+        dt = np.diff(self.t_host)
+        self.t_uniform = bool(self.nt >= 3 and np.all(dt > 0) and
+                              np.max(np.abs(dt - dt[0])) <= 64 * np.finfo(np.float64).eps * np.max(np.abs(self.t_host)))
         if self.dim == 1:
             gx, gw = np.asarray(quad["gl_x"], dtype=np.float64), np.asarray(quad["gl_w"], dtype=np.float64)
             if len(gx) % 2:
@@ -246,9 +251,9 @@ class KronEngine:
                    self._p(Kt), self.ldt, self._stream())
         return Kt
 
-    def _eigh(self, K, n, ld, tag):
-        QT = self._buf("QT_" + tag, n, ld)
-        W = self._buf("W_" + tag, n)
+    def _eigh(self, K, n, ld, tag, QT=None, W=None):
+        QT = self._buf("QT_" + tag, n, ld) if QT is None else QT
+        W = self._buf("W_" + tag, n) if W is None else W
         nws = L.query("gpcsd_eigh_ws_doubles", n, ld)
         ws = self._buf("eigws_" + tag, max(nws, 1))
         info = self._buf("info_" + tag, 1, dtype=torch.int32)
@@ -256,13 +261,58 @@ class KronEngine:
                    self._stream())
         return QT, W, info
 
+    def _side_streams(self):
+        if self._sides is None:
+            self._sides = [torch.cuda.Stream(device=self.device) for _ in range(2)]
+        return self._sides
+
+    def _eigh_temporal(self, Kt):
+        """Eigen-factors of Kt.  On a uniform time grid Kt is symmetric Toeplitz, hence centrosymmetric, and the
+        order-nt problem splits exactly into two independent problems of order ~nt/2 run on two streams
+        (cuSOLVER syevd costs ~1.2 ms + 8 us per column, so this is ~30 % faster at nt = 500); otherwise one
+        syevd.  The eigenvalues come back unsorted in the split case (nothing downstream needs an order)."""
+        nt, ldt = self.nt, self.ldt
+        if not (self.t_uniform and nt >= 32):
+            QT, W, info = self._eigh(Kt, nt, ldt, "t")
+            return QT, W, [info]
+        m, ms = nt // 2, nt // 2 + (nt & 1)
+        lds, lda = _even(ms), _even(m)
+        S, A = self._buf("cs_S", ms, lds), self._buf("cs_A", m, lda)
+        self._call("gpcsd_centro_split", nt, self._p(Kt), ldt, self._p(S), lds, self._p(A), lda, self._stream())
+        main = torch.cuda.current_stream(self.device)
+        side = self._side_streams()[1]
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(ready)
+            UaT, Wa, info_a = self._eigh(A, m, lda, "ta")
+            done = torch.cuda.Event()
+            done.record(side)
+        UsT, Ws, info_s = self._eigh(S, ms, lds, "ts")
+        main.wait_event(done)
+        QT, W = self._buf("QT_t", nt, ldt), self._buf("W_t", nt)
+        self._call("gpcsd_centro_assemble", nt, self._p(UsT), lds, self._p(Ws), self._p(UaT), lda, self._p(Wa),
+                   self._p(QT), ldt, self._p(W), self._stream())
+        return QT, W, [info_s, info_a]
+
     def _factorize(self, hp, jitter, want_grad):
-        """Covariances -> eigen-factors -> 1/D and its reductions (comp_eig_D, utility_functions.py:44-64)."""
+        """Covariances -> eigen-factors -> 1/D and its reductions (comp_eig_D, utility_functions.py:44-64).
+        The spatial and the temporal eigenproblems are independent and run on separate streams."""
         st = {}
         st["Ks"], st["A"], st["dA"], st["U"], st["kern"] = self._spatial_cov(hp, jitter, want_grad)
+        main = torch.cuda.current_stream(self.device)
+        side = self._side_streams()[0]
+        ks_ready = torch.cuda.Event()
+        ks_ready.record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(ks_ready)
+            st["QsT"], st["ls"], info_s = self._eigh(st["Ks"], self.nx, self.ldx, "s")
+            s_done = torch.cuda.Event()
+            s_done.record(side)
         st["Kt"] = self._temporal_cov(hp)
-        st["QsT"], st["ls"], st["info_s"] = self._eigh(st["Ks"], self.nx, self.ldx, "s")
-        st["QtT"], st["lt"], st["info_t"] = self._eigh(st["Kt"], self.nt, self.ldt, "t")
+        st["QtT"], st["lt"], infos_t = self._eigh_temporal(st["Kt"])
+        main.wait_event(s_done)
+        st["infos"] = [info_s] + infos_t
         s_host = np.atleast_1d(np.asarray(hp.sig2n, dtype=np.float64))
         if len(s_host) not in (1, self.nx):
             raise ValueError("sig2n must be a scalar or have one entry per electrode")
@@ -297,8 +347,7 @@ class KronEngine:
 
     # ------------------------------------------------------------------ public evaluations
     def _check_info(self, st):
-        bad = int(st["info_s"].item()) or int(st["info_t"].item())
-        if bad:
+        if any(int(i.item()) for i in st["infos"]):
             raise np.linalg.LinAlgError("Eigenvalues did not converge")
 
     def loglik(self, hp):

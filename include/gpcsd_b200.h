@@ -91,6 +91,15 @@ long gpcsd_eigh_ws_doubles(int n, long ldq);
 int gpcsd_eigh(int n, const double* K, long ldk, double* QT, long ldq, double* W,
                double* ws, long ws_doubles, int* info, void* stream);
 
+/* Exact centrosymmetric split of a symmetric Toeplitz (more generally J K J = K) matrix -- every stationary
+ * temporal kernel of covariances.py:257-305 on a uniform time grid -- into two independent half-size
+ * eigenproblems (Cantoni & Butler 1976), so the np.linalg.eigh(Kt) of utility_functions.py:58 costs two
+ * concurrent syevd of order n/2:  S = K11 + K12 J ((n/2 + n%2)^2, bordered for odd n),  A = K11 - K12 J ((n/2)^2).
+ * gpcsd_centro_assemble rebuilds QT (rows = eigenvectors of K) and W = [Ws, Wa] (unsorted). */
+int gpcsd_centro_split(int n, const double* K, long ldk, double* S, long lds, double* A, long lda, void* stream);
+int gpcsd_centro_assemble(int n, const double* UsT, long lds, const double* Ws, const double* UaT, long lda,
+                          const double* Wa, double* QT, long ldq, double* W, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * D and its reductions (utility_functions.py:54-63; gpcsd1d.py:122):
  *   D_ij = ls_i * lt_j + s_i  (s = sig2n[0] if n_sig2n == 1 else sig2n[i], i = ASCENDING spatial eigen-index)

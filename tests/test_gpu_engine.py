@@ -160,3 +160,23 @@ def test_single_trial_and_ragged_trial_counts(cuda_lib):
         ll_o, grad_o = O.loglik_and_grad(om, lfp)
         assert abs(ll - ll_o) / abs(ll_o) < TOL_LL
         assert np.max(np.abs(grad - grad_o) / np.abs(grad_o)) < TOL_GRAD
+
+
+@pytest.mark.parametrize("nt,uniform", [(41, True), (64, True), (40, False)])
+def test_temporal_eigh_paths_agree_with_oracle(cuda_lib, nt, uniform):
+    """Uniform grid (even / odd nt) -> centrosymmetric split on two streams; jittered grid -> single syevd."""
+    from oracle import gpcsd_oracle as O, synth
+    x, t = synth.geometry_1d(24, nt)
+    if not uniform:
+        t = t + 0.05 * np.sin(np.arange(nt))[:, None]
+    om = synth.model_1d(x, t)
+    lfp = synth.matched_lfp(om, 9, 5 + nt)
+    eng, hp = engine_from_oracle(om, lfp)
+    assert eng.t_uniform == uniform
+    ll, grad = eng.loglik_grad(hp)
+    ll_o, grad_o = O.loglik_and_grad(om, lfp)
+    assert abs(ll - ll_o) / abs(ll_o) < TOL_LL
+    assert np.max(np.abs(grad - grad_o) / np.abs(grad_o)) < grad_tol(om, lfp)
+    out = eng.predict(hp, x, t, "csd")
+    ref = O.predict_kron(om, lfp, x, t, "csd")
+    assert relerr(out["csd_pred"], ref["csd_pred"]) < TOL_PRED

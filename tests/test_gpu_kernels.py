@@ -261,3 +261,44 @@ def test_kt_grad_and_small_helpers(cuda_lib):
     ptrs = (ctypes.c_void_p * 2)(a.data_ptr(), b.data_ptr())
     L.call("gpcsd_sum_arrays", 1000, 2, ptrs, o.data_ptr(), _stream())
     assert np.array_equal(o.cpu().numpy(), (a + b).cpu().numpy())
+
+
+@pytest.mark.parametrize("n", [2, 7, 40, 41, 250, 501])
+def test_centrosymmetric_split_is_exact(cuda_lib, n):
+    """S/A blocks of a symmetric Toeplitz matrix -> eigenpairs of the halves -> assembled QT, W reproduce K."""
+    from gpcsd_b200 import _lib as L
+    t = np.arange(n, dtype=np.float64) * 0.4
+    d = t[:, None] - t[None, :]
+    K = 0.5 * np.exp(-0.5 * d ** 2 / 25.0) + 0.7 * np.exp(-np.abs(d) / 3.0)
+    m, ms = n // 2, n // 2 + (n & 1)
+    Kd, ld = _dev(K)
+    lds, lda = _ld(ms), _ld(max(m, 1))
+    S = torch.zeros((ms, lds), dtype=F64, device="cuda")
+    A = torch.zeros((max(m, 1), lda), dtype=F64, device="cuda")
+    L.call("gpcsd_centro_split", n, Kd.data_ptr(), ld, S.data_ptr(), lds, A.data_ptr(), lda, _stream())
+    J = np.eye(m)[::-1]
+    Sh = S[:, :ms].cpu().numpy()
+    assert relerr(Sh[:m, :m], K[:m, :m] + K[:m, n - m:] @ J) < 1e-15
+    assert relerr(A[:m, :m].cpu().numpy(), K[:m, :m] - K[:m, n - m:] @ J) < 1e-15
+
+    def eig(Md, k, ldm):
+        QT = torch.zeros((k, ldm), dtype=F64, device="cuda")
+        W = torch.zeros(k, dtype=F64, device="cuda")
+        nws = L.query("gpcsd_eigh_ws_doubles", k, ldm)
+        ws = torch.zeros(max(nws, 1), dtype=F64, device="cuda")
+        info = torch.zeros(1, dtype=torch.int32, device="cuda")
+        L.call("gpcsd_eigh", k, Md.data_ptr(), ldm, QT.data_ptr(), ldm, W.data_ptr(), ws.data_ptr(), nws, info.data_ptr(), _stream())
+        assert int(info.item()) == 0
+        return QT, W
+
+    UsT, Ws = eig(S, ms, lds)
+    UaT, Wa = eig(A, m, lda)
+    QT = torch.zeros((n, ld), dtype=F64, device="cuda")
+    W = torch.zeros(n, dtype=F64, device="cuda")
+    L.call("gpcsd_centro_assemble", n, UsT.data_ptr(), lds, Ws.data_ptr(), UaT.data_ptr(), lda, Wa.data_ptr(),
+           QT.data_ptr(), ld, W.data_ptr(), _stream())
+    Q = QT[:, :n].cpu().numpy().T
+    w = W.cpu().numpy()
+    assert relerr(Q.T @ Q, np.eye(n)) < 1e-13
+    assert relerr((Q * w) @ Q.T, K) < 1e-13
+    assert relerr(np.sort(w), np.linalg.eigvalsh(K)) < 1e-12
