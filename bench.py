@@ -127,6 +127,22 @@ def cpu_eval_seconds(sample_trials, reps=1):
     return float(np.median(ts)), os.cpu_count()
 
 
+def cpu_predict_baseline(sample_trials=250):
+    """Kronecker-form numpy port of predict (oracle.predict_kron) on a bounded sample; the reference's own dense
+    (nx nt)^2 formulation needs 36 s and 4.8 GB at this shape and is not timed here."""
+    from oracle import gpcsd_oracle as O
+    from oracle import synth
+    x, t = geometry()
+    om = synth.model_1d(x, t, a=A_LO, b=B_HI, ngl=NGL, sig2n=true_hyper(0)["sig2n"])
+    lfp = np.random.default_rng(8).standard_normal((NX, NT, sample_trials))
+    O.predict_kron(om, lfp[:, :, :16], x, t, "csd")
+    t0 = time.perf_counter()
+    O.predict_kron(om, lfp, x, t, "csd")
+    dt = time.perf_counter() - t0
+    return {"value": sample_trials / dt, "unit": "trials/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": "oracle predict_kron (Kronecker-form numpy port) on 24x500x%d trials" % sample_trials}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -360,6 +376,40 @@ def run_gpu(args):
     timed(step_e2e, W, K + W)
     ms_e2e = timed(step_e2e, K, K + 2 * W)
 
+    # ---- second half of the metric: posterior CSD prediction (type="csd", z = electrode sites), trials/s
+    KP = max(2, K // 3)
+
+    def predict_probe(p, to_host):
+        torch.cuda.set_device(device)
+        with torch.cuda.stream(streams[p]):
+            m = models[p]
+            if to_host:
+                m.predict(m.x, m.t, type="csd")          # public API: results land in host numpy arrays
+                return float(m.csd_pred[0, 0, 0])
+            out = m._get_engine().predict(m._hyperparams(), m.x, m.t, kind="csd", to_host=False)
+            return out["csd_pred"]
+
+    def step_predict(to_host):
+        def run(_s):
+            futs = [pool.submit(predict_probe, p, to_host) for p in range(len(models))]
+            return [f.result() for f in futs]
+        return run
+
+    for m, th in zip(models, thetas):
+        m._set_tparams(th[0], False)
+    timed(step_predict(False), 2, 0)
+    ms_pred = timed(step_predict(False), KP, 0)
+    timed(step_predict(True), 3, 0)                        # lets torch's pinned-host cache reach steady state
+    ms_pred_e2e = timed(step_predict(True), KP, 0)
+    trials_per_step = NPROBES * NTRIALS * world
+    ntc = 2
+    predict_line = {"metric": "gpcsd_csd_predict_trials_per_s", "unit": "trials/s",
+                    "value": trials_per_step * KP / (ms_pred * 1e-3), "ms_per_step": ms_pred / KP,
+                    "e2e": {"value": trials_per_step * KP / (ms_pred_e2e * 1e-3), "ms_per_step": ms_pred_e2e / KP,
+                            "d2h_bytes_per_step": NPROBES * (ntc + 1) * NX * NT * NTRIALS * 8,
+                            "api": "GPCSD1D.predict(x, t, type='csd') -> csd_pred + csd_pred_list as host arrays"},
+                    "steps": KP, "config": "z = the 24 electrode sites, t* = t, per-component (SE, Matern) + summed CSD"}
+
     evals_per_step = NPROBES * world
     value = evals_per_step * K / (ms_total * 1e-3)
     e2e_value = evals_per_step * K / (ms_e2e * 1e-3)
@@ -394,7 +444,8 @@ def run_gpu(args):
                              "peak_source": "in-run cuBLAS DGEMM 4096^3 best-of-5 (FP64; MEASURED_PEAKS.json has only "
                                             "HBM and bf16); DMMA issue-rate microbenchmark: 37.0 TFLOP/s"},
                 "kernel_ms": {k: {"avg_ms": v[0], "calls": v[1]} for k, v in kt.items()},
-                "last_nll": [float(last[p][0]) for p in range(NPROBES)]}
+                "last_nll": [float(last[p][0]) for p in range(NPROBES)],
+                "predict": predict_line}
         if world == 1 and not args.no_cpu_baseline:
             sample = 500
             secs, cores = cpu_eval_seconds(sample, reps=3)
@@ -402,6 +453,7 @@ def run_gpu(args):
             line["cpu_baseline"] = {"value": 1.0 / full, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "oracle loglik_and_grad (numpy/LAPACK restatement; closed-form gradient) on "
                                               "24x500x%d trials, median of 3, time scaled x%d to a 2000-trial block" % (sample, NTRIALS // sample)}
+            line["predict"]["cpu_baseline"] = cpu_predict_baseline()
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -520,10 +520,14 @@ class KronEngine:
         self._check_info(st)
         if not to_host:
             return {k: ([p[:, :, :N] for p in v] if isinstance(v, list) else v[:, :, :N]) for k, v in results.items()}
+        # device -> host: async DMA into pinned buffers (torch's caching host allocator recycles them), one sync
         host = {}
         for k, v in results.items():
             host[k] = [self._to_host(p, N) for p in v] if isinstance(v, list) else self._to_host(v, N)
-        return host
+        torch.cuda.current_stream(self.device).synchronize()
+        return {k: ([h.numpy() for h in v] if isinstance(v, list) else v.numpy()) for k, v in host.items()}
 
     def _to_host(self, dev, N):
-        return np.ascontiguousarray(dev[:, :, :N].cpu().numpy())
+        out = torch.empty((dev.shape[0], dev.shape[1], N), dtype=F64, pin_memory=True)
+        out.copy_(dev[:, :, :N], non_blocking=True)
+        return out

@@ -1,0 +1,98 @@
+"""BASELINE.json's full-size configurations on the GPU (-m gpu): parity against the oracle where it finishes
+in seconds, plus size-independent properties (trial additivity, linearity of the posterior mean, directional
+derivative of the log-likelihood)."""
+import time
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import engine_from_oracle, hp_from_oracle, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def _device_matched_lfp(om, ntrials, seed):
+    """Model-matched draw generated with torch on the device (test-input generator only)."""
+    ls, Qs = np.linalg.eigh(om.Ks(jitter=True))
+    lt, Qt = np.linalg.eigh(om.Kt())
+    Ls = torch.from_numpy(Qs * np.sqrt(np.maximum(ls, 0))).cuda()
+    Lt = torch.from_numpy(Qt * np.sqrt(np.maximum(lt, 0))).cuda()
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    Z = torch.randn((Ls.shape[0], Lt.shape[0], ntrials), dtype=torch.float64, device="cuda", generator=g)
+    Y = torch.einsum("ia,ajr->ijr", Ls, Z)
+    Y = torch.einsum("ijr,bj->ibr", Y, Lt)
+    Y += float(np.sqrt(np.mean(np.atleast_1d(om.sig2n)))) * torch.randn(Y.shape, dtype=torch.float64, device="cuda", generator=g)
+    return Y.cpu().numpy()
+
+
+def test_config2_auditory_full_size(cuda_lib):
+    """configs[1]: 24 ch x 500 t x 2000 trials, per-electrode noise, a=-200, b=2600."""
+    from oracle import gpcsd_oracle as O, synth
+    x, t = synth.geometry_1d(24, 500, ms_grid=True)
+    rng = np.random.default_rng(2)
+    om = synth.model_1d(x, t, a=-200.0, b=2600.0, sig2n=1e-2 * np.exp(0.3 * rng.standard_normal(24)))
+    lfp = _device_matched_lfp(om, 2000, 20)
+    om2 = synth.perturbed(om, 21)
+    eng, hp = engine_from_oracle(om2, lfp)
+    t0 = time.perf_counter()
+    ll, grad = eng.loglik_grad(hp)
+    dt = time.perf_counter() - t0
+    ll_o = O.loglik(om2, lfp)                                   # the reference's literal trial loop
+    assert abs(ll - ll_o) / abs(ll_o) < 1e-9
+    # trial additivity: loglik(all) == loglik(first 700) + loglik(remaining 1300)
+    e1, _ = engine_from_oracle(om2, lfp[:, :, :700])
+    e2, _ = engine_from_oracle(om2, lfp[:, :, 700:])
+    assert abs(ll - (e1.loglik(hp) + e2.loglik(hp))) / abs(ll) < 1e-11
+    # directional derivative along a random direction in log-parameter space
+    tp = O.pack_tparams(om2)
+    d = np.random.default_rng(3).standard_normal(tp.shape)
+    d /= np.linalg.norm(d)
+    vals = np.exp(tp) * np.array([100.0, 100.0] + [1.0] * (len(tp) - 2))
+    analytic = float(np.dot(grad * vals, d))
+    h = 1e-5
+    f = lambda s: eng.loglik(hp_from_oracle(O.unpack_tparams(om2, tp + s * d)))
+    fd = (-f(2 * h) + 8 * f(h) - 8 * f(-h) + f(-2 * h)) / (12 * h)
+    assert abs(fd - analytic) / abs(analytic) < 1e-5
+    print("\n[config2] loglik+grad first call %.1f ms, loglik %.6e" % (1e3 * dt, ll))
+
+
+def test_config3_neuropixels_full_size(cuda_lib):
+    """configs[2]: 384 ch (4 columns x 192 rows, checkerboard) x 250 t x 500 trials, ngl 30 x 120, eps = 1."""
+    from oracle import gpcsd_oracle as O, synth
+    X, t = synth.geometry_neuropixels(384, 250, 0.4)
+    om = synth.model_2d(X, t, ngl1=30, ngl2=120, a1=-16.0, b1=64.0, a2=-100.0, b2=3940.0, eps=1.0, sig2n=0.5)
+    lfp = _device_matched_lfp(om, 500, 30)
+    om2 = synth.perturbed(om, 31, scale=0.05)
+    eng, hp = engine_from_oracle(om2, lfp)
+    ll, grad = eng.loglik_grad(hp)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        ll, grad = eng.loglik_grad(hp)
+    dt = (time.perf_counter() - t0) / 3
+    t0 = time.perf_counter()
+    ll_o = O.loglik(om2, lfp)
+    dt_cpu = time.perf_counter() - t0
+    assert abs(ll - ll_o) / abs(ll_o) < 1e-9
+    assert len(grad) == 8 and np.all(np.isfinite(grad))
+    tp = O.pack_tparams(om2)
+    d = np.random.default_rng(4).standard_normal(tp.shape)
+    d /= np.linalg.norm(d)
+    vals = np.exp(tp) * np.array([100.0, 100.0, 100.0] + [1.0] * (len(tp) - 3))
+    analytic = float(np.dot(grad * vals, d))
+    h = 1e-5
+    f = lambda s: eng.loglik(hp_from_oracle(O.unpack_tparams(om2, tp + s * d)))
+    fd = (-f(2 * h) + 8 * f(h) - 8 * f(-h) + f(-2 * h)) / (12 * h)
+    assert abs(fd - analytic) / abs(analytic) < 1e-4
+    # predict at the script's 4 CSD depths (nz = 4 x-locations... here 24 sites) : linearity + agreement with oracle on a few trials
+    z = X[::16]
+    out = eng.predict(hp, z, t, "both", to_host=True)
+    ref = O.predict_kron(om2, lfp[:, :, :3], z, t, "both")
+    for key in ("csd_pred", "lfp_pred"):
+        assert relerr(out[key][:, :, :3], ref[key]) < 1e-8
+    eng2, _ = engine_from_oracle(om2, 2.0 * lfp[:, :, :8] - 0.5 * lfp[:, :, 8:16])
+    lin = eng2.predict(hp, z, t, "csd")["csd_pred"]
+    assert relerr(lin, 2.0 * out["csd_pred"][:, :, :8] - 0.5 * out["csd_pred"][:, :, 8:16]) < 1e-10
+    print("\n[config3] GPU loglik+grad %.1f ms/eval; CPU oracle loglik (forward only) %.2f s" % (1e3 * dt, dt_cpu))
