@@ -315,27 +315,52 @@ def run_gpu(args):
                 m.update_lfp(m.lfp, m.t)                   # forces the host->device copy of the pinned block
             return m.obj_fun_and_grad(thetas[p][s])
 
-    def run_step(s, upload):
+    def run_steps(first, nsteps, upload):
+        """nsteps evaluations of every probe.  Serial mode: probes one after the other inside each step.
+        Concurrent mode: one free-running host thread per probe (no per-step join), so in steady state one
+        probe's host->device upload / syevd overlaps the other probe's GEMMs."""
         if args.serial:
-            for p in range(len(models)):
-                last[p] = eval_probe(p, s, upload)
-        else:
-            futs = [pool.submit(eval_probe, p, s, upload) for p in range(len(models))]
-            for p, f in enumerate(futs):
-                last[p] = f.result()
+            for s in range(first, first + nsteps):
+                for p in range(len(models)):
+                    last[p] = eval_probe(p, s, upload)
+            return
+
+        def worker(p):
+            r = None
+            for s in range(first, first + nsteps):
+                r = eval_probe(p, s, upload)
+            return r
+        futs = [pool.submit(worker, p) for p in range(len(models))]
+        for p, f in enumerate(futs):
+            last[p] = f.result()
+
+    def timed_steps(nsteps, first, upload):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        run_steps(first, nsteps, upload)
+        for st_ in streams:
+            torch.cuda.current_stream(device).wait_stream(st_)
+        e1.record()
+        barrier()
+        ms = max(e0.elapsed_time(e1), 0.0)
+        ms = max(ms, 1e3 * 0.0)
+        if world > 1:
+            tt = torch.tensor([ms], dtype=torch.float64, device=device)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        return ms
 
     def step_resident(s):
-        run_step(s, False)
-
-    def step_e2e(s):
-        run_step(s, True)
+        run_steps(s, 1, False)
 
     # ---- device-resident arm ("value")
     for p, m in enumerate(models):
         with torch.cuda.stream(streams[p]):
             m._get_engine()                                 # upload once
     torch.cuda.synchronize()
-    timed(step_resident, W, 0)
+    timed_steps(W, 0, False)
     if args.profile_step:
         # one steady-state SERIAL step between cudaProfilerStart/Stop for `ncu --profile-from-start off`
         args.serial = True
@@ -354,16 +379,16 @@ def run_gpu(args):
     # pass 1 (headline): the two probes evaluated concurrently
     for e in engines:
         e.n_launches = 0
-    ms_total = timed(step_resident, K, W)
+    ms_total = timed_steps(K, W, False)
     launches = sum(e.n_launches for e in engines)
     # pass 2: same K steps with the probes one after the other and CUDA events around the dominant kernels
     # (per-kernel durations are only meaningful without a second stream competing for the SMs)
     concurrent = not args.serial
     args.serial = True
-    timed(step_resident, 2, 0)                              # warm the main thread's cuSOLVER handle
+    timed_steps(2, 0, False)                                # warm the main thread's cuSOLVER handles
     for e in engines:
         e.timers = {"gpcsd_project_quad": [], "gpcsd_wsyrk": [], "gpcsd_eigh": [], "gpcsd_dgemm": []}
-    ms_serial = timed(step_resident, K, W)
+    ms_serial = timed_steps(K, W, False)
     clocks = sampler.stop() if rank == 0 else None
     kt = {}
     for name in engines[0].timers:
@@ -373,8 +398,8 @@ def run_gpu(args):
         e.timers = None
     args.serial = not concurrent
     # ---- end-to-end arm
-    timed(step_e2e, W, K + W)
-    ms_e2e = timed(step_e2e, K, K + 2 * W)
+    timed_steps(W, K + W, True)
+    ms_e2e = timed_steps(K, K + 2 * W, True)
 
     # ---- second half of the metric: posterior CSD prediction (type="csd", z = electrode sites), trials/s
     KP = max(2, K // 3)

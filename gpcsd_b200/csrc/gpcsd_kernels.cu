@@ -3,6 +3,8 @@
 #include <cusolverDn.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "common.h"
 #include "dmma_gemm.cuh"
 
@@ -282,25 +284,28 @@ static int dot_blocks(long n) {
 // ------------------------------------------------------------------------------------------------
 // cuSOLVER
 // ------------------------------------------------------------------------------------------------
-// One handle per (host thread, stream): independent eigenproblems run concurrently -- the two factors of one
-// model on side streams, independent models on separate host threads -- and a cuSOLVER handle (with the cuBLAS
-// workspace inside it) must not be shared by work in flight on two streams.
+// One cuSOLVER handle per CUDA stream (process-wide table): independent eigenproblems run concurrently -- the two
+// factors of one model on side streams, independent models on separate host threads/streams -- and a handle
+// (with the cuBLAS workspace inside it) must not be shared by work in flight on two streams.  Creating a handle
+// costs ~100 ms, so they are cached for the life of the process.
 struct SolverSlot {
   cudaStream_t stream;
   cusolverDnHandle_t handle;
 };
-static thread_local SolverSlot g_slots[8];
-static thread_local int g_nslots = 0;
+static SolverSlot g_slots[64];
+static int g_nslots = 0;
+static std::mutex g_slot_mutex;
 static int solver_handle(cusolverDnHandle_t* h, cudaStream_t st = nullptr) {
+  std::lock_guard<std::mutex> lock(g_slot_mutex);
   for (int i = 0; i < g_nslots; ++i)
     if (g_slots[i].stream == st) {
       *h = g_slots[i].handle;
       return 0;
     }
-  if (g_nslots == 8) {  // recycle the oldest slot
+  if (g_nslots == 64) {  // recycle the oldest slot
     cusolverDnDestroy(g_slots[0].handle);
-    for (int i = 1; i < 8; ++i) g_slots[i - 1] = g_slots[i];
-    g_nslots = 7;
+    for (int i = 1; i < 64; ++i) g_slots[i - 1] = g_slots[i];
+    g_nslots = 63;
   }
   cusolverDnHandle_t nh = nullptr;
   if (cusolverDnCreate(&nh) != CUSOLVER_STATUS_SUCCESS) return gp_fail("cusolverDnCreate failed");
