@@ -11,6 +11,7 @@ from tqdm import tqdm
 
 from . import devops
 from .engine import HyperParams, KronEngine
+from .parallel import RestartShard
 
 np.seterr(all='ignore')  # gpcsd1d.py:7 -- NaN/inf propagate as values
 
@@ -182,19 +183,28 @@ class GPCSDModelBase:
         options = dict(options)
         if method == 'L-BFGS-B' and not options.get('disp', False):
             options.pop('disp', None)       # the reference passes disp=False; newer scipy warns on the key
-        nll_values, params, term_msg = [], [], []
-        for _ in tqdm(range(n_restarts), desc="Restarts"):
-            tparams0 = self._sample_tparams0(fix_R)
+        # Every rank draws ALL starting points in order (same RNG stream as an unsharded run, so restart i starts
+        # from the same point whatever the world size) and optimises only its own share of them.
+        shard = RestartShard(getattr(self, "_restart_group", None))
+        starts = [self._sample_tparams0(fix_R) for _ in range(n_restarts)]
+        local = {}
+        for i in tqdm(range(n_restarts), desc="Restarts", disable=shard.rank != 0):
+            if not shard.mine(i):
+                continue
             try:
-                res = scipy.optimize.minimize(lambda tp: self.obj_fun_and_grad(tp, fix_R), tparams0, jac=True,
+                res = scipy.optimize.minimize(lambda tp: self.obj_fun_and_grad(tp, fix_R), starts[i], jac=True,
                                               method=method, options=options, bounds=bounds)
-                nll_values.append(res.fun)
-                params.append(res.x)
-                term_msg.append(res.message)
+                local[i] = (float(res.fun), np.asarray(res.x, dtype=np.float64), str(res.message))
             except (ValueError, np.linalg.LinAlgError) as e:
                 print(e)
                 if self.DIM == 2:
                     print('\nrestarting optimization...')
+        merged = shard.gather(local)
+        nll_values, params, term_msg = [], [], []
+        for i in sorted(merged):
+            nll_values.append(merged[i][0])
+            params.append(merged[i][1])
+            term_msg.append(merged[i][2])
         nll_values = np.array(nll_values)
         if len(nll_values) < 1:
             print('problem with optimization!')

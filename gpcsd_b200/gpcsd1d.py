@@ -19,7 +19,7 @@ class GPCSD1D(GPCSDModelBase):
     SPATIAL_ELL_KEYS = ('ell',)
 
     def __init__(self, lfp, x, t, a=None, b=None, ngl=100, spatial_cov=None, temporal_cov_list=None, R_prior=None,
-                 sig2n_prior=None, distributed=False):
+                 sig2n_prior=None, distributed=False, distributed_restarts=False):
         """
         :param lfp: LFP array (n_spatial, n_time, n_trials); rescale to roughly unit standard deviation
         :param x: electrode positions (n_spatial, 1), microns
@@ -31,6 +31,7 @@ class GPCSD1D(GPCSDModelBase):
         :param R_prior: prior on the cylinder radius R (default inverse-gamma matched to the probe)
         :param sig2n_prior: prior on the noise variance, or a list with one prior per electrode
         :param distributed: True (or a torch.distributed group) shards the trials over the ranks
+        :param distributed_restarts: True (or a group) shards fit()'s multi-start restarts over the ranks instead
         """
         self.lfp = np.atleast_3d(lfp)
         self.x = x
@@ -39,6 +40,7 @@ class GPCSD1D(GPCSDModelBase):
         self.b = np.max(x) if b is None else b
         self.ngl = ngl
         self._group = distributed if distributed else None
+        self._restart_group = distributed_restarts if distributed_restarts else None
         if spatial_cov is None:
             spatial_cov = GPCSD1DSpatialCovSE(x, a=self.a, b=self.b, ngl=ngl)
         self.spatial_cov = spatial_cov

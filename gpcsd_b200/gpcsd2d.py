@@ -16,7 +16,7 @@ class GPCSD2D(GPCSDModelBase):
     SPATIAL_ELL_KEYS = ('ell1', 'ell2')
 
     def __init__(self, lfp, x, t, a1=None, b1=None, a2=None, b2=None, ngl1=20, ngl2=60, spatial_cov=None,
-                 temporal_cov_list=None, R_prior=None, sig2n_prior=None, eps=None, distributed=False):
+                 temporal_cov_list=None, R_prior=None, sig2n_prior=None, eps=None, distributed=False, distributed_restarts=False):
         """
         :param lfp: LFP array (n_spatial, n_time, n_trials); rescale to roughly unit standard deviation
         :param x: electrode positions (n_spatial, 2), microns
@@ -25,6 +25,7 @@ class GPCSD2D(GPCSDModelBase):
         :param ngl1, ngl2: Gauss-Legendre orders
         :param eps: zero-charge offset in front of the array (default 5 * smallest electrode spacing)
         :param distributed: True (or a torch.distributed group) shards the trials over the ranks
+        :param distributed_restarts: True (or a group) shards fit()'s multi-start restarts over the ranks instead
         """
         self.lfp = np.atleast_3d(lfp)
         self.x = x
@@ -35,6 +36,7 @@ class GPCSD2D(GPCSDModelBase):
         self.b2 = np.max(x[:, 1]) if b2 is None else b2
         self.ngl1, self.ngl2 = ngl1, ngl2
         self._group = distributed if distributed else None
+        self._restart_group = distributed_restarts if distributed_restarts else None
         if spatial_cov is None:
             spatial_cov = GPCSD2DSpatialCovSE(self.x, a1=self.a1, b1=self.b1, a2=self.a2, b2=self.b2, ngl1=ngl1, ngl2=ngl2)
         self.spatial_cov = spatial_cov

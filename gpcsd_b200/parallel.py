@@ -47,3 +47,31 @@ class TrialShard:
             t = t.to(device)
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         return t.cpu().numpy()
+
+
+class RestartShard:
+    """Multi-start restarts are independent optimisations of the same model: shard restart indices round-robin
+    over the ranks (every rank holds the full, small LFP), and exchange (nll, params, message) once at the end
+    -- the 'allgather of n_restarts scalars' of SURVEY.md 8(e).  group: None/False -> no sharding."""
+
+    def __init__(self, group=None):
+        self.enabled = group is not None and group is not False
+        if self.enabled and not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("restart sharding requested but torch.distributed is not initialised")
+        self.group = None if (group is True or not self.enabled) else group
+        self.rank = dist.get_rank(self.group) if self.enabled else 0
+        self.world = dist.get_world_size(self.group) if self.enabled else 1
+
+    def mine(self, restart_index):
+        return restart_index % self.world == self.rank
+
+    def gather(self, local):
+        """local: {restart_index: result}; returns the merged dict (identical on every rank)."""
+        if not self.enabled or self.world == 1:
+            return dict(local)
+        parts = [None] * self.world
+        dist.all_gather_object(parts, local, group=self.group)
+        merged = {}
+        for p in parts:
+            merged.update(p)
+        return merged

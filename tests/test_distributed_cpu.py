@@ -81,3 +81,79 @@ def test_trialshard_disabled_by_default():
     assert np.array_equal(sh.allreduce_sum(v), v)
     with pytest.raises(RuntimeError):
         TrialShard(True)
+
+
+class _StubModel:
+    """GPCSDModelBase._fit driven by a cheap analytic objective (no CUDA): checks the restart-sharding logic."""
+
+    def __new__(cls, restart_group):
+        from gpcsd_b200._model import GPCSDModelBase
+        from gpcsd_b200.priors import GPCSDHalfNormalPrior, GPCSDInvGammaPrior
+
+        class M(GPCSDModelBase):
+            DIM = 1
+            SPATIAL_ELL_KEYS = ('ell',)
+
+            def obj_fun_and_grad(self, tparams, fix_R=False):
+                self._set_tparams(tparams, fix_R)
+                tp = np.asarray(tparams)
+                target = np.linspace(-0.5, 0.5, tp.size)
+                # two basins so that different starts end in different local minima
+                f = np.sum((tp - target) ** 2 * ((tp - target - 1.5) ** 2 + 0.3))
+                g = 2 * (tp - target) * ((tp - target - 1.5) ** 2 + 0.3) + (tp - target) ** 2 * 2 * (tp - target - 1.5)
+                return float(f), g
+
+        m = M()
+        ig = GPCSDInvGammaPrior(); ig.set_params(50.0, 500.0)
+
+        class SC:
+            params = {'ell': {'value': 200.0, 'prior': ig, 'min': 10.0, 'max': 5000.0}}
+
+        class TC:
+            KIND = 0
+            def __init__(self):
+                tg = GPCSDInvGammaPrior(); tg.set_params(1.0, 40.0)
+                self.params = {'ell': {'value': 5.0, 'prior': tg, 'min': 0.1, 'max': 500.0},
+                               'sigma2': {'value': 1.0, 'prior': GPCSDHalfNormalPrior(1.0), 'min': 1e-8, 'max': np.inf}}
+        m.spatial_cov = SC()
+        m.temporal_cov_list = [TC(), TC()]
+        m.R = {'value': 100.0, 'prior': ig, 'min': 10.0, 'max': 5000.0}
+        m.sig2n = {'value': 0.1, 'prior': GPCSDHalfNormalPrior(0.1), 'min': 1e-8, 'max': 0.5}
+        m._restart_group = restart_group
+        return m
+
+
+def _fit_stub(restart_group, seed=11, n_restarts=6):
+    np.random.seed(seed)
+    m = _StubModel(restart_group)
+    m._fit(n_restarts, 'L-BFGS-B', False, False, {'maxiter': 200, 'gtol': 1e-10})
+    return np.array([m.R['value'], m.spatial_cov.params['ell']['value'], m.sig2n['value']] +
+                    [tc.params[k]['value'] for tc in m.temporal_cov_list for k in ('ell', 'sigma2')])
+
+
+def _restart_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from gpcsd_b200.parallel import RestartShard
+    sh = RestartShard(True)
+    assert [i for i in range(6) if sh.mine(i)] == list(range(rank, 6, world))
+    q.put((rank, _fit_stub(True)))
+    dist.destroy_process_group()
+
+
+def test_restart_sharding_world2_matches_unsharded():
+    """fit() with restarts sharded over 2 ranks ends at exactly the parameters of the unsharded fit."""
+    single = _fit_stub(None)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_restart_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=240) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert np.array_equal(res[0], res[1])
+    assert np.allclose(res[0], single, rtol=0, atol=0)
