@@ -1,5 +1,6 @@
-// DMMA GEMM kernels + launchers: generic strided-batched GEMM, fused projection+quadratic-form,
-// segment-weighted split-K SYRK.  See include/gpcsd_b200.h for the ABI contract.
+// ABI entry points of the GEMM-shaped stages (gpcsd_dgemm, gpcsd_project_quad, gpcsd_wsyrk) and the small-M
+// kernels: cp.async DMMA GEMM for M <= 32 and the register-only small-M SYRK.  Everything with M > 32 is
+// dispatched to the persistent TMA + mbarrier kernels in gpcsd_tma.cu.  See include/gpcsd_b200.h.
 #include "common.h"
 #include "dmma_gemm.cuh"
 
@@ -38,8 +39,7 @@ struct SmemLayout {
   static constexpr size_t BYTES = (size_t)STAGES * (A_STAGE + B_STAGE) * sizeof(double) + 64;
 };
 
-// C_b = A_b * op(B_b).  grid.x = m_tiles * n_tiles (m fastest so CTAs sharing a B column panel are
-// co-resident and the panel is fetched from HBM once), grid.y = batch.
+// C_b = A_b * op(B_b) for M <= 32 (one 32-row tile).  grid.x = n_tiles, grid.y = batch.
 template <int BM, int BN, int WM, int WN, int STAGES, bool BT, int EPI, int MINB>
 __global__ void __launch_bounds__(NTHREADS, MINB) dmma_gemm_kernel(GemmArgs p) {
   using L = SmemLayout<BM, BN, BT, STAGES>;
@@ -216,105 +216,6 @@ struct SyrkArgs {
   int tiles_1d;    // tiles per side
   double* ws;      // [nsplit][ntiles][BM*BN]
 };
-
-template <int BMN, int WM, int WN, int STAGES, int MINB>
-__global__ void __launch_bounds__(NTHREADS, MINB) wsyrk_kernel(SyrkArgs p) {
-  constexpr int STAGE = BMN * KMAJ_LD;
-  extern __shared__ __align__(16) double smem[];
-  double* sA = smem;
-  double* sB = smem + STAGES * STAGE;
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int g = lane >> 2, q = lane & 3;
-  constexpr int WARPS_M = BMN / WM;
-  static_assert((BMN / WM) * (BMN / WN) == NTHREADS / 32, "warp tiling must use 8 warps");
-  const int wm = warp % WARPS_M, wn = warp / WARPS_M;
-
-  // lower-triangular tile index -> (tm, tn), tn <= tm
-  int t = blockIdx.x, tm = 0;
-  while ((tm + 1) * (tm + 2) / 2 <= t) ++tm;
-  const int tn = t - tm * (tm + 1) / 2;
-  const bool diag = (tm == tn);
-  const int split = blockIdx.y;
-  const long f0 = p.total_kb * split / p.nsplit, f1 = p.total_kb * (split + 1) / p.nsplit;
-  const int nkb = (int)(f1 - f0);
-
-  const double* XA = p.X + (long)tm * BMN * p.row_stride;
-  const double* XB = p.X + (long)tn * BMN * p.row_stride;
-  const int rowsA = p.M - tm * BMN, rowsB = p.M - tn * BMN;
-
-  double acc[WM / 8][WN / 8][2];
-#pragma unroll
-  for (int i = 0; i < WM / 8; ++i)
-#pragma unroll
-    for (int j = 0; j < WN / 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-  KMajorLoader<BMN> ldA, ldB;
-  ldA.init(XA, p.row_stride, rowsA, p.X);
-  ldB.init(XB, p.row_stride, rowsB, p.X);
-  auto load_stage = [&](int st, long f) {
-    const int seg = (int)(f / p.kbps);
-    const long k0 = (long)(f - (long)seg * p.kbps) * BK;
-    const long off = (long)seg * p.seg_stride + k0;
-    ldA.load(sA + st * STAGE, off, p.seglen - k0);
-    if (!diag) ldB.load(sB + st * STAGE, off, p.seglen - k0);
-  };
-
-#pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < nkb) load_stage(s, f0 + s);
-    cp_async_commit();
-  }
-  for (int kb = 0; kb < nkb; ++kb) {
-    cp_async_wait<STAGES - 2>();
-    __syncthreads();
-    const int nxt = kb + STAGES - 1;
-    if (nxt < nkb) load_stage(nxt % STAGES, f0 + nxt);
-    cp_async_commit();
-    const int st = kb % STAGES;
-    const double wgt = p.w ? __ldg(p.w + (f0 + kb) / p.kbps) : 1.0;
-    const double* a = sA + st * STAGE + (wm * WM) * KMAJ_LD;
-    const double* bb = (diag ? sA : sB) + st * STAGE + (wn * WN) * KMAJ_LD;
-    if (p.w)
-      mma_kblock<WM, WN, true, KMAJ_LD, true>(a, bb, acc, g, q, wgt);
-    else
-      mma_kblock<WM, WN, true, KMAJ_LD, false>(a, bb, acc, g, q, 1.0);
-  }
-  cp_async_wait<0>();
-
-  const long ntiles = (long)p.tiles_1d * (p.tiles_1d + 1) / 2;
-  double* out = p.ws + ((long)split * ntiles + t) * (BMN * BMN);
-#pragma unroll
-  for (int i = 0; i < WM / 8; ++i)
-#pragma unroll
-    for (int j = 0; j < WN / 8; ++j) {
-      const int r = wm * WM + i * 8 + g, c = wn * WN + j * 8 + 2 * q;
-      *reinterpret_cast<double2*>(out + r * BMN + c) = make_double2(acc[i][j][0], acc[i][j][1]);
-    }
-}
-
-template <int BMN>
-__global__ void wsyrk_reduce_kernel(const double* __restrict__ ws, int nsplit, int tiles_1d, int M,
-                                    double* __restrict__ C, long ldc) {
-  const long ntiles = (long)tiles_1d * (tiles_1d + 1) / 2;
-  const int t = blockIdx.y;
-  int tm = 0;
-  while ((tm + 1) * (tm + 2) / 2 <= t) ++tm;
-  const int tn = t - tm * (tm + 1) / 2;
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= BMN * BMN) return;
-  const int r = e / BMN, c = e % BMN;
-  const int m = tm * BMN + r, n = tn * BMN + c;
-  if (m >= M || n >= M) return;
-  double s = 0.0;
-  for (int sp = 0; sp < nsplit; ++sp) s += ws[((long)sp * ntiles + t) * (BMN * BMN) + e];
-  if (tm == tn) {
-    C[(long)m * ldc + n] = s;
-  } else {
-    C[(long)m * ldc + n] = s;
-    C[(long)n * ldc + m] = s;
-  }
-}
 
 // ---- M <= 32: register-only variant ---------------------------------------------------------------
 // One diagonal tile only, so the B fragment of MMA column-tile j IS the A fragment of row-tile j: lane (g,q)
