@@ -47,6 +47,8 @@ def fwd_model_2d(arr, x1, x2, z, R, eps, varsigma=1):
     x2 = np.asarray(x2, dtype=np.float64).reshape(-1)
     z = np.asarray(z, dtype=np.float64)
     arr = np.asarray(arr, dtype=np.float64)
+    if arr.ndim == 4 and arr.shape[3] == 1:       # callers pass (nx1, nx2, nt, 1) (sim_from_gp_2D.py:70); the reference squeezes it
+        arr = arr[..., 0]
     wt = b_fwd_2d(z[:, 0][:, None, None] - x1[None, :, None], z[:, 1][:, None, None] - x2[None, None, :], R, eps)
     wt = wt * _trapz_weights(x1)[None, :, None] * _trapz_weights(x2)[None, None, :]
     return np.einsum("zab,abt->zt", wt, arr, optimize=True)

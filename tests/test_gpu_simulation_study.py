@@ -99,3 +99,41 @@ def test_nonfinite_and_error_semantics(cuda_lib):
     m.update_lfp(np.random.randn(23, 40, 3), t)
     with pytest.raises(ValueError):
         m.loglik()
+
+
+def test_sim_from_gp_2d_flow(cuda_lib):
+    """simulation_studies/sim_from_gp_2D.py:19-100 on a smaller dense grid: sample a 2-D CSD from the prior on a dense
+    grid, forward-model it to a sparse electrode grid, switch the model to the electrode geometry with
+    update_lfp(.., x=...), predict CSD on the dense grid and LFP at the electrodes with the true parameters."""
+    from gpcsd_b200.covariances import GPCSDTemporalCovMatern, GPCSDTemporalCovSE
+    from gpcsd_b200.forward_models import fwd_model_2d
+    from gpcsd_b200.gpcsd2d import GPCSD2D
+    from gpcsd_b200.utility_functions import expand_grid
+    np.random.seed(0)
+    a1, b1, a2, b2, nt = 0, 60, 0, 600, 10
+    t = np.linspace(0, 100, nt)[:, None]
+    nx1, nx2, nz1, nz2 = 4, 20, 8, 60
+    x1, x2 = np.linspace(a1, b1, nx1)[:, None], np.linspace(a2, b2, nx2)[:, None]
+    z1, z2 = np.linspace(a1, b1, nz1)[:, None], np.linspace(a2, b2, nz2)[:, None]
+    x_grid, z_grid = expand_grid(x1, x2), expand_grid(z1, z2)
+    gen = GPCSD2D(np.zeros((z_grid.shape[0], nt, 1)), x=z_grid, t=t, a1=a1, b1=b1, a2=a2, b2=b2,
+                  temporal_cov_list=[GPCSDTemporalCovSE(t), GPCSDTemporalCovMatern(t)], ngl1=12, ngl2=40, eps=10.0)
+    gen.R['value'] = 30.0
+    gen.sig2n['value'] = 0.05
+    gen.spatial_cov.params['ell1']['value'], gen.spatial_cov.params['ell2']['value'] = 40.0, 100.0
+    gen.temporal_cov_list[0].params['ell']['value'], gen.temporal_cov_list[0].params['sigma2']['value'] = 5, 20
+    gen.temporal_cov_list[1].params['ell']['value'], gen.temporal_cov_list[1].params['sigma2']['value'] = 1, 10
+    csd_dense, nan_lfp = gen.sample_prior(1, type="csd")
+    assert csd_dense.shape == (nz1 * nz2, nt, 1) and np.all(np.isnan(nan_lfp))
+    clean = np.atleast_3d(fwd_model_2d(csd_dense.reshape((nz1, nz2, nt, -1)), z1, z2, x_grid, 30.0, gen.eps))
+    lfp_sparse = clean + np.random.normal(0, np.sqrt(0.05), clean.shape)
+    gen.update_lfp(lfp_sparse, t, x_grid)                       # geometry switch: dense CSD grid -> electrode grid
+    assert gen.spatial_cov.x is x_grid
+    gen.predict(z_grid, t, type="csd")
+    gen.predict(x_grid, t, type="lfp")
+    assert gen.csd_pred.shape == (nz1 * nz2, nt, 1) and gen.lfp_pred.shape == (nx1 * nx2, nt, 1)
+    r2_lfp = _r2(gen.lfp_pred, clean)
+    corr = np.corrcoef(gen.csd_pred.ravel(), csd_dense.ravel())[0, 1]
+    print("\n[2-D flow] R2(lfp_pred, noiseless lfp) = %.3f, corr(csd_pred, true csd) = %.3f" % (r2_lfp, corr))
+    assert r2_lfp > 0.9          # the posterior mean de-noises the LFP
+    assert corr > 0.5            # and recovers the CSD pattern from 4 electrode columns
