@@ -93,28 +93,30 @@ __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.
 // one 16-deep k-block of a 64x32 warp tile.
 //   aBase/bBase: shared-memory byte addresses of the stage's A / B tiles
 //   B_KMAJOR: B tile stored [n rows][16 k] (NT / SYRK) else 8 boxes [16 k][16 n] (NN)
-template <bool B_KMAJOR, bool SCALE_A>
-__device__ __forceinline__ void tma_mma_kblock(uint32_t aBase, uint32_t bBase, double (&acc)[T_MT][4][2], int wm, int wn, int g,
+// NTW = 8-column MMA tiles per warp (warp tile 64 x 8*NTW; CTA tile 128 x 32*NTW)
+template <bool B_KMAJOR, bool SCALE_A, int NTW = 4>
+__device__ __forceinline__ void tma_mma_kblock(uint32_t aBase, uint32_t bBase, double (&acc)[T_MT][NTW][2], int wm, int wn, int g,
                                                int q, double ascale) {
   const int pg = perm8(g);
   // (row & 7) == pg for every row tile (rows advance by 8), so the swizzle XOR term is loop-invariant
   const uint32_t aRow = aBase + (wm * T_WM + pg) * 128;
-  const uint32_t bRow = bBase + (wn * T_WN + pg) * 128;
+  constexpr int WN = 8 * NTW;
+  const uint32_t bRow = bBase + (wn * WN + pg) * 128;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {  // k-step pairs (2h, 2h+1)
     const uint32_t kch = (uint32_t)(((4 * h + q) ^ pg) << 4);
-    double b0[4], b1[4];
+    double b0[NTW], b1[NTW];
     if (B_KMAJOR) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < NTW; ++j) {
         const double2 t = lds128(bRow + j * 1024 + kch);
         b0[j] = t.x;
         b1[j] = t.y;
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int n = wn * T_WN + 8 * j + g;
+      for (int j = 0; j < NTW; ++j) {
+        const int n = wn * WN + 8 * j + g;
         const uint32_t box = bBase + (n >> 4) * 2048 + (n & 1) * 8;
         const int c = (n & 15) >> 1;
         const int k0 = 8 * h + 2 * q, k1 = k0 + 1;
@@ -136,11 +138,11 @@ __device__ __forceinline__ void tma_mma_kblock(uint32_t aBase, uint32_t bBase, d
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma884(acc[4 * ih + i][j][0], acc[4 * ih + i][j][1], af[i].x, b0[j]);
+        for (int j = 0; j < NTW; ++j) dmma884(acc[4 * ih + i][j][0], acc[4 * ih + i][j][1], af[i].x, b0[j]);
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma884(acc[4 * ih + i][j][0], acc[4 * ih + i][j][1], af[i].y, b1[j]);
+        for (int j = 0; j < NTW; ++j) dmma884(acc[4 * ih + i][j][0], acc[4 * ih + i][j][1], af[i].y, b1[j]);
     }
   }
 }
@@ -175,9 +177,10 @@ __device__ __forceinline__ void pipeline_setup(uint8_t*& tiles, uint64_t*& full,
 }
 
 // C_b = A_b * op(B_b): persistent tiles, TMA producer + 8 DMMA consumer warps.
-template <bool BT, int EPI>
+template <bool BT, int EPI, int NTW>
 __global__ void __launch_bounds__(T_THREADS, 1)
     tma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TmaGemmArgs p) {
+  constexpr int BN = 32 * NTW, WN = 8 * NTW;     // CTA tile 128 x BN, warp tile 64 x WN
   uint8_t* tiles;
   uint64_t *full, *empty;
   pipeline_setup(tiles, full, empty);
@@ -194,19 +197,19 @@ __global__ void __launch_bounds__(T_THREADS, 1)
         const int mt = (int)(t % p.m_tiles);
         const long r = t / p.m_tiles;
         const int nt_ = (int)(r % p.n_tiles), b = (int)(r / p.n_tiles);
-        const int m0 = mt * T_BM, n0 = nt_ * T_BN;
+        const int m0 = mt * T_BM, n0 = nt_ * BN;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % T_STAGES;
           mbar_wait(empty + s, ((it / T_STAGES) & 1) ^ 1);
-          mbar_expect_tx(full + s, T_STAGE_BYTES);
+          mbar_expect_tx(full + s, T_TILE_BYTES + BN * BK * 8);
           uint8_t* sa = tiles + (size_t)s * T_STAGE_BYTES;
           uint8_t* sb = sa + T_TILE_BYTES;
           tma_load_3d(sa, &tmA, full + s, kb * BK, m0, p.a_batched ? b : 0);
           if (BT) {
-            tma_load_3d(sb, &tmB, full + s, kb * BK, n0, b);
+            tma_load_3d(sb, &tmB, full + s, kb * BK, n0, b);       // box 16 k x BN rows
           } else {
 #pragma unroll
-            for (int x = 0; x < 8; ++x) tma_load_3d(sb + x * 2048, &tmB, full + s, n0 + 16 * x, kb * BK, b);
+            for (int x = 0; x < BN / 16; ++x) tma_load_3d(sb + x * 2048, &tmB, full + s, n0 + 16 * x, kb * BK, b);
           }
         }
       }
@@ -226,17 +229,17 @@ __global__ void __launch_bounds__(T_THREADS, 1)
     const int mt = (int)(t % p.m_tiles);
     const long r = t / p.m_tiles;
     const int nt_ = (int)(r % p.n_tiles), b = (int)(r / p.n_tiles);
-    const int m0 = mt * T_BM, n0 = nt_ * T_BN;
-    double acc[T_MT][4][2];
+    const int m0 = mt * T_BM, n0 = nt_ * BN;
+    double acc[T_MT][NTW][2];
 #pragma unroll
     for (int i = 0; i < T_MT; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+      for (int j = 0; j < NTW; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     for (int kb = 0; kb < nkb; ++kb, ++it) {
       const int s = it % T_STAGES;
       mbar_wait(full + s, (it / T_STAGES) & 1);
       const uint32_t sa = smem_u32(tiles + (size_t)s * T_STAGE_BYTES);
-      tma_mma_kblock<BT, false>(sa, sa + T_TILE_BYTES, acc, wm, wn, g, q, 1.0);
+      tma_mma_kblock<BT, false, NTW>(sa, sa + T_TILE_BYTES, acc, wm, wn, g, q, 1.0);
       __syncwarp();
       if (lane == 0) mbar_arrive(empty + s);
     }
@@ -249,18 +252,18 @@ __global__ void __launch_bounds__(T_THREADS, 1)
       double rr = 1.0;
       if (EPI == TEPI_QUAD) rr = __ldg(p.rD + (long)b * p.ldrd + m);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < NTW; ++j) {
         double v0 = acc[i][j][0], v1 = acc[i][j][1];
         if (EPI == TEPI_QUAD) {
           v0 *= rr;
           v1 *= rr;
         }
         if (BT) {
-          const long na = (long)n0 + wn * T_WN + 8 * j + q, nb = na + 4;
+          const long na = (long)n0 + wn * WN + 8 * j + q, nb = na + 4;
           if (na < p.N) C[(long)m * p.ldc + na] = v0;
           if (nb < p.N) C[(long)m * p.ldc + nb] = v1;
         } else {
-          const long n = (long)n0 + wn * T_WN + 8 * j + 2 * q;
+          const long n = (long)n0 + wn * WN + 8 * j + 2 * q;
           if (n >= p.N) continue;
           const bool two = (n + 1 < p.N);
           if (EPI == TEPI_QUAD) {
@@ -455,9 +458,9 @@ static int make_map3(CUtensorMap* m, const double* base, uint64_t d0, uint64_t d
   return 0;
 }
 
-template <bool BT, int EPI>
+template <bool BT, int EPI, int NTW>
 static int launch_tma_gemm(const CUtensorMap& tA, const CUtensorMap& tB, TmaGemmArgs& p, cudaStream_t st) {
-  auto kern = tma_gemm_kernel<BT, EPI>;
+  auto kern = tma_gemm_kernel<BT, EPI, NTW>;
   static bool attr = false;
   if (!attr) {
     GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_SMEM_BYTES));
@@ -470,9 +473,37 @@ static int launch_tma_gemm(const CUtensorMap& tA, const CUtensorMap& tB, TmaGemm
   return 0;
 }
 
+// Tile width: 128, 96 or 64 columns.  Persistent CTAs run ceil(tiles / SMs) rounds of cost ~BN each, so the
+// narrower tiles win when they shave the ragged last round or the padded last column tile
+// (configs[1]: N = 2000 -> 16 x 128 = 2048 columns in 11 rounds vs 21 x 96 = 2016 columns in 14 rounds: -4.5 %).
+static int pick_ntw(int M, int N, int batch) {
+  const long mt = (M + T_BM - 1) / T_BM, sms = gp_num_sms();
+  int best = 4;
+  double best_cost = 1e300;
+  for (int ntw = 4; ntw >= 2; --ntw) {
+    const int bn = 32 * ntw;
+    const long tiles = mt * ((N + bn - 1) / bn) * batch;
+    const long rounds = (tiles + sms - 1) / sms;
+    const double cost = (double)rounds * (bn + 6.0);      // +6: per-tile prologue/epilogue overhead in column units
+    if (cost < best_cost * 0.995) {
+      best_cost = cost;
+      best = ntw;
+    }
+  }
+  return best;
+}
+
 int tma_gemm_ctas(int M, int N, int batch) {
-  const long ntiles = (long)((M + T_BM - 1) / T_BM) * ((N + T_BN - 1) / T_BN) * batch;
+  const int bn = 32 * pick_ntw(M, N, batch);
+  const long ntiles = (long)((M + T_BM - 1) / T_BM) * ((N + bn - 1) / bn) * batch;
   return (int)(ntiles < gp_num_sms() ? ntiles : gp_num_sms());
+}
+
+template <bool BT, int EPI>
+static int launch_tma_gemm_ntw(int ntw, const CUtensorMap& tA, const CUtensorMap& tB, TmaGemmArgs& p, cudaStream_t st) {
+  if (ntw == 4) return launch_tma_gemm<BT, EPI, 4>(tA, tB, p, st);
+  if (ntw == 3) return launch_tma_gemm<BT, EPI, 3>(tA, tB, p, st);
+  return launch_tma_gemm<BT, EPI, 2>(tA, tB, p, st);
 }
 
 // C_b = A_b op(B_b); epi_quad != 0 fuses the /D + quadratic-form epilogue.  Returns 0 on success.
@@ -481,10 +512,11 @@ int tma_gemm(int transB, int M, int N, int K, const double* A, long lda, long sA
              cudaStream_t st) {
   CUtensorMap tA, tB;
   const bool a_batched = (sA != 0 && batch > 1);
+  const int ntw = pick_ntw(M, N, batch), bn = 32 * ntw;
   if (int e = make_map3(&tA, A, K, M, a_batched ? batch : 1, lda, a_batched ? sA : 0, BK, T_BM, 1)) return e;
   const long sBe = (batch > 1) ? sB : 0;
   if (transB) {
-    if (int e = make_map3(&tB, B, K, N, batch, ldb, sBe, BK, T_BN, 1)) return e;
+    if (int e = make_map3(&tB, B, K, N, batch, ldb, sBe, BK, bn, 1)) return e;
   } else {
     if (int e = make_map3(&tB, B, N, K, batch, ldb, sBe, 16, BK, 1)) return e;
   }
@@ -492,12 +524,12 @@ int tma_gemm(int transB, int M, int N, int K, const double* A, long lda, long sA
   p.C = C; p.ldc = ldc; p.sC = sC;
   p.M = M; p.N = N; p.K = K; p.batch = batch;
   p.m_tiles = (M + T_BM - 1) / T_BM;
-  p.n_tiles = (N + T_BN - 1) / T_BN;
+  p.n_tiles = (N + bn - 1) / bn;
   p.a_batched = a_batched ? 1 : 0;
   p.rD = rD; p.ldrd = ldrd; p.partials = partials;
-  if (epi_quad) return launch_tma_gemm<false, TEPI_QUAD>(tA, tB, p, st);
-  if (transB) return launch_tma_gemm<true, TEPI_STORE>(tA, tB, p, st);
-  return launch_tma_gemm<false, TEPI_STORE>(tA, tB, p, st);
+  if (epi_quad) return launch_tma_gemm_ntw<false, TEPI_QUAD>(ntw, tA, tB, p, st);
+  if (transB) return launch_tma_gemm_ntw<true, TEPI_STORE>(ntw, tA, tB, p, st);
+  return launch_tma_gemm_ntw<false, TEPI_STORE>(ntw, tA, tB, p, st);
 }
 
 int tma_wsyrk(int M, int nseg, int seglen, const double* X, long row_stride, long seg_stride, const double* w, double* C,
