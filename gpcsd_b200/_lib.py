@@ -34,6 +34,8 @@ SIGNATURES = {
     "gpcsd_wsyrk": (c_int, [c_int, c_int, c_int, _P, c_long, c_long, _P, _P, c_long, _P, _P]),
     "gpcsd_eigh_ws_doubles": (c_long, [c_int, c_long]),
     "gpcsd_eigh": (c_int, [c_int, _P, c_long, _P, c_long, _P, _P, c_long, _P, _P]),
+    "gpcsd_eigh_batched_ws_bytes": (c_long, [c_int, c_long, c_int]),
+    "gpcsd_eigh_batched": (c_int, [c_int, c_int, _P, c_long, _P, _P, c_long, _P, _P]),
     "gpcsd_centro_split": (c_int, [c_int, _P, c_long, _P, c_long, _P, c_long, _P]),
     "gpcsd_centro_assemble": (c_int, [c_int, _P, c_long, _P, _P, c_long, _P, _P, c_long, _P, _P]),
     "gpcsd_eig_D": (c_int, [c_int, c_int, _P, _P, _P, c_int, _P, c_long, _P, _P, _P, _P, _P, _P]),

@@ -524,6 +524,49 @@ int gpcsd_sum_vec(long n, const double* in, double* out, void* stream) {
   return 0;
 }
 
+// ---- batched small-order path --------------------------------------------------------------------------------
+// cusolverDnXsyevBatched keeps every matrix of order <= 128 inside one CTA (measured on B200: two 128x128 problems in
+// 0.78 ms, 64 problems of order 50 in 0.39 ms) while a single syevd of order 128 costs 2.1 ms of launch/sync latency;
+// above 128 (or with batch == 1) it is no faster than syevd.  Used for the two halves of the split temporal factor when
+// nt <= 256 and for spatial factors of order <= 128 (batch 2 with the matrix duplicated).
+static cusolverDnParams_t g_params = nullptr;
+static int solver_params(cusolverDnParams_t* p) {
+  std::lock_guard<std::mutex> lock(g_slot_mutex);
+  if (!g_params && cusolverDnCreateParams(&g_params) != CUSOLVER_STATUS_SUCCESS) return gp_fail("cusolverDnCreateParams failed");
+  *p = g_params;
+  return 0;
+}
+
+long gpcsd_eigh_batched_ws_bytes(int n, long ld, int batch) {
+  cusolverDnHandle_t h;
+  cusolverDnParams_t prm;
+  if (solver_handle(&h) || solver_params(&prm)) return -1;
+  size_t wd = 0, wh = 0;
+  cusolverStatus_t s = cusolverDnXsyevBatched_bufferSize(h, prm, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, CUDA_R_64F,
+                                                         nullptr, ld, CUDA_R_64F, nullptr, CUDA_R_64F, &wd, &wh, batch);
+  if (s != CUSOLVER_STATUS_SUCCESS || wh != 0) {
+    gp_fail("cusolverDnXsyevBatched_bufferSize failed (or asks for host workspace)");
+    return -1;
+  }
+  return (long)wd;
+}
+
+int gpcsd_eigh_batched(int n, int batch, double* A, long ld, double* W, void* ws, long ws_bytes, int* info, void* stream) {
+  cusolverDnHandle_t h;
+  cusolverDnParams_t prm;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int e = solver_handle(&h, st)) return e;
+  if (int e = solver_params(&prm)) return e;
+  // in: `batch` symmetric matrices [n][ld] stacked with stride n*ld; out: eigenvectors as ROWS (column-major Q == row-major Q^T)
+  cusolverStatus_t s = cusolverDnXsyevBatched(h, prm, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, CUDA_R_64F, A, ld,
+                                              CUDA_R_64F, W, CUDA_R_64F, ws, (size_t)ws_bytes, nullptr, 0, info, batch);
+  if (s != CUSOLVER_STATUS_SUCCESS) {
+    snprintf(g_err, sizeof(g_err), "cusolverDnXsyevBatched failed with status %d", (int)s);
+    return 3;
+  }
+  return 0;
+}
+
 long gpcsd_eigh_ws_doubles(int n, long ldq) {
   cusolverDnHandle_t h;
   if (solver_handle(&h)) return -1;

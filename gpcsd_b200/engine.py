@@ -271,6 +271,31 @@ class KronEngine:
                    self._stream())
         return QT, W, info
 
+    SMALL_EIGH_MAX = 128        # order limit of cuSOLVER's one-CTA-per-matrix batched path (measured, see csrc)
+
+    def _eigh_small_batched(self, stack, n, ld, batch, tag):
+        """Eigen-decompose `batch` stacked matrices [batch][n][ld] in place (eigenvectors as rows)."""
+        W = self._buf("Wb_" + tag, batch, n)
+        nbytes = L.query("gpcsd_eigh_batched_ws_bytes", n, ld, batch)
+        ws = self._buf("eigbws_" + tag, max((nbytes + 7) // 8, 1))
+        info = self._buf("infob_" + tag, batch, dtype=torch.int32)
+        self._call("gpcsd_eigh_batched", n, batch, self._p(stack), ld, self._p(W), self._p(ws), nbytes, info.data_ptr(),
+                   self._stream())
+        return W, info
+
+    def _eigh_spatial(self, Ks):
+        """Factor of order nx: orders 33..128 go through the batched small-matrix path (batch 2, matrix duplicated --
+        batch 1 would fall back to the latency-bound syevd), everything else is one syevd."""
+        nx, ld = self.nx, self.ldx
+        if not (32 < nx <= self.SMALL_EIGH_MAX):
+            QT, W, info = self._eigh(Ks, nx, ld, "s")
+            return QT, W, [info]
+        stack = self._buf("QT_s2", 2, nx, ld)
+        stack[0].copy_(Ks)
+        stack[1].copy_(Ks)
+        W, info = self._eigh_small_batched(stack, nx, ld, 2, "s")
+        return stack[0], W[0], [info]
+
     def _side_streams(self):
         if self._sides is None:
             self._sides = [torch.cuda.Stream(device=self.device) for _ in range(2)]
@@ -287,6 +312,16 @@ class KronEngine:
             return QT, W, [info]
         m, ms = nt // 2, nt // 2 + (nt & 1)
         lds, lda = _even(ms), _even(m)
+        if nt % 2 == 0 and 2 <= m <= self.SMALL_EIGH_MAX:
+            # both halves have order m <= 128: one batched call, each problem inside a single CTA
+            stack = self._buf("cs_stack", 2, m, lds)
+            self._call("gpcsd_centro_split", nt, self._p(Kt), ldt, self._p(stack), lds, self._p(stack, m * lds), lds,
+                       self._stream())
+            Wb, info = self._eigh_small_batched(stack, m, lds, 2, "t")
+            QT, W = self._buf("QT_t", nt, ldt), self._buf("W_t", nt)
+            self._call("gpcsd_centro_assemble", nt, self._p(stack), lds, self._p(Wb), self._p(stack, m * lds), lds,
+                       self._p(Wb, m), self._p(QT), ldt, self._p(W), self._stream())
+            return QT, W, [info]
         S, A = self._buf("cs_S", ms, lds), self._buf("cs_A", m, lda)
         self._call("gpcsd_centro_split", nt, self._p(Kt), ldt, self._p(S), lds, self._p(A), lda, self._stream())
         main = torch.cuda.current_stream(self.device)
@@ -316,13 +351,13 @@ class KronEngine:
         ks_ready.record(main)
         with torch.cuda.stream(side):
             side.wait_event(ks_ready)
-            st["QsT"], st["ls"], info_s = self._eigh(st["Ks"], self.nx, self.ldx, "s")
+            st["QsT"], st["ls"], infos_s = self._eigh_spatial(st["Ks"])
             s_done = torch.cuda.Event()
             s_done.record(side)
         st["Kt"] = self._temporal_cov(hp)
         st["QtT"], st["lt"], infos_t = self._eigh_temporal(st["Kt"])
         main.wait_event(s_done)
-        st["infos"] = [info_s] + infos_t
+        st["infos"] = infos_s + infos_t
         s_host = np.atleast_1d(np.asarray(hp.sig2n, dtype=np.float64))
         if len(s_host) not in (1, self.nx):
             raise ValueError("sig2n must be a scalar or have one entry per electrode")
@@ -359,7 +394,7 @@ class KronEngine:
 
     # ------------------------------------------------------------------ public evaluations
     def _check_info(self, st):
-        if any(int(i.item()) for i in st["infos"]):
+        if any(bool(torch.any(i != 0).item()) for i in st["infos"]):
             raise np.linalg.LinAlgError("Eigenvalues did not converge")
 
     def loglik(self, hp):

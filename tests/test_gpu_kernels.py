@@ -302,3 +302,30 @@ def test_centrosymmetric_split_is_exact(cuda_lib, n):
     assert relerr(Q.T @ Q, np.eye(n)) < 1e-13
     assert relerr((Q * w) @ Q.T, K) < 1e-13
     assert relerr(np.sort(w), np.linalg.eigvalsh(K)) < 1e-12
+
+
+@pytest.mark.parametrize("n,batch", [(24, 2), (50, 5), (125, 2), (128, 3)])
+def test_eigh_batched_small_orders(cuda_lib, n, batch):
+    from gpcsd_b200 import _lib as L
+    rng = np.random.default_rng(n + batch)
+    ld = _ld(n)
+    Ks = []
+    stack = torch.zeros((batch, n, ld), dtype=F64, device="cuda")
+    for b in range(batch):
+        K = rng.standard_normal((n, n))
+        K = K @ K.T + b * np.eye(n)
+        Ks.append(K)
+        stack[b, :, :n] = torch.from_numpy(K).cuda()
+    W = torch.zeros((batch, n), dtype=F64, device="cuda")
+    nbytes = L.query("gpcsd_eigh_batched_ws_bytes", n, ld, batch)
+    ws = torch.zeros(max((nbytes + 7) // 8, 1), dtype=F64, device="cuda")
+    info = torch.ones(batch, dtype=torch.int32, device="cuda")
+    L.call("gpcsd_eigh_batched", n, batch, stack.data_ptr(), ld, W.data_ptr(), ws.data_ptr(), nbytes, info.data_ptr(), _stream())
+    assert torch.all(info == 0)
+    for b in range(batch):
+        w = W[b].cpu().numpy()
+        Q = stack[b, :, :n].cpu().numpy().T
+        assert np.all(np.diff(w) >= 0)
+        assert relerr(w, np.linalg.eigvalsh(Ks[b])) < 1e-12
+        assert relerr((Q * w) @ Q.T, Ks[b]) < 1e-12
+        assert relerr(Q.T @ Q, np.eye(n)) < 1e-12
