@@ -374,6 +374,40 @@ __global__ void copy_matrix_kernel(int n, const double* __restrict__ in, long ld
   out[(long)i * ldo + j] = in[(long)i * ldi + j];
 }
 
+// Generalisation to any fixed-point-free involution pi of the index set with K[pi(i)][pi(j)] == K[i][j] (e.g. the point
+// reflection of a Neuropixels checkerboard about the centre of the integration box): with representatives ra[] and
+// partners rb[] = pi(ra[]),  S = K[ra,ra] + K[ra,rb],  A = K[ra,ra] - K[ra,rb]  (order n/2 each).
+__global__ void pairsym_split_kernel(int m, const double* __restrict__ K, long ldk, const int* __restrict__ ra,
+                                     const int* __restrict__ rb, double* __restrict__ S, long lds, double* __restrict__ A,
+                                     long lda) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)m * m) return;
+  const int i = (int)(idx / m), j = (int)(idx % m);
+  const double a = K[(long)ra[i] * ldk + ra[j]], b = K[(long)ra[i] * ldk + rb[j]];
+  S[(long)i * lds + j] = a + b;
+  A[(long)i * lda + j] = a - b;
+}
+
+__global__ void pairsym_assemble_kernel(int m, const int* __restrict__ ra, const int* __restrict__ rb,
+                                        const double* __restrict__ UsT, long lds, const double* __restrict__ Ws,
+                                        const double* __restrict__ UaT, long lda, const double* __restrict__ Wa,
+                                        double* __restrict__ QT, long ldq, double* __restrict__ W) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 2L * m * m) return;
+  const int a = (int)(idx / m), c = (int)(idx % m);   // a: eigenvector index 0..2m-1, c: representative index
+  const double h = 0.70710678118654752;
+  if (a < m) {
+    const double v = h * UsT[(long)a * lds + c];
+    QT[(long)a * ldq + ra[c]] = v;
+    QT[(long)a * ldq + rb[c]] = v;
+  } else {
+    const double v = h * UaT[(long)(a - m) * lda + c];
+    QT[(long)a * ldq + ra[c]] = v;
+    QT[(long)a * ldq + rb[c]] = -v;
+  }
+  if (c == 0) W[a] = (a < m) ? Ws[a] : Wa[a - m];
+}
+
 }  // namespace gpcsd
 
 using namespace gpcsd;
@@ -591,6 +625,24 @@ int gpcsd_centro_split(int n, const double* K, long ldk, double* S, long lds, do
 int gpcsd_centro_assemble(int n, const double* UsT, long lds, const double* Ws, const double* UaT, long lda,
                           const double* Wa, double* QT, long ldq, double* W, void* stream) {
   centro_assemble_kernel<<<GRID1D((long)n * n), 0, (cudaStream_t)stream>>>(n, UsT, lds, Ws, UaT, lda, Wa, QT, ldq, W);
+  GP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int gpcsd_pairsym_split(int n, const double* K, long ldk, const int* ra, const int* rb, double* S, long lds, double* A,
+                        long lda, void* stream) {
+  if (n < 2 || (n & 1)) return gp_fail("pairsym_split: n must be even and >= 2");
+  const long m = n / 2;
+  pairsym_split_kernel<<<GRID1D(m * m), 0, (cudaStream_t)stream>>>((int)m, K, ldk, ra, rb, S, lds, A, lda);
+  GP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int gpcsd_pairsym_assemble(int n, const int* ra, const int* rb, const double* UsT, long lds, const double* Ws,
+                           const double* UaT, long lda, const double* Wa, double* QT, long ldq, double* W, void* stream) {
+  if (n < 2 || (n & 1)) return gp_fail("pairsym_assemble: n must be even and >= 2");
+  const long m = n / 2;
+  pairsym_assemble_kernel<<<GRID1D(2 * m * m), 0, (cudaStream_t)stream>>>((int)m, ra, rb, UsT, lds, Ws, UaT, lda, Wa, QT, ldq, W);
   GP_CUDA(cudaGetLastError());
   return 0;
 }

@@ -148,6 +148,44 @@ class KronEngine:
             self.x_dev = self._dev(x.reshape(self.nx, 2))
         self.ldx = _even(self.nx)
         self.ldt = _even(self.nt)
+        self.s_pairs = self._find_reflection_pairs(x, quad)
+
+    def _find_reflection_pairs(self, x, quad):
+        """Fixed-point-free involution pi of the electrode sites induced by the point reflection s -> c - s about the
+        centre of the integration box (c = a + b per dimension; the Gauss-Legendre nodes are symmetric about it).  If
+        the site set is invariant, Ks[pi(i)][pi(j)] == Ks[i][j] and the spatial eigenproblem splits into two
+        independent ones of half the order.  Returns (ra, rb) device int32 arrays or None."""
+        nx = self.nx
+        if nx < 4 or nx % 2:
+            return None
+        if self.dim == 1:
+            g = np.asarray(quad["gl_x"], dtype=np.float64)
+            pts, c = x.reshape(nx, 1), np.array([g.min() + g.max()])
+        else:
+            g1, g2 = np.asarray(quad["gl_x1"], dtype=np.float64), np.asarray(quad["gl_x2"], dtype=np.float64)
+            pts, c = x.reshape(nx, 2), np.array([g1.min() + g1.max(), g2.min() + g2.max()])
+        scale = max(float(np.max(np.abs(pts))), float(np.max(np.abs(c))), 1e-300)
+        key = lambda p: tuple(np.round(p / scale, 11))
+        index = {}
+        for i in range(nx):
+            k = key(pts[i])
+            if k in index:
+                return None            # duplicate sites
+            index[k] = i
+        pi = np.empty(nx, dtype=np.int64)
+        for i in range(nx):
+            j = index.get(key(c - pts[i]))
+            if j is None or j == i:
+                return None
+            pi[i] = j
+        if not np.array_equal(pi[pi], np.arange(nx)):
+            return None
+        # exactness guard: the reflected coordinates must agree to rounding, not just to the matching tolerance
+        if np.max(np.abs((c - pts) - pts[pi])) > 64 * np.finfo(np.float64).eps * scale:
+            return None
+        ra = np.array([i for i in range(nx) if i < pi[i]], dtype=np.int32)
+        rb = pi[ra].astype(np.int32)
+        return (torch.from_numpy(ra).to(self.device), torch.from_numpy(rb).to(self.device))
 
     def set_lfp(self, lfp, local=False):
         """Upload this rank's slab of trials.  lfp: host (nx, nt, ntrials) float64 (C order; numpy array or
@@ -283,10 +321,41 @@ class KronEngine:
                    self._stream())
         return W, info
 
-    def _eigh_spatial(self, Ks):
-        """Factor of order nx: orders 33..128 go through the batched small-matrix path (batch 2, matrix duplicated --
-        batch 1 would fall back to the latency-bound syevd), everything else is one syevd."""
+    def _eigh_pair(self, S, A, m, ld, tag, side):
+        """Eigen-factors of two independent symmetric matrices of order m (leading dimension ld).  Order <= 128: one
+        batched call (S and A must then be the two slabs of one [2][m][ld] stack); larger: two syevd on two streams."""
+        if m <= self.SMALL_EIGH_MAX and A.data_ptr() == S.data_ptr() + 8 * m * ld:
+            Wb, info = self._eigh_small_batched(S, m, ld, 2, tag)
+            return S, Wb[0], A, Wb[1], [info]
+        main = torch.cuda.current_stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(ready)
+            UaT, Wa, info_a = self._eigh(A, m, ld, tag + "a")
+            done = torch.cuda.Event()
+            done.record(side)
+        UsT, Ws, info_s = self._eigh(S, m, ld, tag + "s")
+        main.wait_event(done)
+        return UsT, Ws, UaT, Wa, [info_s, info_a]
+
+    def _eigh_spatial(self, Ks, allow_split):
+        """Factor of order nx.  If the geometry has the point-reflection symmetry (and the eigenvalue order is not needed:
+        scalar noise) the problem is split into two of order nx/2; orders <= 128 go through the batched small-matrix path
+        (batch 2 -- batch 1 would fall back to the latency-bound syevd); everything else is one syevd."""
         nx, ld = self.nx, self.ldx
+        if allow_split and self.s_pairs is not None and nx >= 64:
+            ra, rb = self.s_pairs
+            m = nx // 2
+            ldm = _even(m)
+            stack = self._buf("ps_stack", 2, m, ldm)
+            self._call("gpcsd_pairsym_split", nx, self._p(Ks), ld, ra.data_ptr(), rb.data_ptr(), self._p(stack), ldm,
+                       self._p(stack, m * ldm), ldm, self._stream())
+            UsT, Ws, UaT, Wa, infos = self._eigh_pair(stack[0], stack[1], m, ldm, "sp", self._side_streams()[2])
+            QT, W = self._buf("QT_s", nx, ld), self._buf("W_s", nx)
+            self._call("gpcsd_pairsym_assemble", nx, ra.data_ptr(), rb.data_ptr(), self._p(UsT), ldm, self._p(Ws),
+                       self._p(UaT), ldm, self._p(Wa), self._p(QT), ld, self._p(W), self._stream())
+            return QT, W, infos
         if not (32 < nx <= self.SMALL_EIGH_MAX):
             QT, W, info = self._eigh(Ks, nx, ld, "s")
             return QT, W, [info]
@@ -298,7 +367,7 @@ class KronEngine:
 
     def _side_streams(self):
         if self._sides is None:
-            self._sides = [torch.cuda.Stream(device=self.device) for _ in range(2)]
+            self._sides = [torch.cuda.Stream(device=self.device) for _ in range(3)]
         return self._sides
 
     def _eigh_temporal(self, Kt):
@@ -351,7 +420,7 @@ class KronEngine:
         ks_ready.record(main)
         with torch.cuda.stream(side):
             side.wait_event(ks_ready)
-            st["QsT"], st["ls"], infos_s = self._eigh_spatial(st["Ks"])
+            st["QsT"], st["ls"], infos_s = self._eigh_spatial(st["Ks"], allow_split=not hp.vector_noise)
             s_done = torch.cuda.Event()
             s_done.record(side)
         st["Kt"] = self._temporal_cov(hp)

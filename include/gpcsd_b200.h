@@ -107,6 +107,14 @@ int gpcsd_centro_split(int n, const double* K, long ldk, double* S, long lds, do
 int gpcsd_centro_assemble(int n, const double* UsT, long lds, const double* Ws, const double* UaT, long lda,
                           const double* Wa, double* QT, long ldq, double* W, void* stream);
 
+/* Same split for any fixed-point-free involution pi with K[pi(i)][pi(j)] == K[i][j] (n even): device int arrays
+ * ra[n/2] (representatives) and rb[n/2] = pi(ra).  Used for the spatial factor of geometries that are invariant under the
+ * point reflection about the centre of the integration box (Neuropixels checkerboard, covariances.py:204-232). */
+int gpcsd_pairsym_split(int n, const double* K, long ldk, const int* ra, const int* rb, double* S, long lds, double* A,
+                        long lda, void* stream);
+int gpcsd_pairsym_assemble(int n, const int* ra, const int* rb, const double* UsT, long lds, const double* Ws,
+                           const double* UaT, long lda, const double* Wa, double* QT, long ldq, double* W, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * D and its reductions (utility_functions.py:54-63; gpcsd1d.py:122):
  *   D_ij = ls_i * lt_j + s_i  (s = sig2n[0] if n_sig2n == 1 else sig2n[i], i = ASCENDING spatial eigen-index)

@@ -68,7 +68,7 @@ def main():
     for nt in args.nt:
         X, t = neuropixels_geometry(args.nch, nt)
         g1, w1 = gl(-16.0, 64.0, 30)
-        g2, w2 = gl(-100.0, 3940.0, 120)
+        g2, w2 = gl(-100.0, float(X[:, 1].max()) + 100.0, 120)   # fit_gpcsd2d.py:86-90
         eng = KronEngine(2, X, t, dict(gl_x1=g1, gl_w1=w1, gl_x2=g2, gl_w2=w2), group=(True if world > 1 else None))
         hp = HyperParams(R=100.0, ells=(40.0, 200.0), temporal=[(0, 5.0, 1e-10), (1, 1.0, 1.4e-10)], sig2n=0.5, eps=1.0)
         for N in args.trials:

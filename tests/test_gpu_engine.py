@@ -180,3 +180,36 @@ def test_temporal_eigh_paths_agree_with_oracle(cuda_lib, nt, uniform):
     out = eng.predict(hp, x, t, "csd")
     ref = O.predict_kron(om, lfp, x, t, "csd")
     assert relerr(out["csd_pred"], ref["csd_pred"]) < TOL_PRED
+
+
+def test_spatial_reflection_symmetry_split(cuda_lib):
+    """Neuropixels-like checkerboard with symmetric integration bounds: the point reflection about the box centre maps
+    the sites onto themselves, the engine splits the spatial eigenproblem, and results still match the oracle.  A shifted
+    box (no symmetry) and per-electrode noise (eigenvalue order needed) must take the unsplit path."""
+    from oracle import gpcsd_oracle as O, synth
+    X, t = synth.geometry_neuropixels(96, 40, 0.4)
+    ymax = X[:, 1].max()
+    om = synth.model_2d(X, t, ngl1=10, ngl2=40, a1=-16.0, b1=64.0, a2=-100.0, b2=ymax + 100.0, eps=1.0, sig2n=0.5)
+    lfp = synth.matched_lfp(om, 7, 12)
+    eng, hp = engine_from_oracle(om, lfp)
+    assert eng.s_pairs is not None and eng.s_pairs[0].numel() == 48
+    ll, grad = eng.loglik_grad(hp)
+    ll_o, grad_o = O.loglik_and_grad(om, lfp)
+    assert abs(ll - ll_o) / abs(ll_o) < TOL_LL
+    assert np.max(np.abs(grad - grad_o) / np.abs(grad_o)) < grad_tol(om, lfp)
+    out = eng.predict(hp, X[::7], t, "both")
+    ref = O.predict_kron(om, lfp, X[::7], t, "both")
+    assert relerr(out["csd_pred"], ref["csd_pred"]) < TOL_PRED and relerr(out["lfp_pred"], ref["lfp_pred"]) < TOL_PRED
+    # shifted box: not symmetric
+    om_shift = synth.model_2d(X, t, ngl1=10, ngl2=40, a1=-16.0, b1=64.0, a2=-100.0, b2=ymax + 140.0, eps=1.0, sig2n=0.5)
+    eng2, hp2 = engine_from_oracle(om_shift, lfp)
+    assert eng2.s_pairs is None
+    assert abs(eng2.loglik(hp2) - O.loglik(om_shift, lfp)) / abs(O.loglik(om_shift, lfp)) < TOL_LL
+    # 1-D probe with symmetric bounds and per-electrode noise: symmetry detected but NOT used (ascending order matters)
+    x1, t1 = synth.geometry_1d(24, 40)
+    rng = np.random.default_rng(0)
+    om1 = synth.model_1d(x1, t1, sig2n=1e-2 * np.exp(0.3 * rng.standard_normal(24)))
+    lfp1 = synth.matched_lfp(om1, 5, 3)
+    eng3, hp3 = engine_from_oracle(om1, lfp1)
+    assert eng3.s_pairs is not None
+    assert abs(eng3.loglik(hp3) - O.loglik(om1, lfp1)) / abs(O.loglik(om1, lfp1)) < 1e-8

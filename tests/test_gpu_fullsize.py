@@ -62,10 +62,12 @@ def test_config3_neuropixels_full_size(cuda_lib):
     """configs[2]: 384 ch (4 columns x 192 rows, checkerboard) x 250 t x 500 trials, ngl 30 x 120, eps = 1."""
     from oracle import gpcsd_oracle as O, synth
     X, t = synth.geometry_neuropixels(384, 250, 0.4)
-    om = synth.model_2d(X, t, ngl1=30, ngl2=120, a1=-16.0, b1=64.0, a2=-100.0, b2=3940.0, eps=1.0, sig2n=0.5)
+    # integration box as in neuropixels/fit_gpcsd2d.py:86-90: min - 16 .. max + 16, min - 100 .. max + 100
+    om = synth.model_2d(X, t, ngl1=30, ngl2=120, a1=-16.0, b1=64.0, a2=-100.0, b2=float(X[:, 1].max()) + 100.0, eps=1.0, sig2n=0.5)
     lfp = _device_matched_lfp(om, 500, 30)
     om2 = synth.perturbed(om, 31, scale=0.05)
     eng, hp = engine_from_oracle(om2, lfp)
+    assert eng.s_pairs is not None                    # checkerboard + symmetric box: point-reflection symmetry is found
     ll, grad = eng.loglik_grad(hp)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
