@@ -16,6 +16,14 @@ from .parallel import RestartShard
 np.seterr(all='ignore')  # gpcsd1d.py:7 -- NaN/inf propagate as values
 
 
+class _nullcontext:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
 def _is_scalar(v):
     return np.isscalar(v) or np.ndim(v) == 0
 
@@ -177,8 +185,47 @@ class GPCSDModelBase:
             grad[0] = 0.0
         return -1.0 * (ll + lp), grad
 
+    def _pure_objective(self, engine, fix_R):
+        """(nll, d nll / d tparams) as a function of tparams that does NOT write into the model's dictionaries, bound to
+        its own engine: what the concurrent restarts of fit() optimise.  Same arithmetic as obj_fun_and_grad."""
+        slots = self._param_slots()
+        scales = np.array([sc for _, sc in slots], dtype=np.float64)
+        priors = [d['prior'] for d, _ in slots]
+        noise_scalar = self._noise_is_scalar()
+        priors += [self.sig2n['prior']] if noise_scalar else list(self.sig2n['prior'])
+        nslots, nsp = len(slots), len(self.SPATIAL_ELL_KEYS)
+        kinds = [tc.KIND for tc in self.temporal_cov_list]
+        R_fixed = float(self.R['value'])
+        eps = float(getattr(self, "eps", 0.0) or 0.0)
+        dim = self.DIM
+
+        def fun(tparams):
+            tp = np.asarray(tparams, dtype=np.float64)
+            vals = np.exp(tp)
+            vals[:nslots] *= scales
+            if fix_R:
+                vals[0] = R_fixed
+            lp = 0.0
+            for p, v in zip(priors, vals):
+                lp = lp + p.lpdf(v)
+            dlp = np.array([p.dlpdf(v) if v > 0 else 0.0 for p, v in zip(priors, vals)])
+            temporal = [(kinds[k], float(vals[1 + nsp + 2 * k]), float(vals[2 + nsp + 2 * k])) for k in range(len(kinds))]
+            sig = float(vals[nslots]) if noise_scalar else np.array(vals[nslots:])
+            hp = HyperParams(R=float(vals[0]), ells=tuple(float(v) for v in vals[1:1 + nsp]), temporal=temporal, sig2n=sig, eps=eps)
+            try:
+                ll, g = engine.loglik_grad(hp)
+            except np.linalg.LinAlgError:
+                if dim == 1:
+                    raise
+                return np.inf, np.zeros(len(vals))                  # gpcsd2d.py:215-219
+            grad = -(np.asarray(g) + dlp) * vals
+            if fix_R:
+                grad[0] = 0.0
+            return -1.0 * (ll + lp), grad
+        return fun
+
     # ------------------------------------------------------------------ fit
-    def _fit(self, n_restarts, method, fix_R, verbose, options):
+    def _fit(self, n_restarts, method, fix_R, verbose, options, n_workers=2):
         bounds = self._bounds()
         options = dict(options)
         if method == 'L-BFGS-B' and not options.get('disp', False):
@@ -187,18 +234,57 @@ class GPCSDModelBase:
         # from the same point whatever the world size) and optimises only its own share of them.
         shard = RestartShard(getattr(self, "_restart_group", None))
         starts = [self._sample_tparams0(fix_R) for _ in range(n_restarts)]
-        local = {}
-        for i in tqdm(range(n_restarts), desc="Restarts", disable=shard.rank != 0):
-            if not shard.mine(i):
-                continue
+        mine = [i for i in range(n_restarts) if shard.mine(i)]
+        # Restarts are independent: run up to n_workers of them concurrently, one host thread + CUDA stream + engine
+        # workspace each (all sharing the uploaded LFP), so one restart's latency-bound syevd overlaps another's GEMMs.
+        # Trial-sharded models keep one worker: collectives of concurrent evaluations must not interleave.
+        if getattr(self, "_group", None) is not None:
+            n_workers = 1
+        n_workers = max(1, min(int(n_workers), len(mine)))
+        base = self._get_engine()
+        engines = [base]
+        for _ in range(n_workers - 1):
+            e = KronEngine(self.DIM, self.x, self.t, self._quadrature(), group=getattr(self, "_group", None), jitter=self.JITTER)
+            e.share_data_with(base)
+            engines.append(e)
+        import queue
+        import threading
+        import torch
+        free = queue.Queue()
+        for e in engines:
+            free.put((e, torch.cuda.Stream(device=e.device) if n_workers > 1 else None))
+        local, lock = {}, threading.Lock()
+        bar = tqdm(total=n_restarts, desc="Restarts", disable=shard.rank != 0)
+
+        def run(i):
+            eng, stream = free.get()
             try:
-                res = scipy.optimize.minimize(lambda tp: self.obj_fun_and_grad(tp, fix_R), starts[i], jac=True,
-                                              method=method, options=options, bounds=bounds)
-                local[i] = (float(res.fun), np.asarray(res.x, dtype=np.float64), str(res.message))
+                if stream is not None:
+                    torch.cuda.set_device(eng.device)       # worker threads start on device 0
+                ctx = torch.cuda.stream(stream) if stream is not None else _nullcontext()
+                with ctx:
+                    res = scipy.optimize.minimize(self._pure_objective(eng, fix_R), starts[i], jac=True, method=method,
+                                                  options=options, bounds=bounds)
+                with lock:
+                    local[i] = (float(res.fun), np.asarray(res.x, dtype=np.float64), str(res.message))
             except (ValueError, np.linalg.LinAlgError) as e:
                 print(e)
                 if self.DIM == 2:
                     print('\nrestarting optimization...')
+            finally:
+                free.put((eng, stream))
+                with lock:
+                    bar.update(1)
+
+        if n_workers == 1:
+            for i in mine:
+                run(i)
+        else:
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=n_workers) as pool:
+                list(pool.map(run, mine))
+        bar.update(n_restarts - len(mine))
+        bar.close()
         merged = shard.gather(local)
         nll_values, params, term_msg = [], [], []
         for i in sorted(merged):

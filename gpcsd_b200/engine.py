@@ -76,6 +76,14 @@ class KronEngine:
         self._y_ready = None
         self.timers = None      # {abi_name: [(start_event, end_event), ...]} when bench.py profiles a kernel
 
+    def share_data_with(self, other):
+        """Evaluate on `other`'s uploaded LFP (no copy): lets several engines -- one per concurrent multi-start restart,
+        each with its own workspaces and streams -- work on the same device-resident data."""
+        if (other.nx, other.nt) != (self.nx, self.nt):
+            raise ValueError("engines have different geometry")
+        self.Y, self.ntrials, self.ntrials_total, self.ldn = other.Y, other.ntrials, other.ntrials_total, other.ldn
+        self._y_ready = other._y_ready
+
     # ------------------------------------------------------------------ plumbing
     def _dev(self, arr):
         return torch.as_tensor(np.ascontiguousarray(arr, dtype=np.float64)).to(self.device)
@@ -211,6 +219,7 @@ class KronEngine:
         ldn = _ld8(max(n, 1))
         if self.Y is None or self.Y.shape != (self.nx, self.nt, ldn):
             self.Y = torch.zeros((self.nx, self.nt, ldn), dtype=F64, device=self.device)
+            self._ws.clear()                                   # workspaces sized by the old trial count are dropped
         slab = src[:, :, lo:hi]
         if src.is_cuda:
             self.Y[:, :, :n].copy_(slab)

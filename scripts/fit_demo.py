@@ -16,30 +16,32 @@ import bench  # noqa: E402
 
 def main():
     n_restarts = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+    n_workers = int(sys.argv[2]) if len(sys.argv) > 2 else 2
     torch.cuda.set_device(0)
     import __graft_entry__ as ge
     ge.ensure_built()
     m = bench.make_models(torch.device("cuda", 0), 1, torch)[0]
     truth = m.extract_model_params()
+    from gpcsd_b200.engine import KronEngine
     count = {"n": 0}
-    orig = m.obj_fun_and_grad
+    orig = KronEngine.loglik_grad
 
-    def counted(tp, fix_R=False):
+    def counted(self, hp):
         count["n"] += 1
-        return orig(tp, fix_R)
-    m.obj_fun_and_grad = counted
+        return orig(self, hp)
+    KronEngine.loglik_grad = counted
     np.random.seed(0)
     f_true = m.obj_fun(np.log(np.array([truth['R'] / 100, truth['spatial_ell'] / 100] +
                                        [v for pair in zip(truth['temporal_ell_list'], truth['temporal_sigma2_list']) for v in pair] +
                                        list(truth['sig2n']))))
     t0 = time.perf_counter()
-    m.fit(n_restarts=n_restarts, verbose=True)
+    m.fit(n_restarts=n_restarts, verbose=True, n_workers=n_workers)
     dt = time.perf_counter() - t0
     fit = m.extract_model_params()
     tp = np.log(np.array([fit['R'] / 100, fit['spatial_ell'] / 100] +
                          [v for pair in zip(fit['temporal_ell_list'], fit['temporal_sigma2_list']) for v in pair] + list(fit['sig2n'])))
     f_fit = m.obj_fun(tp)
-    print("fit: %d restarts, %d objective+gradient evaluations, %.2f s wall (%.1f ms per evaluation)" % (n_restarts, count["n"], dt, 1e3 * dt / max(count["n"], 1)))
+    print("fit: %d restarts (%d workers), %d objective+gradient evaluations, %.2f s wall (%.1f ms per evaluation)" % (n_restarts, n_workers, count["n"], dt, 1e3 * dt / max(count["n"], 1)))
     print("nll at generating parameters %.3f, at fitted parameters %.3f" % (f_true, f_fit))
     print("R %.1f -> %.1f | ell %.1f -> %.1f | ell_t %s -> %s" % (truth['R'], fit['R'], truth['spatial_ell'], fit['spatial_ell'],
                                                               np.round(truth['temporal_ell_list'], 2), np.round(fit['temporal_ell_list'], 2)))

@@ -94,14 +94,18 @@ class _StubModel:
             DIM = 1
             SPATIAL_ELL_KEYS = ('ell',)
 
-            def obj_fun_and_grad(self, tparams, fix_R=False):
-                self._set_tparams(tparams, fix_R)
-                tp = np.asarray(tparams)
-                target = np.linspace(-0.5, 0.5, tp.size)
-                # two basins so that different starts end in different local minima
-                f = np.sum((tp - target) ** 2 * ((tp - target - 1.5) ** 2 + 0.3))
-                g = 2 * (tp - target) * ((tp - target - 1.5) ** 2 + 0.3) + (tp - target) ** 2 * 2 * (tp - target - 1.5)
-                return float(f), g
+            def _get_engine(self):
+                return None
+
+            def _pure_objective(self, engine, fix_R):
+                def fun(tparams):
+                    tp = np.asarray(tparams)
+                    target = np.linspace(-0.5, 0.5, tp.size)
+                    # two basins so that different starts end in different local minima
+                    f = np.sum((tp - target) ** 2 * ((tp - target - 1.5) ** 2 + 0.3))
+                    g = 2 * (tp - target) * ((tp - target - 1.5) ** 2 + 0.3) + (tp - target) ** 2 * 2 * (tp - target - 1.5)
+                    return float(f), g
+                return fun
 
         m = M()
         ig = GPCSDInvGammaPrior(); ig.set_params(50.0, 500.0)
@@ -126,7 +130,7 @@ class _StubModel:
 def _fit_stub(restart_group, seed=11, n_restarts=6):
     np.random.seed(seed)
     m = _StubModel(restart_group)
-    m._fit(n_restarts, 'L-BFGS-B', False, False, {'maxiter': 200, 'gtol': 1e-10})
+    m._fit(n_restarts, 'L-BFGS-B', False, False, {'maxiter': 200, 'gtol': 1e-10}, n_workers=1)
     return np.array([m.R['value'], m.spatial_cov.params['ell']['value'], m.sig2n['value']] +
                     [tc.params[k]['value'] for tc in m.temporal_cov_list for k in ('ell', 'sigma2')])
 

@@ -156,3 +156,22 @@ def test_update_lfp_reuploads(cuda_lib, golden_dir):
     assert abs(ll1 - float(g["loglik"])) < 1e-9 * abs(ll1) and ll2 != ll1
     m.update_lfp(g["lfp"], g["t"])
     assert abs(float(m.loglik()) - ll1) < 1e-12 * abs(ll1)
+
+
+def test_fit_concurrent_workers_match_sequential(cuda_lib):
+    """fit(n_workers=2) -- restarts on two threads/streams/engines sharing the uploaded LFP -- must end at exactly the
+    parameters of the sequential fit (same starts, deterministic kernels)."""
+    from gpcsd_b200.gpcsd1d import GPCSD1D
+    from oracle import synth
+    x, t = synth.geometry_1d(24, 40)
+    om = synth.model_1d(x, t, sig2n=1e-2)
+    lfp = synth.matched_lfp(om, 25, 17)
+    opts = {'maxiter': 40, 'disp': False, 'gtol': 1e-5, 'ftol': 1e7 * np.finfo(float).eps}
+    out = []
+    for workers in (1, 2):
+        np.random.seed(5)
+        m = GPCSD1D(lfp, x, t)
+        m.fit(n_restarts=4, options=opts, n_workers=workers)
+        p = m.extract_model_params()
+        out.append(np.array([p['R'], p['spatial_ell'], p['sig2n']] + p['temporal_ell_list'] + p['temporal_sigma2_list']))
+    assert np.array_equal(out[0], out[1])
