@@ -636,23 +636,32 @@ class KronEngine:
                 self.gemm(0, nt, nt, nt, KtsT, self.ldt, 0, Qt, self.ldt, 0, Tk, self.ldt, 0)
                 out = torch.empty((nz, nt, ldn), dtype=F64, device=self.device)
                 self.gemm(0, nt, max(N, 1), nt, Tk, self.ldt, 0, V, ldn, nt * ldn, out, ldn, nt * ldn, batch=nz)
-                parts.append(out)
+                parts.append(self._maybe_download(out, N, to_host))
             tot = torch.empty((nz, nt, ldn), dtype=F64, device=self.device)
-            ptrs = (ctypes.c_void_p * len(parts))(*[p.data_ptr() for p in parts])
+            ptrs = (ctypes.c_void_p * len(parts))(*[(p[0] if to_host else p).data_ptr() for p in parts])
             self._call("gpcsd_sum_arrays", nz * nt * ldn, len(parts), ptrs, self._p(tot), self._stream())
-            results[name + "_pred"] = tot
+            results[name + "_pred"] = self._maybe_download(tot, N, to_host)
             results[name + "_pred_list"] = parts
         self._check_info(st)
         if not to_host:
             return {k: ([p[:, :, :N] for p in v] if isinstance(v, list) else v[:, :, :N]) for k, v in results.items()}
-        # device -> host: async DMA into pinned buffers (torch's caching host allocator recycles them), one sync
-        host = {}
-        for k, v in results.items():
-            host[k] = [self._to_host(p, N) for p in v] if isinstance(v, list) else self._to_host(v, N)
-        torch.cuda.current_stream(self.device).synchronize()
-        return {k: ([h.numpy() for h in v] if isinstance(v, list) else v.numpy()) for k, v in host.items()}
+        # every output has been streaming to pinned host memory on the copy stream since it was produced
+        self._copy_stream.synchronize()
+        return {k: ([h[1].numpy() for h in v] if isinstance(v, list) else v[1].numpy()) for k, v in results.items()}
 
-    def _to_host(self, dev, N):
-        out = torch.empty((dev.shape[0], dev.shape[1], N), dtype=F64, pin_memory=True)
-        out.copy_(dev[:, :, :N], non_blocking=True)
-        return out
+    def _maybe_download(self, dev, N, to_host):
+        """to_host: start the device->host DMA of a finished output on the copy stream (overlaps the GEMMs of the next
+        temporal component; pinned buffers come from torch's caching host allocator) and return (device, host)."""
+        if not to_host:
+            return dev
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream(self.device))
+        host = torch.empty((dev.shape[0], dev.shape[1], N), dtype=F64, pin_memory=True)
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(done)
+            host.copy_(dev[:, :, :N], non_blocking=True)
+            dev.record_stream(self._copy_stream)
+        return (dev, host)
+
