@@ -200,6 +200,10 @@ class GPCSDModelBase:
         dim = self.DIM
 
         def fun(tparams):
+            with np.errstate(all='ignore'):        # numpy's error state is per thread; gpcsd1d.py:7 semantics in the workers too
+                return _fun(tparams)
+
+        def _fun(tparams):
             tp = np.asarray(tparams, dtype=np.float64)
             vals = np.exp(tp)
             vals[:nslots] *= scales
