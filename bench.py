@@ -461,7 +461,7 @@ def run_gpu(args):
                         "d2h_bytes_per_step": NPROBES * (8 + 2 * 2 + 2 * NX) * 8,
                         "api": "GPCSD1D.update_lfp(pinned lfp) + GPCSD1D.obj_fun_and_grad(tparams)"},
                 "gpu_launches": launches,
-                "roofline": {"bound": "tensor", "kernel": "tma_gemm_kernel<NN,EPI_QUAD> (gpcsd_project_quad: persistent TMA+mbarrier DMMA GEMM, fused /D + quadratic form)",
+                "roofline": {"bound": "tensor", "kernel": "tma_gemm_kernel<NN,EPI_QUAD,NTW=3> (gpcsd_project_quad: persistent TMA+mbarrier DMMA GEMM, 128x96 tiles, fused /D + quadratic form)",
                              "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                              "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                              "algorithmic_flops_per_launch": algo_flops, "avg_launch_ms": dur_ms,
