@@ -17,8 +17,8 @@ replicated (recomputed deterministically on every rank); partial (loglik, gradie
 with ONE all-reduce of P+1 doubles per evaluation.  ``predict`` needs no collective.
 """
 import ctypes
-from dataclasses import dataclass, field
-from typing import List, Optional, Sequence, Tuple, Union
+from dataclasses import dataclass
+from typing import List, Tuple, Union
 
 import numpy as np
 import torch

@@ -22,7 +22,7 @@ Pinning status
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may import this.
 """
 from dataclasses import dataclass, field
-from typing import List, Optional, Sequence, Tuple, Union
+from typing import List, Tuple, Union
 
 import numpy as np
 import scipy.special
