@@ -41,6 +41,11 @@ def test_config2_auditory_full_size(cuda_lib):
     dt = time.perf_counter() - t0
     ll_o = O.loglik(om2, lfp)                                   # the reference's literal trial loop
     assert abs(ll - ll_o) / abs(ll_o) < 1e-9
+    # full 30-component gradient against the oracle's closed form (per-electrode noise: eigenvector-identity
+    # conditioned, SURVEY.md section 6 -> 1e-4 on the noise components, 1e-7 on the kernel hyperparameters)
+    _, grad_o = O.loglik_and_grad(om2, lfp)
+    rel = np.abs(grad - grad_o) / np.maximum(np.abs(grad_o), 1e-6 * np.max(np.abs(grad_o)))
+    assert np.max(rel[:6]) < 1e-7 and np.max(rel[6:]) < 1e-4, rel
     # trial additivity: loglik(all) == loglik(first 700) + loglik(remaining 1300)
     e1, _ = engine_from_oracle(om2, lfp[:, :, :700])
     e2, _ = engine_from_oracle(om2, lfp[:, :, 700:])
@@ -79,6 +84,8 @@ def test_config3_neuropixels_full_size(cuda_lib):
     dt_cpu = time.perf_counter() - t0
     assert abs(ll - ll_o) / abs(ll_o) < 1e-9
     assert len(grad) == 8 and np.all(np.isfinite(grad))
+    _, grad_o = O.loglik_and_grad(om2, lfp)                     # scalar noise: no eigen-gap division anywhere
+    assert np.max(np.abs(grad - grad_o) / np.abs(grad_o)) < 1e-8
     tp = O.pack_tparams(om2)
     d = np.random.default_rng(4).standard_normal(tp.shape)
     d /= np.linalg.norm(d)
