@@ -175,3 +175,28 @@ def test_fit_concurrent_workers_match_sequential(cuda_lib):
         p = m.extract_model_params()
         out.append(np.array([p['R'], p['spatial_ell'], p['sig2n']] + p['temporal_ell_list'] + p['temporal_sigma2_list']))
     assert np.array_equal(out[0], out[1])
+
+
+def test_fit_fix_R_and_changing_trial_counts(cuda_lib):
+    """fix_R=True keeps R (gpcsd1d.py:161,195-196,234); update_lfp with a different trial count re-sizes the device
+    buffers; both give oracle-consistent likelihoods afterwards."""
+    from gpcsd_b200.gpcsd1d import GPCSD1D
+    from oracle import gpcsd_oracle as O, synth
+    x, t = synth.geometry_1d(24, 36)
+    om = synth.model_1d(x, t, sig2n=1e-2)
+    lfp = synth.matched_lfp(om, 21, 8)
+    np.random.seed(9)
+    m = GPCSD1D(lfp[:, :, :12], x, t)
+    m.R['value'] = 123.0
+    m.fit(n_restarts=2, fix_R=True, options={'maxiter': 25, 'disp': False, 'gtol': 1e-5, 'ftol': 1e7 * np.finfo(float).eps})
+    assert m.R['value'] == 123.0
+    for n in (21, 5, 16):                                   # grow, shrink, grow: buffers follow the trial count
+        m.update_lfp(lfp[:, :, :n], t)
+        p = m.extract_model_params()
+        om_fit = O.Model(1, om.spatial, t, p['R'], (p['spatial_ell'],),
+                         [(0, p['temporal_ell_list'][0], p['temporal_sigma2_list'][0]), (1, p['temporal_ell_list'][1], p['temporal_sigma2_list'][1])],
+                         float(p['sig2n']))
+        ll, ll_o = float(m.loglik()), O.loglik(om_fit, lfp[:, :, :n])
+        assert abs(ll - ll_o) < 1e-9 * abs(ll_o)
+        m.predict(x, t)
+        assert m.csd_pred.shape == (24, 36, n)
