@@ -98,6 +98,14 @@ int gpcsd_eigh(int n, const double* K, long ldk, double* QT, long ldq, double* W
 long gpcsd_eigh_batched_ws_bytes(int n, long ld, int batch);
 int gpcsd_eigh_batched(int n, int batch, double* A, long ld, double* W, void* ws, long ws_bytes, int* info, void* stream);
 
+/* Building blocks of the in-house eigensolver for orders 130..256 (gpcsd_eig.cu; see gpcsd_eigh_dc below):
+ * Householder tridiagonalisation M = H T H^T of `nmat` stacked matrices on 8-CTA clusters (matrix resident in distributed
+ * shared memory), and the back-transformation of eigenvectors stored as rows.  d[nmat][n], e[nmat][n] (e[k] = T[k+1][k]),
+ * V[nmat][n][ldv] (row k = reflector k, implicit 1 at column k+1), tau[nmat][n]. */
+int gpcsd_tridiag(int n, int nmat, const double* M, long ldm, double* d, double* e, double* V, long ldv, double* tau,
+                  void* stream);
+int gpcsd_backtransform(int n, int nmat, const double* V, long ldv, const double* tau, double* XT, long ldx, void* stream);
+
 /* Exact centrosymmetric split of a symmetric Toeplitz (more generally J K J = K) matrix -- every stationary
  * temporal kernel of covariances.py:257-305 on a uniform time grid -- into two independent half-size
  * eigenproblems (Cantoni & Butler 1976), so the np.linalg.eigh(Kt) of utility_functions.py:58 costs two
