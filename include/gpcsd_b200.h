@@ -98,12 +98,24 @@ int gpcsd_eigh(int n, const double* K, long ldk, double* QT, long ldq, double* W
 long gpcsd_eigh_batched_ws_bytes(int n, long ld, int batch);
 int gpcsd_eigh_batched(int n, int batch, double* A, long ld, double* W, void* ws, long ws_bytes, int* info, void* stream);
 
-/* Building blocks of the in-house eigensolver for orders 130..256 (gpcsd_eig.cu; see gpcsd_eigh_dc below):
- * Householder tridiagonalisation M = H T H^T of `nmat` stacked matrices on 8-CTA clusters (matrix resident in distributed
- * shared memory), and the back-transformation of eigenvectors stored as rows.  d[nmat][n], e[nmat][n] (e[k] = T[k+1][k]),
- * V[nmat][n][ldv] (row k = reflector k, implicit 1 at column k+1), tau[nmat][n]. */
+/* In-house symmetric eigensolver for orders 3..256 (gpcsd_eig.cu), one 8-CTA thread-block cluster per matrix, batched:
+ * replaces np.linalg.eigh of comp_eig_D (utility_functions.py:58-59) where cuSOLVER syevd is latency-bound.
+ * M[nmat][n][ldm] symmetric (not modified) -> QT[nmat][n][ldq] (rows = eigenvectors), W[nmat][n] ascending. */
+long gpcsd_eigh_dc_ws_doubles(int n, long ldq, int nmat);
+int gpcsd_eigh_dc(int n, int nmat, const double* M, long ldm, double* QT, long ldq, double* W, double* ws, long ws_doubles,
+                  void* stream);
+
+/* Its three stages, exported for tests and reuse:
+ * (1) Householder tridiagonalisation M = H T H^T (matrix resident in distributed shared memory): d[nmat][n], e[nmat][n]
+ *     (e[k] = T[k+1][k]), V[nmat][n][ldv] (row k = reflector k, implicit 1 at column k+1), tau[nmat][n];
+ * (2) divide-and-conquer eigen-decomposition of the tridiagonal matrices (Cuppen / Gu-Eisenstat): W ascending, XT rows =
+ *     eigenvectors of T; ws = 2*nmat*n*ldx doubles;
+ * (3) back-transformation of eigenvectors stored as rows, in place. */
 int gpcsd_tridiag(int n, int nmat, const double* M, long ldm, double* d, double* e, double* V, long ldv, double* tau,
                   void* stream);
+long gpcsd_tridiag_eig_ws_doubles(int n, long ldx, int nmat);
+int gpcsd_tridiag_eig(int n, int nmat, const double* d, const double* e, double* W, double* XT, long ldx, double* ws,
+                      long ws_doubles, void* stream);
 int gpcsd_backtransform(int n, int nmat, const double* V, long ldv, const double* tau, double* XT, long ldx, void* stream);
 
 /* Exact centrosymmetric split of a symmetric Toeplitz (more generally J K J = K) matrix -- every stationary

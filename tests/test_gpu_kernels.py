@@ -370,3 +370,86 @@ def test_cluster_tridiagonalisation_and_backtransform(cuda_lib, n, nmat):
         scale = np.max(np.abs(Ms[b]))
         assert np.max(np.abs(Q.T @ Q - np.eye(n))) < 1e-12
         assert np.max(np.abs(Ms[b] @ Q - Q * lams[b])) < 1e-12 * scale * n
+
+
+def _tridiag_cases(n, rng):
+    t = np.arange(n) * 0.7
+    dd = t[:, None] - t[None, :]
+    import scipy.linalg
+    H = scipy.linalg.hessenberg(3.0 * np.exp(-0.5 * dd ** 2 / 30.0))
+    yield np.diag(H).copy(), np.diag(H, -1).copy()                       # SE kernel: numerically degenerate tail
+    yield rng.standard_normal(n), rng.standard_normal(n - 1)
+    yield np.abs(np.arange(n) - (n - 1) / 2), np.ones(n - 1)             # Wilkinson
+    yield 2 * np.ones(n), -np.ones(n - 1)
+    yield np.ones(n), np.zeros(n - 1)
+    yield np.tile(np.arange(1, 6.0), (n + 4) // 5)[:n], np.where(np.arange(n - 1) % 5 == 4, 1e-9, 1.0)   # glued
+
+
+@pytest.mark.parametrize("n", [2, 3, 7, 24, 33, 64, 65, 125, 192, 250, 256])
+def test_tridiag_eig_divide_and_conquer(cuda_lib, n):
+    """Cluster divide-and-conquer eigensolver on tridiagonal matrices vs LAPACK (batched: all cases in one launch)."""
+    import scipy.linalg
+    from gpcsd_b200 import _lib as L
+    rng = np.random.default_rng(n)
+    cases = list(_tridiag_cases(n, rng))
+    nmat, ld = len(cases), _ld(n)
+    d = torch.zeros((nmat, n), dtype=F64, device="cuda")
+    e = torch.zeros((nmat, n), dtype=F64, device="cuda")
+    for b, (dh, eh) in enumerate(cases):
+        d[b] = torch.from_numpy(dh).cuda()
+        e[b, : n - 1] = torch.from_numpy(eh).cuda()
+    W = torch.zeros((nmat, n), dtype=F64, device="cuda")
+    XT = torch.full((nmat, n, ld), 7.0, dtype=F64, device="cuda")
+    nws = L.query("gpcsd_tridiag_eig_ws_doubles", n, ld, nmat)
+    ws = torch.full((nws,), float("nan"), dtype=F64, device="cuda")      # the workspace may hold anything
+    L.call("gpcsd_tridiag_eig", n, nmat, d.data_ptr(), e.data_ptr(), W.data_ptr(), XT.data_ptr(), ld, ws.data_ptr(), nws,
+           _stream())
+    torch.cuda.synchronize()
+    for b, (dh, eh) in enumerate(cases):
+        T = np.diag(dh) + np.diag(eh, 1) + np.diag(eh, -1)
+        lam = scipy.linalg.eigvalsh_tridiagonal(dh, eh) if n > 1 else dh
+        sc = np.max(np.abs(T))
+        Wh, Q = W[b].cpu().numpy(), XT[b, :, :n].cpu().numpy().T
+        assert np.all(np.diff(Wh) >= 0), b
+        assert np.max(np.abs(Wh - lam)) <= 5e-14 * sc, b
+        assert np.max(np.abs(Q.T @ Q - np.eye(n))) <= 2e-14, b
+        assert np.max(np.abs(T @ Q - Q * Wh)) <= 2e-14 * sc, b
+        if ld > n:
+            assert torch.all(XT[b, :, n:] == 7.0)       # padding untouched
+
+
+@pytest.mark.parametrize("n,nmat", [(3, 1), (24, 2), (50, 3), (125, 2), (192, 2), (250, 2), (256, 1)])
+def test_eigh_dc_full(cuda_lib, n, nmat):
+    """gpcsd_eigh_dc (tridiagonalise -> divide and conquer -> back-transform) vs numpy.linalg.eigh on GP covariance factors."""
+    from gpcsd_b200 import _lib as L
+    rng = np.random.default_rng(n + nmat)
+    ld = _ld(n)
+    stack = torch.zeros((nmat, n, ld), dtype=F64, device="cuda")
+    Ms = []
+    for b in range(nmat):
+        t = np.arange(n) * (0.5 + b)
+        dd = t[:, None] - t[None, :]
+        if b == 0:
+            K = 0.5 * np.exp(-0.5 * dd ** 2 / 400.0) + 0.2 * np.exp(-np.abs(dd) / 5.0)
+        elif b == 1:
+            K = np.exp(-0.5 * dd ** 2 / 50.0) + 1e-8 * np.eye(n)
+        else:
+            K = rng.standard_normal((n, n))
+            K = K + K.T
+        Ms.append(K)
+        stack[b, :, :n] = torch.from_numpy(K).cuda()
+    keep = stack.clone()
+    QT = torch.zeros((nmat, n, ld), dtype=F64, device="cuda")
+    W = torch.zeros((nmat, n), dtype=F64, device="cuda")
+    nws = L.query("gpcsd_eigh_dc_ws_doubles", n, ld, nmat)
+    ws = torch.full((nws,), float("nan"), dtype=F64, device="cuda")      # the workspace may hold anything
+    L.call("gpcsd_eigh_dc", n, nmat, stack.data_ptr(), ld, QT.data_ptr(), ld, W.data_ptr(), ws.data_ptr(), nws, _stream())
+    torch.cuda.synchronize()
+    assert torch.equal(stack, keep)
+    for b in range(nmat):
+        lam = np.linalg.eigvalsh(Ms[b])
+        sc = np.max(np.abs(lam))
+        Wh, Q = W[b].cpu().numpy(), QT[b, :, :n].cpu().numpy().T
+        assert np.max(np.abs(Wh - lam)) <= 1e-13 * sc * max(1, n / 16)
+        assert np.max(np.abs(Q.T @ Q - np.eye(n))) <= 1e-12
+        assert np.max(np.abs(Ms[b] @ Q - Q * Wh)) <= 1e-13 * sc * n
