@@ -387,7 +387,7 @@ def run_gpu(args):
     args.serial = True
     timed_steps(2, 0, False)                                # warm the main thread's cuSOLVER handles
     for e in engines:
-        e.timers = {"gpcsd_project_quad": [], "gpcsd_wsyrk": [], "gpcsd_eigh": [], "gpcsd_dgemm": []}
+        e.timers = {"gpcsd_project_quad": [], "gpcsd_wsyrk": [], "gpcsd_eigh": [], "gpcsd_eigh_dc": [], "gpcsd_dgemm": []}
     ms_serial = timed_steps(K, W, False)
     clocks = sampler.stop() if rank == 0 else None
     kt = {}

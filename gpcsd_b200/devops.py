@@ -177,7 +177,8 @@ def kphig_2d(quad, x, z, R, eps, ell1, ell2):
 
 
 def eigh(K):
-    """Ascending eigenvalues and eigenvectors (columns) of a symmetric matrix via gpcsd_eigh."""
+    """Ascending eigenvalues and eigenvectors (columns) of a symmetric matrix: the in-house cluster solver
+    (gpcsd_eigh_dc) for orders 3..256, cuSOLVER syevd (gpcsd_eigh) otherwise."""
     _require_cuda()
     K = np.asarray(K, dtype=np.float64)
     n = K.shape[0]
@@ -185,6 +186,11 @@ def eigh(K):
     ld = Kd.shape[1]
     QT = torch.zeros((n, ld), dtype=F64, device="cuda")
     W = torch.zeros(n, dtype=F64, device="cuda")
+    if 3 <= n <= 256:
+        nws = L.query("gpcsd_eigh_dc_ws_doubles", n, ld, 1)
+        ws = torch.empty(nws, dtype=F64, device="cuda")
+        L.call("gpcsd_eigh_dc", n, 1, Kd.data_ptr(), ld, QT.data_ptr(), ld, W.data_ptr(), ws.data_ptr(), nws, _stream())
+        return W.cpu().numpy(), QT[:, :n].cpu().numpy().T.copy()
     nws = L.query("gpcsd_eigh_ws_doubles", n, ld)
     ws = torch.zeros(max(nws, 1), dtype=F64, device="cuda")
     info = torch.zeros(1, dtype=torch.int32, device="cuda")

@@ -101,7 +101,8 @@ class KronEngine:
         return torch.cuda.current_stream(self.device).cuda_stream
 
     # kernels of OURS launched per ABI call (cuSOLVER's own launches inside gpcsd_eigh are not counted)
-    _LAUNCHES = {"gpcsd_project_quad": 2, "gpcsd_wsyrk": 2, "gpcsd_eig_D": 2, "gpcsd_kt_grad": 2, "gpcsd_dot": 2}
+    _LAUNCHES = {"gpcsd_project_quad": 2, "gpcsd_wsyrk": 2, "gpcsd_eig_D": 2, "gpcsd_kt_grad": 2, "gpcsd_dot": 2,
+                 "gpcsd_eigh_dc": 3}
 
     def _call(self, name, *args):
         self.n_launches += self._LAUNCHES.get(name, 1)
@@ -308,7 +309,14 @@ class KronEngine:
                    self._p(Kt), self.ldt, self._stream())
         return Kt
 
+    DC_EIGH_MAX = 256           # order limit of the in-house cluster eigensolver (gpcsd_eigh_dc, csrc/gpcsd_eig.cu)
+
     def _eigh(self, K, n, ld, tag, QT=None, W=None):
+        """Eigen-factors of one symmetric matrix (eigenvectors as rows, eigenvalues ascending): the in-house cluster
+        solver up to order 256, cuSOLVER syevd above."""
+        if 3 <= n <= self.DC_EIGH_MAX:
+            QTs, Ws = self._eigh_dc(K, n, ld, 1, tag, QT=QT, W=W)
+            return QTs[0], Ws[0], self._zero_info()
         QT = self._buf("QT_" + tag, n, ld) if QT is None else QT
         W = self._buf("W_" + tag, n) if W is None else W
         nws = L.query("gpcsd_eigh_ws_doubles", n, ld)
@@ -318,24 +326,28 @@ class KronEngine:
                    self._stream())
         return QT, W, info
 
-    SMALL_EIGH_MAX = 128        # order limit of cuSOLVER's one-CTA-per-matrix batched path (measured, see csrc)
+    def _zero_info(self):
+        if getattr(self, "_info0", None) is None:
+            self._info0 = torch.zeros(1, dtype=torch.int32, device=self.device)
+        return self._info0
 
-    def _eigh_small_batched(self, stack, n, ld, batch, tag):
-        """Eigen-decompose `batch` stacked matrices [batch][n][ld] in place (eigenvectors as rows)."""
-        W = self._buf("Wb_" + tag, batch, n)
-        nbytes = L.query("gpcsd_eigh_batched_ws_bytes", n, ld, batch)
-        ws = self._buf("eigbws_" + tag, max((nbytes + 7) // 8, 1))
-        info = self._buf("infob_" + tag, batch, dtype=torch.int32)
-        self._call("gpcsd_eigh_batched", n, batch, self._p(stack), ld, self._p(W), self._p(ws), nbytes, info.data_ptr(),
-                   self._stream())
-        return W, info
+    def _eigh_dc(self, stack, n, ld, nmat, tag, QT=None, W=None):
+        """`nmat` stacked symmetric matrices [nmat][n][ld] -> (QT [nmat][n][ld] rows = eigenvectors, W [nmat][n] ascending)
+        in one launch sequence of the cluster solver (one 8-CTA cluster per matrix); the input is left untouched."""
+        QT = self._buf("QTdc_" + tag, nmat, n, ld) if QT is None else QT.view(nmat, n, ld)
+        W = self._buf("Wdc_" + tag, nmat, n) if W is None else W.view(nmat, n)
+        nws = L.query("gpcsd_eigh_dc_ws_doubles", n, ld, nmat)
+        ws = self._buf("eigdcws_" + tag, nws)
+        self._call("gpcsd_eigh_dc", n, nmat, self._p(stack), ld, self._p(QT), ld, self._p(W), self._p(ws), nws, self._stream())
+        return QT, W
 
     def _eigh_pair(self, S, A, m, ld, tag, side):
-        """Eigen-factors of two independent symmetric matrices of order m (leading dimension ld).  Order <= 128: one
-        batched call (S and A must then be the two slabs of one [2][m][ld] stack); larger: two syevd on two streams."""
-        if m <= self.SMALL_EIGH_MAX and A.data_ptr() == S.data_ptr() + 8 * m * ld:
-            Wb, info = self._eigh_small_batched(S, m, ld, 2, tag)
-            return S, Wb[0], A, Wb[1], [info]
+        """Eigen-factors of two independent symmetric matrices of order m (leading dimension ld).  Order <= 256: one
+        batched call of the cluster solver (S and A must then be the two slabs of one [2][m][ld] stack); larger: two
+        syevd on two streams."""
+        if 3 <= m <= self.DC_EIGH_MAX and A.data_ptr() == S.data_ptr() + 8 * m * ld:
+            QT, W = self._eigh_dc(S, m, ld, 2, tag)
+            return QT[0], W[0], QT[1], W[1], [self._zero_info()]
         main = torch.cuda.current_stream(self.device)
         ready = torch.cuda.Event()
         ready.record(main)
@@ -365,14 +377,8 @@ class KronEngine:
             self._call("gpcsd_pairsym_assemble", nx, ra.data_ptr(), rb.data_ptr(), self._p(UsT), ldm, self._p(Ws),
                        self._p(UaT), ldm, self._p(Wa), self._p(QT), ld, self._p(W), self._stream())
             return QT, W, infos
-        if not (32 < nx <= self.SMALL_EIGH_MAX):
-            QT, W, info = self._eigh(Ks, nx, ld, "s")
-            return QT, W, [info]
-        stack = self._buf("QT_s2", 2, nx, ld)
-        stack[0].copy_(Ks)
-        stack[1].copy_(Ks)
-        W, info = self._eigh_small_batched(stack, nx, ld, 2, "s")
-        return stack[0], W[0], [info]
+        QT, W, info = self._eigh(Ks, nx, ld, "s")
+        return QT, W, [info]
 
     def _side_streams(self):
         if self._sides is None:
@@ -381,25 +387,24 @@ class KronEngine:
 
     def _eigh_temporal(self, Kt):
         """Eigen-factors of Kt.  On a uniform time grid Kt is symmetric Toeplitz, hence centrosymmetric, and the
-        order-nt problem splits exactly into two independent problems of order ~nt/2 run on two streams
-        (cuSOLVER syevd costs ~1.2 ms + 8 us per column, so this is ~30 % faster at nt = 500); otherwise one
-        syevd.  The eigenvalues come back unsorted in the split case (nothing downstream needs an order)."""
+        order-nt problem splits exactly into two independent problems of order ~nt/2 (one batched call of the cluster
+        solver up to nt = 512, two concurrent syevd above); otherwise one solve of order nt.  The eigenvalues come back unsorted in the split case (nothing downstream needs an order)."""
         nt, ldt = self.nt, self.ldt
         if not (self.t_uniform and nt >= 32):
             QT, W, info = self._eigh(Kt, nt, ldt, "t")
             return QT, W, [info]
         m, ms = nt // 2, nt // 2 + (nt & 1)
         lds, lda = _even(ms), _even(m)
-        if nt % 2 == 0 and 2 <= m <= self.SMALL_EIGH_MAX:
-            # both halves have order m <= 128: one batched call, each problem inside a single CTA
+        if nt % 2 == 0 and 3 <= m <= self.DC_EIGH_MAX:
+            # both halves have order m <= 256: one batched call of the cluster solver (two clusters side by side)
             stack = self._buf("cs_stack", 2, m, lds)
             self._call("gpcsd_centro_split", nt, self._p(Kt), ldt, self._p(stack), lds, self._p(stack, m * lds), lds,
                        self._stream())
-            Wb, info = self._eigh_small_batched(stack, m, lds, 2, "t")
+            U, Wb = self._eigh_dc(stack, m, lds, 2, "t")
             QT, W = self._buf("QT_t", nt, ldt), self._buf("W_t", nt)
-            self._call("gpcsd_centro_assemble", nt, self._p(stack), lds, self._p(Wb), self._p(stack, m * lds), lds,
+            self._call("gpcsd_centro_assemble", nt, self._p(U), lds, self._p(Wb), self._p(U, m * lds), lds,
                        self._p(Wb, m), self._p(QT), ldt, self._p(W), self._stream())
-            return QT, W, [info]
+            return QT, W, [self._zero_info()]
         S, A = self._buf("cs_S", ms, lds), self._buf("cs_A", m, lda)
         self._call("gpcsd_centro_split", nt, self._p(Kt), ldt, self._p(S), lds, self._p(A), lda, self._stream())
         main = torch.cuda.current_stream(self.device)
