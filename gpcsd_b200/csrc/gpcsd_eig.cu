@@ -20,6 +20,7 @@
 //
 // All matrices row-major; eigenvectors are stored as ROWS (Q^T), the convention of gpcsd_eigh.
 #include <cooperative_groups.h>
+#include <stddef.h>
 
 #include "common.h"
 #include "dc_core.h"
@@ -29,147 +30,216 @@ namespace cg = cooperative_groups;
 
 namespace gpcsd {
 
-constexpr int TRD_CLUSTER = 8;        // CTAs per matrix
-constexpr int TRD_THREADS = 256;
-constexpr int TRD_MAXN = 256;
-constexpr int TRD_ROWS = TRD_MAXN / TRD_CLUSTER;   // local rows per CTA (row i lives in CTA i % 8, slot i / 8)
-constexpr int TRD_LD = TRD_MAXN + 2;               // smem row stride (even, +2 keeps rows 16-byte aligned and de-phased)
-
-struct TridiagSmem {
-  double A[TRD_ROWS][TRD_LD];   // local row slab (full rows, both triangles kept current)
-  double v[2][TRD_MAXN];        // reflector, double buffered by column parity (written by the owner into every CTA)
-  double p[2][TRD_MAXN];        // tau * A22 * v, all-gathered (every CTA writes its rows into every CTA)
-  double part[2][TRD_CLUSTER];  // partial p.v per CTA
-  double hdr[2][4];             // tau, beta broadcast by the owner
-  double red[TRD_THREADS / 32];
-};
-
-__device__ __forceinline__ double cta_sum(double x, double* red) {
-  x = warp_sum(x);
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  __syncthreads();
-  if (l == 0) red[w] = x;
-  __syncthreads();
-  double s = 0.0;
-#pragma unroll
-  for (int i = 0; i < TRD_THREADS / 32; ++i) s += red[i];
-  return s;
+// shared::cluster address of `ptr` (a shared-memory object of this CTA) in CTA `rank` of the cluster, and a remote store
+__device__ __forceinline__ uint32_t dsmem_addr(const void* ptr, int rank) {
+  uint32_t local = (uint32_t)__cvta_generic_to_shared(ptr), remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(remote) : "r"(local), "r"(rank));
+  return remote;
+}
+__device__ __forceinline__ void dsmem_store(uint32_t addr, double v) {
+  asm volatile("st.shared::cluster.f64 [%0], %1;\n" ::"r"(addr), "d"(v) : "memory");
+}
+// remote store that also signals 8 transaction bytes on an mbarrier of the SAME remote CTA: data and "it has arrived" travel
+// together, so the consumer needs neither a cluster barrier nor a fence
+__device__ __forceinline__ void dsmem_store_signal(uint32_t addr, double v, uint32_t mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];\n" ::"r"(addr), "d"(v), "r"(mbar)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra.uni WAIT_DONE;\n"
+      "bra.uni WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_addr(bar)),
+      "r"(parity)
+      : "memory");
 }
 
-// grid = 8 * nmat CTAs, cluster (8,1,1).  M: [nmat][n][ldm] symmetric.  Out: d[nmat][n], e[nmat][n] (e[k] = T[k+1][k]),
-// V[nmat][n][ldv] (row k holds reflector k: V[k][j] for j > k+1, implicit 1 at j = k+1), tau[nmat][n].
-__global__ void __cluster_dims__(TRD_CLUSTER, 1, 1) __launch_bounds__(TRD_THREADS, 1)
+constexpr int TRD_CLUSTER = 8;        // CTAs per matrix
+constexpr int TRD_MAXN = 256;
+constexpr int TRD_WARPS = 16;                      // warps per CTA
+constexpr int TRD_RPW = TRD_MAXN / (TRD_CLUSTER * TRD_WARPS);   // rows per warp (2): row i lives in CTA i % 8, slot i / 8
+constexpr int TRD_NR = TRD_MAXN / 32;              // row elements per lane
+
+struct TridiagSmem {
+  double v[2][TRD_MAXN];   // reflector, double buffered by column parity (written by the owner warp into every CTA)
+  double p[2][TRD_MAXN];   // tau * A22 * v, all-gathered (every row warp writes its entries into every CTA)
+  double hdr[2][2];        // tau broadcast by the owner
+  uint64_t bar_v, bar_p[2];   // transaction barriers: "reflector k has arrived", "all p_i of column k have arrived" (by parity)
+};
+
+// Register-resident Householder tridiagonalisation.  grid = 8 * nmat CTAs, cluster (8,1,1), up to 16 warps per CTA:
+// every matrix row lives in the REGISTERS of one warp (slot s = i / 8 belongs to warp s % 16; lane l holds columns l, l+32,
+// ...; both triangles are kept current), so the symv p = tau A v and the rank-2 update A -= v w^T + w v^T touch shared
+// memory only for the two exchanged vectors.  Per column: the warp that owns row k+1 builds the next reflector straight
+// from its registers right after updating them and stores it into every CTA of the cluster (distributed shared memory);
+// every row warp stores its p_i into every CTA.  Both exchanges are st.async stores that complete transaction bytes on an
+// mbarrier in the receiving CTA, so the per-column synchronisation is two mbarrier waits (~DSMEM latency) -- no cluster
+// barrier, no fence (a cluster barrier costs a MEMBAR.ALL.GPU that also waits for the reflector stores to global memory),
+// no CTA-wide barrier, no shared-memory reduction.  The exchanged vectors are double buffered by column parity; the data
+// dependencies of the algorithm (reflector k+1 needs every p of column k, p of column k+1 needs reflector k+1) guarantee
+// that no CTA can run more than one exchange ahead of the slowest one (the p barrier is doubled by column parity so that
+// a fast CTA's p of column k+1 can never be counted against a slow CTA's still-open column k).
+// M: [nmat][n][ldm] symmetric.  Out: d[nmat][n], e[nmat][n] (e[k] = T[k+1][k]), V[nmat][n][ldv] (row k holds reflector k:
+// V[k][j] for j > k+1, implicit 1 at j = k+1), tau[nmat][n].
+__global__ void __cluster_dims__(TRD_CLUSTER, 1, 1) __launch_bounds__(32 * TRD_WARPS, 1)
     tridiag_cluster_kernel(int n, const double* __restrict__ M, long ldm, double* __restrict__ d, double* __restrict__ e,
                            double* __restrict__ V, long ldv, double* __restrict__ tau) {
-  extern __shared__ __align__(16) unsigned char trd_raw[];
-  TridiagSmem& S = *reinterpret_cast<TridiagSmem*>(trd_raw);
+  __shared__ __align__(16) TridiagSmem S;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int mat = blockIdx.x / TRD_CLUSTER;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   M += (long)mat * n * ldm;
   d += (long)mat * n;
   e += (long)mat * n;
   tau += (long)mat * n;
   V += (long)mat * n * ldv;
 
-  // load the local rows
-  const int nloc = (n - rank + TRD_CLUSTER - 1) / TRD_CLUSTER;   // rows rank, rank+8, ...
-  for (int idx = tid; idx < nloc * n; idx += TRD_THREADS) {
-    const int s = idx / n, j = idx % n;
-    S.A[s][j] = M[(long)(rank + s * TRD_CLUSTER) * ldm + j];
+  int row[TRD_RPW];
+  double a[TRD_RPW][TRD_NR];
+#pragma unroll
+  for (int q = 0; q < TRD_RPW; ++q) {
+    row[q] = rank + (warp + q * TRD_WARPS) * TRD_CLUSTER;
+#pragma unroll
+    for (int m = 0; m < TRD_NR; ++m) {
+      const int j = lane + 32 * m;
+      a[q][m] = (row[q] < n && j < n) ? M[(long)row[q] * ldm + j] : 0.0;
+    }
   }
-  TridiagSmem* peers[TRD_CLUSTER];
-#pragma unroll
-  for (int r = 0; r < TRD_CLUSTER; ++r) peers[r] = cluster.map_shared_rank(&S, r);
-  cluster.sync();
-
-  for (int k = 0; k < n - 2; ++k) {
+  const int peer_rank = lane & (TRD_CLUSTER - 1);
+  if (threadIdx.x == 0) {
+    mbar_init(&S.bar_v, 1);
+    mbar_init(&S.bar_p[0], 1);
+    mbar_init(&S.bar_p[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  cluster.sync();                       // every CTA's shared memory and barriers are live before remote stores
+  for (int k = -1; k < n - 2; ++k) {    // k = -1: only builds reflector 0
     const int buf = k & 1;
-    const int len = n - k - 1;          // trailing order; reflector acts on indices k+1 .. n-1
-    // ---- (a) the owner of row k builds the reflector from its row (== column k by symmetry) and broadcasts it
-    if (rank == k % TRD_CLUSTER) {
-      const double* row = S.A[k / TRD_CLUSTER];
-      double ss = 0.0;
-      for (int j = k + 2 + tid; j < n; j += TRD_THREADS) ss += row[j] * row[j];
-      const double xnorm2 = cta_sum(ss, S.red);
-      const double alpha = row[k + 1];
-      double t = 0.0, beta = alpha, scal = 0.0;
-      if (xnorm2 > 0.0) {
-        beta = -copysign(sqrt(alpha * alpha + xnorm2), alpha);
-        t = (beta - alpha) / beta;
-        scal = 1.0 / (alpha - beta);
-      }
-      for (int j = k + 1 + tid; j < n; j += TRD_THREADS) {
-        const double vj = (j == k + 1) ? 1.0 : row[j] * scal;
-#pragma unroll
-        for (int r = 0; r < TRD_CLUSTER; ++r) peers[r]->v[buf][j] = vj;
-        if (j > k + 1) V[(long)k * ldv + j] = vj;
-      }
-      if (tid == 0) {
-#pragma unroll
-        for (int r = 0; r < TRD_CLUSTER; ++r) {
-          peers[r]->hdr[buf][0] = t;
-          peers[r]->hdr[buf][1] = beta;
-        }
-        d[k] = row[k];
-        e[k] = beta;
-        tau[k] = t;
-      }
+    const int kn = k + 1;
+    if (threadIdx.x == 0) {             // arm this column's transaction counts (early arrivals are fine)
+      if (k >= 0) mbar_expect_tx(&S.bar_p[buf], 8u * (uint32_t)(n - k - 1));
+      if (kn < n - 2) mbar_expect_tx(&S.bar_v, 8u * (uint32_t)(n - kn));
     }
-    cluster.sync();
-    const double t = S.hdr[buf][0];
-    // ---- (b) p_i = tau * sum_j A_ij v_j for the local rows i > k, all-gathered; partial p.v
-    double pv = 0.0;
-    for (int s = warp; s < nloc; s += TRD_THREADS / 32) {
-      const int i = rank + s * TRD_CLUSTER;
-      if (i <= k) continue;
-      double acc = 0.0;
-      for (int j = k + 1 + lane; j < n; j += 32) acc += S.A[s][j] * S.v[buf][j];
-      acc = warp_sum(acc) * t;
-      if (lane == 0) {
+    if (k >= 0) {
+      const double t = S.hdr[buf][0];
+      // ---- p_i = tau * sum_{j > k} A_ij v_j, all-gathered
+      double acc[TRD_RPW];
 #pragma unroll
-        for (int r = 0; r < TRD_CLUSTER; ++r) peers[r]->p[buf][i] = acc;
-        pv += acc * S.v[buf][i];
+      for (int q = 0; q < TRD_RPW; ++q) acc[q] = 0.0;
+#pragma unroll
+      for (int m = 0; m < TRD_NR; ++m) {
+        const int j = lane + 32 * m;
+        const double vj = (j > k && j < n) ? S.v[buf][j] : 0.0;
+#pragma unroll
+        for (int q = 0; q < TRD_RPW; ++q) acc[q] += a[q][m] * vj;
       }
-    }
-    const double pvsum = cta_sum(pv, S.red);
-    if (tid == 0) {
 #pragma unroll
-      for (int r = 0; r < TRD_CLUSTER; ++r) peers[r]->part[buf][rank] = pvsum;
-    }
-    cluster.sync();
-    // ---- (c) w = p - (tau/2)(p.v) v ;  A22 -= v w^T + w v^T on the local rows
-    double dot = 0.0;
+      for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-    for (int r = 0; r < TRD_CLUSTER; ++r) dot += S.part[buf][r];
-    const double c = 0.5 * t * dot;
-    if (t != 0.0) {
-      for (int s = warp; s < nloc; s += TRD_THREADS / 32) {
-        const int i = rank + s * TRD_CLUSTER;
-        if (i <= k) continue;
-        const double vi = S.v[buf][i], wi = S.p[buf][i] - c * vi;
-        for (int j = k + 1 + lane; j < n; j += 32) {
-          const double vj = S.v[buf][j], wj = S.p[buf][j] - c * vj;
-          S.A[s][j] -= vi * wj + wi * vj;
+        for (int q = 0; q < TRD_RPW; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+#pragma unroll
+      for (int q = 0; q < TRD_RPW; ++q)
+        if (row[q] > k && row[q] < n && lane < TRD_CLUSTER)
+          dsmem_store_signal(dsmem_addr(&S.p[buf][row[q]], peer_rank), acc[q] * t, dsmem_addr(&S.bar_p[buf], peer_rank));
+      mbar_wait_cluster(&S.bar_p[buf], (uint32_t)((k >> 1) & 1));
+      // ---- w = p - (tau/2)(p.v) v ;  A22 -= v w^T + w v^T on the own rows
+      double pv = 0.0;
+#pragma unroll
+      for (int m = 0; m < TRD_NR; ++m) {
+        const int j = lane + 32 * m;
+        if (j > k && j < n) pv += S.v[buf][j] * S.p[buf][j];
+      }
+      const double c = 0.5 * t * warp_sum(pv);
+#pragma unroll
+      for (int q = 0; q < TRD_RPW; ++q) {
+        if (row[q] > k && row[q] < n) {
+          const double vi = S.v[buf][row[q]], wi = S.p[buf][row[q]] - c * vi;
+#pragma unroll
+          for (int m = 0; m < TRD_NR; ++m) {
+            const int j = lane + 32 * m;
+            if (j > k && j < n) {
+              const double vj = S.v[buf][j];
+              a[q][m] -= vi * (S.p[buf][j] - c * vj) + wi * vj;
+            }
+          }
         }
       }
     }
-    __syncthreads();   // the next owner reads its own (just updated) row; v/p buffers alternate, so no cluster barrier here
-    (void)len;
+    // ---- the owner of row k+1 builds reflector k+1 (== column k+1 by symmetry) straight from the registers it has just
+    //      updated, and stores it into every CTA
+    if (kn < n - 2) {
+#pragma unroll
+      for (int q = 0; q < TRD_RPW; ++q) {
+        if (row[q] != kn) continue;                // warp-uniform
+        const int nb = kn & 1, j1 = kn + 1;
+        double sel = 0.0, dia = 0.0, ss = 0.0;
+#pragma unroll
+        for (int m = 0; m < TRD_NR; ++m) {
+          const int j = lane + 32 * m;
+          if (j == j1) sel = a[q][m];
+          if (j == kn) dia = a[q][m];
+          if (j > j1 && j < n) ss += a[q][m] * a[q][m];
+        }
+        const double alpha = __shfl_sync(0xffffffffu, sel, j1 & 31);
+        const double akk = __shfl_sync(0xffffffffu, dia, kn & 31);
+        const double xnorm2 = warp_sum(ss);
+        double t = 0.0, beta = alpha, scal = 0.0;
+        if (xnorm2 > 0.0) {
+          beta = -copysign(sqrt(alpha * alpha + xnorm2), alpha);
+          t = (beta - alpha) / beta;
+          scal = 1.0 / (alpha - beta);
+        }
+        if (lane < TRD_CLUSTER) dsmem_store_signal(dsmem_addr(&S.hdr[nb][0], peer_rank), t, dsmem_addr(&S.bar_v, peer_rank));
+#pragma unroll
+        for (int m = 0; m < TRD_NR; ++m) {
+          const int j = lane + 32 * m;
+          if (j >= j1 && j < n) {
+            const double vj = (j == j1) ? 1.0 : a[q][m] * scal;
+#pragma unroll
+            for (int r = 0; r < TRD_CLUSTER; ++r) dsmem_store_signal(dsmem_addr(&S.v[nb][j], r), vj, dsmem_addr(&S.bar_v, r));
+            if (j > j1) V[(long)kn * ldv + j] = vj;
+          }
+        }
+        if (lane == 0) {
+          d[kn] = akk;
+          e[kn] = beta;
+          tau[kn] = t;
+        }
+      }
+      mbar_wait_cluster(&S.bar_v, (uint32_t)(kn & 1));
+    }
   }
   // last 2x2 block
-  cluster.sync();
-  if (rank == (n - 2) % TRD_CLUSTER && tid == 0) {
-    const double* row = S.A[(n - 2) / TRD_CLUSTER];
-    d[n - 2] = row[n - 2];
-    e[n - 2] = row[n - 1];
-    tau[n - 2] = 0.0;
-  }
-  if (rank == (n - 1) % TRD_CLUSTER && tid == 0) {
-    d[n - 1] = S.A[(n - 1) / TRD_CLUSTER][n - 1];
-    e[n - 1] = 0.0;
-    tau[n - 1] = 0.0;
+#pragma unroll
+  for (int q = 0; q < TRD_RPW; ++q) {
+    if (row[q] == n - 2 || row[q] == n - 1) {
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int m = 0; m < TRD_NR; ++m) {
+        const int j = lane + 32 * m;
+        if (j == row[q]) s0 = a[q][m];
+        if (j == n - 1) s1 = a[q][m];
+      }
+      const double dd = __shfl_sync(0xffffffffu, s0, row[q] & 31), ee = __shfl_sync(0xffffffffu, s1, (n - 1) & 31);
+      if (lane == 0) {
+        d[row[q]] = dd;
+        e[row[q]] = (row[q] == n - 2) ? ee : 0.0;
+        tau[row[q]] = 0.0;
+      }
+    }
   }
   cluster.sync();   // keep every CTA's shared memory alive until all remote accesses are done
 }
@@ -533,12 +603,9 @@ extern "C" {
 int gpcsd_tridiag(int n, int nmat, const double* M, long ldm, double* d, double* e, double* V, long ldv, double* tau,
                   void* stream) {
   if (n < 3 || n > TRD_MAXN) return gp_fail("gpcsd_tridiag: order must be in 3..256");
-  static bool attr = false;
-  if (!attr) {
-    GP_CUDA(cudaFuncSetAttribute(tridiag_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TridiagSmem)));
-    attr = true;
-  }
-  tridiag_cluster_kernel<<<TRD_CLUSTER * nmat, TRD_THREADS, sizeof(TridiagSmem), (cudaStream_t)stream>>>(n, M, ldm, d, e, V, ldv, tau);
+  const int slots = (n + TRD_CLUSTER - 1) / TRD_CLUSTER;               // rows per CTA
+  const int threads = 32 * (slots < TRD_WARPS ? slots : TRD_WARPS);
+  tridiag_cluster_kernel<<<TRD_CLUSTER * nmat, threads, 0, (cudaStream_t)stream>>>(n, M, ldm, d, e, V, ldv, tau);
   GP_CUDA(cudaGetLastError());
   return 0;
 }
