@@ -24,7 +24,7 @@ def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES + \
+    cmd = [nvcc] + NVCC_FLAGS + os.environ.get("GPCSD_NVCC_FLAGS", "").split() + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES + \
           ["-lcusolver", "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
     res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if res.returncode != 0:

@@ -45,6 +45,14 @@ __device__ __forceinline__ void dsmem_store_signal(uint32_t addr, double v, uint
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];\n" ::"r"(addr), "d"(v), "r"(mbar)
                : "memory");
 }
+// one bulk copy (the TMA engine; size a multiple of 16 B) from this CTA's shared memory into a peer's, completing `bytes`
+// on an mbarrier of the peer -- a single instruction instead of bytes/8 st.async requests (measured: ~17 cycles of issue per
+// 8-byte st.async request, 2200 cycles for a 16-entry row to 8 peers)
+__device__ __forceinline__ void dsmem_bulk_copy(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t mbar_cluster) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst_cluster),
+               "r"(src_cta), "r"(bytes), "r"(mbar_cluster)
+               : "memory");
+}
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_addr(bar)), "r"(count) : "memory");
@@ -72,25 +80,58 @@ constexpr int TRD_WARPS = 16;                      // warps per CTA
 constexpr int TRD_RPW = TRD_MAXN / (TRD_CLUSTER * TRD_WARPS);   // rows per warp (2): row i lives in CTA i % 8, slot i / 8
 constexpr int TRD_NR = TRD_MAXN / 32;              // row elements per lane
 
+// -DGPCSD_EIG_PROF: clock64 phase timers of the cluster kernels (developer builds only; scratch/ubench/trd_prof.py)
+#ifdef GPCSD_EIG_PROF
+__device__ long long g_eig_prof[64];
+#define EIG_PROF_DECL long long prof_t[16] = {0}; long long prof_last = clock64();
+__device__ long long g_eig_trace[8 * 16 * 12];
+#define EIG_PROF(i) { const long long t_ = clock64(); prof_t[i] += t_ - prof_last; prof_last = t_; \
+    if (rank == 0 && k >= 4 && k < 12 && lane == 0) g_eig_trace[((k - 4) * 16 + warp) * 12 + i] = t_; }
+#define EIG_PROF_DUMP(cond, cnt) if ((cond) && (threadIdx.x & 31) == 0) { for (int i_ = 0; i_ < (cnt); ++i_) g_eig_prof[i_] = prof_t[i_]; }
+#else
+#define EIG_PROF_DECL
+#define EIG_PROF(i)
+#define EIG_PROF_DUMP(cond, cnt)
+#endif
+
 struct TridiagSmem {
-  double v[2][TRD_MAXN];   // reflector, double buffered by column parity (written by the owner warp into every CTA)
-  double p[2][TRD_MAXN];   // tau * A22 * v, all-gathered (every row warp writes its entries into every CTA)
-  double hdr[2][2];        // tau broadcast by the owner
-  uint64_t bar_v, bar_p[2];   // transaction barriers: "reflector k has arrived", "all p_i of column k have arrived" (by parity)
+  double p[2][TRD_MAXN];          // tau * A22 * v of one column, all-gathered (every row warp stores its entries into every CTA)
+  double rowb[2][TRD_MAXN];       // row k+1 of the matrix as it stands BEFORE reflector k is applied (stored by its owner)
+  double vs[TRD_WARPS][TRD_MAXN]; // per-warp private copy of the current reflector (single-element reads without shuffles)
+  double stage[2][TRD_MAXN];      // source of the owner's bulk row copies (by slot parity)
+  uint64_t bar[2];                // transaction barriers of the per-column exchange, by exchange parity
 };
 
-// Register-resident Householder tridiagonalisation.  grid = 8 * nmat CTAs, cluster (8,1,1), up to 16 warps per CTA:
-// every matrix row lives in the REGISTERS of one warp (slot s = i / 8 belongs to warp s % 16; lane l holds columns l, l+32,
-// ...; both triangles are kept current), so the symv p = tau A v and the rank-2 update A -= v w^T + w v^T touch shared
-// memory only for the two exchanged vectors.  Per column: the warp that owns row k+1 builds the next reflector straight
-// from its registers right after updating them and stores it into every CTA of the cluster (distributed shared memory);
-// every row warp stores its p_i into every CTA.  Both exchanges are st.async stores that complete transaction bytes on an
-// mbarrier in the receiving CTA, so the per-column synchronisation is two mbarrier waits (~DSMEM latency) -- no cluster
-// barrier, no fence (a cluster barrier costs a MEMBAR.ALL.GPU that also waits for the reflector stores to global memory),
-// no CTA-wide barrier, no shared-memory reduction.  The exchanged vectors are double buffered by column parity; the data
-// dependencies of the algorithm (reflector k+1 needs every p of column k, p of column k+1 needs reflector k+1) guarantee
-// that no CTA can run more than one exchange ahead of the slowest one (the p barrier is doubled by column parity so that
-// a fast CTA's p of column k+1 can never be counted against a slow CTA's still-open column k).
+// 1/sqrt(s) and 1/x to full double precision from the single-precision hardware approximations plus two Newton steps: the
+// library sqrt and division are ~30 dependent FP64 instructions each (~1000 cycles for sqrt + div on this part, measured
+// with clock64 inside the kernel) and they sit on the per-column critical path.  Arguments outside the float range take
+// the library path.
+__device__ __forceinline__ double fast_rsqrt(double s) {
+  if (!(s > 1e-30 && s < 1e30)) return 1.0 / sqrt(s);
+  const double y = (double)rsqrtf((float)s);          // ~2^-22
+  const double r = fma(-s * y, y, 1.0);               // 1 - s y^2
+  return fma(y * r, fma(r, 0.375, 0.5), y);           // y (1 + r/2 + 3 r^2/8): third order -> ~2^-62 (+ rounding)
+}
+// one third-order step from a single-precision seed y0 ~ 1/x
+__device__ __forceinline__ double refine_recip(double x, double y0) {
+  const double r = fma(-x, y0, 1.0);
+  return fma(y0 * r, 1.0 + r, y0);                    // y (1 + r + r^2)
+}
+
+// Register-resident, single-exchange Householder tridiagonalisation.  grid = 8 * nmat CTAs, cluster (8,1,1), up to 16 warps
+// per CTA.  Every matrix row lives in the REGISTERS of one warp (slot s = i / 8 belongs to warp s % 16 of CTA i % 8; lane l
+// holds columns l, l+32, ...; both triangles are kept current), so the symv p = tau A v and the rank-2 update
+// A -= v w^T + w v^T never touch shared memory for the matrix.
+//
+// The classical algorithm needs two cluster-wide exchanges per column (broadcast the reflector, all-gather p).  Here there
+// is ONE: exchange k+1 carries every p_i of column k AND the not-yet-updated row k+1 of its owner.  After receiving it every
+// warp redundantly (and bit-identically) finishes column k (w = p - tau/2 (p.v) v), applies that rank-2 update to the
+// received row to obtain column k+1 of the current matrix, builds reflector k+1 from it, updates its own rows and computes
+// its p_i for column k+1.  Exchanges are st.async stores that complete transaction bytes on an mbarrier of the receiving
+// CTA (double buffered by parity): no cluster barrier (it costs a MEMBAR.ALL.GPU that also waits for the reflector stores
+// to global memory), no fence, no CTA-wide barrier, no shared-memory reduction -- the per-column critical path is three
+// warp reductions, one rsqrt, one reciprocal and one distributed-shared-memory latency.  A CTA cannot run more than one
+// exchange ahead of the slowest one because every p_i of exchange k+1 needs all of exchange k.
 // M: [nmat][n][ldm] symmetric.  Out: d[nmat][n], e[nmat][n] (e[k] = T[k+1][k]), V[nmat][n][ldv] (row k holds reflector k:
 // V[k][j] for j > k+1, implicit 1 at j = k+1), tau[nmat][n].
 __global__ void __cluster_dims__(TRD_CLUSTER, 1, 1) __launch_bounds__(32 * TRD_WARPS, 1)
@@ -118,120 +159,196 @@ __global__ void __cluster_dims__(TRD_CLUSTER, 1, 1) __launch_bounds__(32 * TRD_W
       a[q][m] = (row[q] < n && j < n) ? M[(long)row[q] * ldm + j] : 0.0;
     }
   }
+  double* vs = S.vs[warp];
+#pragma unroll
+  for (int m = 0; m < TRD_NR; ++m) vs[lane + 32 * m] = 0.0;
   const int peer_rank = lane & (TRD_CLUSTER - 1);
   if (threadIdx.x == 0) {
-    mbar_init(&S.bar_v, 1);
-    mbar_init(&S.bar_p[0], 1);
-    mbar_init(&S.bar_p[1], 1);
+    mbar_init(&S.bar[0], 1);
+    mbar_init(&S.bar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   cluster.sync();                       // every CTA's shared memory and barriers are live before remote stores
-  for (int k = -1; k < n - 2; ++k) {    // k = -1: only builds reflector 0
-    const int buf = k & 1;
-    const int kn = k + 1;
-    if (threadIdx.x == 0) {             // arm this column's transaction counts (early arrivals are fine)
-      if (k >= 0) mbar_expect_tx(&S.bar_p[buf], 8u * (uint32_t)(n - k - 1));
-      if (kn < n - 2) mbar_expect_tx(&S.bar_v, 8u * (uint32_t)(n - kn));
+
+  // the owner of row r ships entries j >= (r & ~1) of that row into rowb[pb] of every CTA (signalling bar[pb]): registers ->
+  // own shared memory -> one bulk copy per peer
+  auto send_row = [&](const double (&x)[TRD_NR], int r, int pb) {
+    double* stg = S.stage[(r >> 3) & 1];
+#pragma unroll
+    for (int m = 0; m < TRD_NR; ++m) stg[lane + 32 * m] = x[m];
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    __syncwarp();
+    const int j0 = r & ~1;
+    const uint32_t bytes = 8u * (uint32_t)(((n + 1) & ~1) - j0);
+    if (lane < TRD_CLUSTER)
+      dsmem_bulk_copy(dsmem_addr(&S.rowb[pb][j0], lane), smem_addr(stg + j0), bytes, dsmem_addr(&S.bar[pb], lane));
+  };
+
+  // A warp takes part in column k while it owns a row >= k; afterwards it leaves the loop (it would neither send nor be
+  // waited for).  The warp that owns the CTA's LAST row stays longest and arms the CTA's barriers.
+  int last_row = -1;
+#pragma unroll
+  for (int q = 0; q < TRD_RPW; ++q)
+    if (row[q] < n) last_row = row[q];
+  const bool armer = lane == 0 && last_row >= 0 && last_row + TRD_CLUSTER >= n;
+
+  // exchange 0: row 0 only
+  if (armer) mbar_expect_tx(&S.bar[0], 8u * (uint32_t)((n + 1) & ~1));
+#pragma unroll
+  for (int q = 0; q < TRD_RPW; ++q)
+    if (row[q] == 0) send_row(a[q], 0, 0);
+
+  double vprev[TRD_NR];                 // reflector k-1 (zero before the first column)
+#pragma unroll
+  for (int m = 0; m < TRD_NR; ++m) vprev[m] = 0.0;
+  double tprev = 0.0;
+
+  EIG_PROF_DECL
+  for (int k = 0; k <= n - 2; ++k) {    // k = n-2: only finishes column n-3
+    EIG_PROF(0)
+    const int pb = k & 1;               // exchange k: p of column k-1 and row k
+    const bool build = k < n - 2;
+    if (last_row < k) break;
+    if (armer && build)                 // arm exchange k+1: p of column k (rows i > k) and row k+1 (entries j >= k+1)
+      mbar_expect_tx(&S.bar[pb ^ 1], 8u * (uint32_t)(n - k - 1) +
+                                         ((k + 1 < n - 2) ? 8u * (uint32_t)(((n + 1) & ~1) - ((k + 1) & ~1)) : 0u));
+    const int m0 = k >> 5;              // lane blocks below m0 only hold columns < k: nothing to do there
+    mbar_wait_cluster(&S.bar[pb], (uint32_t)((k >> 1) & 1));
+    EIG_PROF(1)
+    // ---- finish column k-1: w = p - (tau/2)(p.v) v
+    double w[TRD_NR];
+    double pv0 = 0.0, pv1 = 0.0;
+#pragma unroll
+    for (int m = 0; m < TRD_NR; ++m) {
+      const int j = lane + 32 * m;
+      w[m] = (m >= m0 && k > 0 && j >= k && j < n) ? S.p[pb][j] : 0.0;
+      if (m & 1) pv1 += w[m] * vprev[m]; else pv0 += w[m] * vprev[m];
     }
-    if (k >= 0) {
-      const double t = S.hdr[buf][0];
-      // ---- p_i = tau * sum_{j > k} A_ij v_j, all-gathered
-      double acc[TRD_RPW];
+    const double pv = pv0 + pv1;
+    const double pk = (k > 0) ? S.p[pb][k] : 0.0;            // p_k, r_k, r_{k+1}: uniform loads
+    const double rk = S.rowb[pb][k], rk1 = S.rowb[pb][k + 1];
+    const double vk1 = vs[k + 1];                            // v^{k-1}_{k+1}
+    double vi[TRD_RPW], pi[TRD_RPW];
 #pragma unroll
-      for (int q = 0; q < TRD_RPW; ++q) acc[q] = 0.0;
+    for (int q = 0; q < TRD_RPW; ++q) {
+      const int r = (row[q] < n) ? row[q] : 0;
+      vi[q] = vs[r];
+      pi[q] = (k > 0) ? S.p[pb][r] : 0.0;
+    }
+    const double c = 0.5 * tprev * warp_sum(pv);
+    EIG_PROF(2)
 #pragma unroll
-      for (int m = 0; m < TRD_NR; ++m) {
-        const int j = lane + 32 * m;
-        const double vj = (j > k && j < n) ? S.v[buf][j] : 0.0;
+    for (int m = 0; m < TRD_NR; ++m)
+      if (m >= m0) w[m] -= c * vprev[m];
+    // ---- apply it to the own rows (rows i >= k; rows below are final)
 #pragma unroll
-        for (int q = 0; q < TRD_RPW; ++q) acc[q] += a[q][m] * vj;
+    for (int q = 0; q < TRD_RPW; ++q) {
+      if (k > 0 && row[q] >= k && row[q] < n) {
+        const double wi = pi[q] - c * vi[q];
+#pragma unroll
+        for (int m = 0; m < TRD_NR; ++m)
+          if (m >= m0) a[q][m] -= vi[q] * w[m] + wi * vprev[m];
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-        for (int q = 0; q < TRD_RPW; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+    }
+    if (!build) break;
+    EIG_PROF(3)
+    // ---- the owner of row k+1 ships it (as it stands now, before reflector k) with the next exchange
+    if (k + 1 < n - 2) {
 #pragma unroll
       for (int q = 0; q < TRD_RPW; ++q)
-        if (row[q] > k && row[q] < n && lane < TRD_CLUSTER)
-          dsmem_store_signal(dsmem_addr(&S.p[buf][row[q]], peer_rank), acc[q] * t, dsmem_addr(&S.bar_p[buf], peer_rank));
-      mbar_wait_cluster(&S.bar_p[buf], (uint32_t)((k >> 1) & 1));
-      // ---- w = p - (tau/2)(p.v) v ;  A22 -= v w^T + w v^T on the own rows
-      double pv = 0.0;
+        if (row[q] == k + 1) send_row(a[q], k + 1, pb ^ 1);
+    }
+    EIG_PROF(4)
+    // ---- row k of the current matrix (== column k), rebuilt from the received pre-update row; reflector k.
+    //      v^{k-1}_k = 1 (0 before the first column), so x_j = r_j - vk w_j - wk v_j with wk = p_k - c vk.
+    {
+      const double vk = (k > 0) ? 1.0 : 0.0, wk = pk - c * vk;
+      const double akk = rk - 2.0 * vk * wk;
+      const double alpha = rk1 - vk * ((k > 0 ? S.p[pb][k + 1] : 0.0) - c * vk1) - wk * vk1;
+      double x[TRD_NR];
+      double ss0 = 0.0, ss1 = 0.0;
 #pragma unroll
       for (int m = 0; m < TRD_NR; ++m) {
         const int j = lane + 32 * m;
-        if (j > k && j < n) pv += S.v[buf][j] * S.p[buf][j];
+        x[m] = (m >= m0 && j > k + 1 && j < n) ? S.rowb[pb][j] - vk * w[m] - wk * vprev[m] : 0.0;
+        if (m & 1) ss1 += x[m] * x[m]; else ss0 += x[m] * x[m];
       }
-      const double c = 0.5 * t * warp_sum(pv);
-#pragma unroll
-      for (int q = 0; q < TRD_RPW; ++q) {
-        if (row[q] > k && row[q] < n) {
-          const double vi = S.v[buf][row[q]], wi = S.p[buf][row[q]] - c * vi;
-#pragma unroll
-          for (int m = 0; m < TRD_NR; ++m) {
-            const int j = lane + 32 * m;
-            if (j > k && j < n) {
-              const double vj = S.v[buf][j];
-              a[q][m] -= vi * (S.p[buf][j] - c * vj) + wi * vj;
-            }
-          }
+      const double xnorm2 = warp_sum(ss0 + ss1);
+      EIG_PROF(5)
+      double t = 0.0, beta = alpha, scal = 0.0;
+      if (xnorm2 > 0.0) {
+        const double s2 = alpha * alpha + xnorm2, aa = fabs(alpha);
+        const double rn = fast_rsqrt(s2);                    // 1 / |beta|
+        const double ab = s2 * rn;                           // |beta|
+        beta = -copysign(ab, alpha);
+        t = 1.0 + aa * rn;                                   // (beta - alpha) / beta
+        const double den = aa + ab;                          // |alpha - beta|
+        double rden;
+        if (s2 > 1e-30 && s2 < 1e30) {                       // single-precision seed computed off the critical path
+          const float sf = (float)s2;
+          rden = refine_recip(den, (double)__frcp_rn((float)aa + sqrtf(sf)));
+        } else {
+          rden = 1.0 / den;
         }
+        scal = copysign(rden, alpha);                        // 1 / (alpha - beta)
       }
-    }
-    // ---- the owner of row k+1 builds reflector k+1 (== column k+1 by symmetry) straight from the registers it has just
-    //      updated, and stores it into every CTA
-    if (kn < n - 2) {
 #pragma unroll
-      for (int q = 0; q < TRD_RPW; ++q) {
-        if (row[q] != kn) continue;                // warp-uniform
-        const int nb = kn & 1, j1 = kn + 1;
-        double sel = 0.0, dia = 0.0, ss = 0.0;
+      for (int m = 0; m < TRD_NR; ++m) {
+        const int j = lane + 32 * m;
+        vprev[m] = (j == k + 1) ? 1.0 : x[m] * scal;
+        vs[j] = vprev[m];
+      }
+      tprev = t;
+      EIG_PROF(6)
+      if (row[0] == k + 1 || row[TRD_RPW - 1] == k + 1) {     // one warp of the cluster (an active one) records the column
 #pragma unroll
         for (int m = 0; m < TRD_NR; ++m) {
           const int j = lane + 32 * m;
-          if (j == j1) sel = a[q][m];
-          if (j == kn) dia = a[q][m];
-          if (j > j1 && j < n) ss += a[q][m] * a[q][m];
-        }
-        const double alpha = __shfl_sync(0xffffffffu, sel, j1 & 31);
-        const double akk = __shfl_sync(0xffffffffu, dia, kn & 31);
-        const double xnorm2 = warp_sum(ss);
-        double t = 0.0, beta = alpha, scal = 0.0;
-        if (xnorm2 > 0.0) {
-          beta = -copysign(sqrt(alpha * alpha + xnorm2), alpha);
-          t = (beta - alpha) / beta;
-          scal = 1.0 / (alpha - beta);
-        }
-        if (lane < TRD_CLUSTER) dsmem_store_signal(dsmem_addr(&S.hdr[nb][0], peer_rank), t, dsmem_addr(&S.bar_v, peer_rank));
-#pragma unroll
-        for (int m = 0; m < TRD_NR; ++m) {
-          const int j = lane + 32 * m;
-          if (j >= j1 && j < n) {
-            const double vj = (j == j1) ? 1.0 : a[q][m] * scal;
-#pragma unroll
-            for (int r = 0; r < TRD_CLUSTER; ++r) dsmem_store_signal(dsmem_addr(&S.v[nb][j], r), vj, dsmem_addr(&S.bar_v, r));
-            if (j > j1) V[(long)kn * ldv + j] = vj;
-          }
+          if (j > k + 1 && j < n) V[(long)k * ldv + j] = vprev[m];
         }
         if (lane == 0) {
-          d[kn] = akk;
-          e[kn] = beta;
-          tau[kn] = t;
+          d[k] = akk;
+          e[k] = beta;
+          tau[k] = t;
         }
       }
-      mbar_wait_cluster(&S.bar_v, (uint32_t)(kn & 1));
     }
+    EIG_PROF(7)
+    // ---- p_i = tau * sum_j A_ij v_j for the own rows i > k, stored into every CTA
+    double acc[TRD_RPW], acc1[TRD_RPW];
+#pragma unroll
+    for (int q = 0; q < TRD_RPW; ++q) acc[q] = acc1[q] = 0.0;
+#pragma unroll
+    for (int m = 0; m < TRD_NR; ++m)
+      if (m >= m0) {
+#pragma unroll
+        for (int q = 0; q < TRD_RPW; ++q) {
+          if (m & 1) acc1[q] += a[q][m] * vprev[m]; else acc[q] += a[q][m] * vprev[m];
+        }
+      }
+#pragma unroll
+    for (int q = 0; q < TRD_RPW; ++q) acc[q] += acc1[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int q = 0; q < TRD_RPW; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+#pragma unroll
+    for (int q = 0; q < TRD_RPW; ++q)
+      if (row[q] > k && row[q] < n && lane < TRD_CLUSTER)
+        dsmem_store_signal(dsmem_addr(&S.p[pb ^ 1][row[q]], peer_rank), acc[q] * tprev, dsmem_addr(&S.bar[pb ^ 1], peer_rank));
+    EIG_PROF(8)
+    __syncwarp();     // vs[] written above is read (by other lanes of this warp) in the next column
   }
-  // last 2x2 block
+  EIG_PROF_DUMP(last_row == n - 1, 9)
+  // last 2x2 block (rows n-2 and n-1 are final now)
 #pragma unroll
   for (int q = 0; q < TRD_RPW; ++q) {
     if (row[q] == n - 2 || row[q] == n - 1) {
       double s0 = 0.0, s1 = 0.0;
 #pragma unroll
       for (int m = 0; m < TRD_NR; ++m) {
-        const int j = lane + 32 * m;
-        if (j == row[q]) s0 = a[q][m];
-        if (j == n - 1) s1 = a[q][m];
+        if (lane + 32 * m == row[q]) s0 = a[q][m];
+        if (lane + 32 * m == n - 1) s1 = a[q][m];
       }
       const double dd = __shfl_sync(0xffffffffu, s0, row[q] & 31), ee = __shfl_sync(0xffffffffu, s1, (n - 1) & 31);
       if (lane == 0) {
@@ -598,6 +715,17 @@ __global__ void __launch_bounds__(32 * BT_WARPS) backtransform_kernel(int n, con
 using namespace gpcsd;
 
 extern "C" {
+#ifdef GPCSD_EIG_PROF
+int gpcsd_dbg_prof(long long* out) {
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(out, g_eig_prof, sizeof(long long) * 64);
+}
+int gpcsd_dbg_trace(long long* out) {
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(out, g_eig_trace, sizeof(long long) * 8 * 16 * 12);
+}
+#endif
+
 
 // Householder tridiagonalisation of `nmat` symmetric matrices of order n (3 <= n <= 256) on 8-CTA clusters.
 int gpcsd_tridiag(int n, int nmat, const double* M, long ldm, double* d, double* e, double* V, long ldv, double* tau,
