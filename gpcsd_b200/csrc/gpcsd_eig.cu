@@ -83,14 +83,16 @@ constexpr int TRD_NR = TRD_MAXN / 32;              // row elements per lane
 // -DGPCSD_EIG_PROF: clock64 phase timers of the cluster kernels (developer builds only; scratch/ubench/trd_prof.py)
 #ifdef GPCSD_EIG_PROF
 __device__ long long g_eig_prof[64];
-#define EIG_PROF_DECL long long prof_t[16] = {0}; long long prof_last = clock64();
+#define EIG_PROF_DECL long long prof_t[32] = {0}; long long prof_last = clock64();
 __device__ long long g_eig_trace[8 * 16 * 12];
 #define EIG_PROF(i) { const long long t_ = clock64(); prof_t[i] += t_ - prof_last; prof_last = t_; \
     if (rank == 0 && k >= 4 && k < 12 && lane == 0) g_eig_trace[((k - 4) * 16 + warp) * 12 + i] = t_; }
+#define EIG_PROF2(i) { const long long t_ = clock64(); prof_t[i] += t_ - prof_last; prof_last = t_; }
 #define EIG_PROF_DUMP(cond, cnt) if ((cond) && (threadIdx.x & 31) == 0) { for (int i_ = 0; i_ < (cnt); ++i_) g_eig_prof[i_] = prof_t[i_]; }
 #else
 #define EIG_PROF_DECL
 #define EIG_PROF(i)
+#define EIG_PROF2(i)
 #define EIG_PROF_DUMP(cond, cnt)
 #endif
 
@@ -391,9 +393,12 @@ struct DcSmem {
 
 // grid = 8 * nmat CTAs, cluster (8,1,1).  d_in[nmat][n], e_in[nmat][n] with e_in[k] = T[k+1][k].  Qa, Qb: [nmat][n][ldq]
 // workspaces.  Out: W[nmat][n] ascending, XT[nmat][n][ldx] rows = eigenvectors of T in the order of W.
+// With Cmat != nullptr the LAST merge is left to the caller as a full-GPU GEMM: the kernel stops after the secular solve of
+// the top level and writes its coefficient matrix Cmat[nmat][n][ldc] (rows already in ascending eigenvalue order, deflated
+// rows = unit vectors) so that XT = Cmat * Q, Q = the level below (in Qa if ceil(log2 n) is odd, else Qb).
 __global__ void __cluster_dims__(DC_CLUSTER, 1, 1) __launch_bounds__(DC_THREADS, 1)
     dc_cluster_kernel(int n, const double* __restrict__ d_in, const double* __restrict__ e_in, double* Qa, double* Qb, long ldq,
-                      double* __restrict__ W, double* XT, long ldx) {
+                      double* __restrict__ W, double* XT, long ldx, double* __restrict__ Cmat, long ldc) {
   extern __shared__ __align__(16) unsigned char dc_raw[];
   DcSmem& S = *reinterpret_cast<DcSmem*>(dc_raw);
   cg::cluster_group cluster = cg::this_cluster();
@@ -408,6 +413,7 @@ __global__ void __cluster_dims__(DC_CLUSTER, 1, 1) __launch_bounds__(DC_THREADS,
   Qb += (long)mat * n * ldq;
   W += (long)mat * n;
   XT += (long)mat * n * ldx;
+  if (Cmat) Cmat += (long)mat * n * ldc;
   DcSmem* peer = cluster.map_shared_rank(&S, lane & (DC_CLUSTER - 1));
 
   // ---- scale to unit max-norm, tear every off-diagonal (leaves of size 1), Q = I
@@ -432,10 +438,15 @@ __global__ void __cluster_dims__(DC_CLUSTER, 1, 1) __launch_bounds__(DC_THREADS,
   }
   double* Qold = Qa;
   double* Qnew = Qb;
+  EIG_PROF_DECL
   cluster.sync();
+  EIG_PROF2(0)
 
   const int levels = dc::num_levels(n);
   for (int L = 1; L <= levels; ++L) {
+#ifdef GPCSD_EIG_PROF
+    const long long lvl_t0 = clock64();
+#endif
     const int nodes = 1 << (levels - L);
     const int mmax = (n + nodes - 1) / nodes;
     // ---- node table
@@ -464,6 +475,7 @@ __global__ void __cluster_dims__(DC_CLUSTER, 1, 1) __launch_bounds__(DC_THREADS,
       atomicMax(&S.nzmax[p], (unsigned long long)__double_as_longlong(fabs(zz)));
     }
     __syncthreads();
+    EIG_PROF2(1)
     // ---- counting sort of the node's eigenvalues
     if (tid < n) {
       const int p = S.pid[tid], a = S.na[p], b = S.nb[p];
@@ -476,6 +488,7 @@ __global__ void __cluster_dims__(DC_CLUSTER, 1, 1) __launch_bounds__(DC_THREADS,
       S.srt[a + r] = tid;
     }
     __syncthreads();
+    EIG_PROF2(2)
     // ---- deflation, one thread per node
     if (tid < nodes) {
       const int a = S.na[tid], m = S.nb[tid] - a;
@@ -488,6 +501,7 @@ __global__ void __cluster_dims__(DC_CLUSTER, 1, 1) __launch_bounds__(DC_THREADS,
       S.nrot[tid] = nrot;
     }
     __syncthreads();
+    EIG_PROF2(3)
     // ---- deflating Givens rotations on the rows of Qold: one thread per column, the running row stays in a register
     if (warp == 0) {
       const int col = rank * 32 + lane;
@@ -519,6 +533,7 @@ __global__ void __cluster_dims__(DC_CLUSTER, 1, 1) __launch_bounds__(DC_THREADS,
       }
     }
     cluster.sync();
+    EIG_PROF2(4)
     // ---- secular roots: one warp per root, broadcast (mu, org) to every CTA
     for (int g = gw; g < n; g += GW) {
       const int p = S.pid[g], a = S.na[p], r = g - a, k = S.nk[p];
@@ -533,6 +548,7 @@ __global__ void __cluster_dims__(DC_CLUSTER, 1, 1) __launch_bounds__(DC_THREADS,
       }
     }
     cluster.sync();
+    EIG_PROF2(5)
     // ---- Gu-Eisenstat z
     for (int g = gw; g < n; g += GW) {
       const int p = S.pid[g], a = S.na[p], r = g - a, k = S.nk[p];
@@ -542,10 +558,48 @@ __global__ void __cluster_dims__(DC_CLUSTER, 1, 1) __launch_bounds__(DC_THREADS,
       }
     }
     cluster.sync();
+    EIG_PROF2(6)
     // ---- new eigenvalues (every CTA, identical)
     if (tid < n) {
       const int p = S.pid[tid], a = S.na[p], r = tid - a;
       S.dn[tid] = (r < S.nk[p]) ? S.dl[a + S.org[tid]] + S.mu[tid] : S.dl[tid];
+    }
+    if (Cmat != nullptr && L == levels) {
+      // ---- top level handed to the caller: final order, eigenvalues, coefficient matrix (one warp per output row)
+      __syncthreads();
+      if (tid < n) {
+        const double dg = S.dn[tid];
+        int r = 0;
+        for (int h = 0; h < n; ++h) {
+          const double dh = S.dn[h];
+          r += (dh < dg) || (dh == dg && h < tid);
+        }
+        S.srt[tid] = r;                       // final position of merged row tid
+        S.pid[S.row[tid]] = tid;              // old row -> its position in the merge (first k: kept, then deflated)
+        if (rank == 0) W[r] = dg * scale;
+      }
+      __syncthreads();
+      const int k = S.nk[0];
+      for (int g = gw; g < n; g += GW) {
+        double* out = Cmat + (long)S.srt[g] * ldc;
+        if (g < k) {
+          const int org_i = S.org[g];
+          const double mu_i = S.mu[g];
+          double nrm = 0.0;
+          for (int j = lane; j < k; j += 32) {
+            const double cf = S.zh[j] / dc::delta_ji(S.dl, j, org_i, mu_i);
+            nrm += cf * cf;
+          }
+          const double inv = 1.0 / sqrt(warp_sum(nrm));
+          for (int c = lane; c < n; c += 32) {
+            const int pos = S.pid[c];
+            out[c] = (pos < k) ? S.zh[pos] / dc::delta_ji(S.dl, pos, org_i, mu_i) * inv : 0.0;
+          }
+        } else {
+          for (int c = lane; c < n; c += 32) out[c] = (S.pid[c] == g) ? 1.0 : 0.0;
+        }
+      }
+      break;
     }
     // ---- eigenvector update: new row a+i = sum_j zh_j / (dl_j - lambda_i) / |.| * old row row[a+j]; deflated rows are copied
     if (mmax <= DC_DIRECT_MAX) {
@@ -646,8 +700,16 @@ __global__ void __cluster_dims__(DC_CLUSTER, 1, 1) __launch_bounds__(DC_THREADS,
     Qold = Qnew;
     Qnew = t;
     __syncthreads();
+    EIG_PROF2(7)
+#ifdef GPCSD_EIG_PROF
+    prof_t[16 + L] = clock64() - lvl_t0;
+#endif
   }
 
+  if (Cmat != nullptr) {
+    cluster.sync();
+    return;
+  }
   // ---- ascending order, undo the scaling, permute the rows into XT
   if (tid < n) {
     const double dg = S.d[tid];
@@ -665,6 +727,8 @@ __global__ void __cluster_dims__(DC_CLUSTER, 1, 1) __launch_bounds__(DC_THREADS,
     for (int col = lane; col < n; col += 32) XT[dst + col] = __ldcg(Qold + (long)g * ldq + col);
   }
   cluster.sync();   // no CTA may exit while peers can still address its shared memory
+  EIG_PROF2(8)
+  EIG_PROF_DUMP(rank == 0 && tid == 0 && mat == 0, 32)
 }
 
 // Apply H = H_0 H_1 ... H_{n-3} to every eigenvector: row x of XT (eigenvector of T) -> H x (H_k symmetric), reflectors
@@ -710,6 +774,14 @@ __global__ void __launch_bounds__(32 * BT_WARPS) backtransform_kernel(int n, con
   }
 }
 
+// stacked identity matrices [nmat][n][ld] (padding columns zero)
+__global__ void identity_rows_kernel(int n, long ld, long total, double* __restrict__ R) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const long c = idx % ld, r = (idx / ld) % n;
+  R[idx] = (c == r) ? 1.0 : 0.0;
+}
+
 }  // namespace gpcsd
 
 using namespace gpcsd;
@@ -751,39 +823,83 @@ int gpcsd_backtransform(int n, int nmat, const double* V, long ldv, const double
 // conquer on 8-CTA clusters: W[nmat][n] ascending, XT[nmat][n][ldx] rows = eigenvectors.  ws: 2*nmat*n*ldx doubles.
 long gpcsd_tridiag_eig_ws_doubles(int n, long ldx, int nmat) { return 2L * nmat * n * ldx; }
 
-int gpcsd_tridiag_eig(int n, int nmat, const double* d, const double* e, double* W, double* XT, long ldx, double* ws,
-                      long ws_doubles, void* stream) {
-  if (n < 2 || n > DC_MAXN) return gp_fail("gpcsd_tridiag_eig: order must be in 2..256");
-  if (ws_doubles < gpcsd_tridiag_eig_ws_doubles(n, ldx, nmat)) return gp_fail("gpcsd_tridiag_eig: workspace too small");
+static int dc_launch(int n, int nmat, const double* d, const double* e, double* Qa, double* Qb, long ldq, double* W, double* XT,
+                     long ldx, double* Cmat, long ldc, cudaStream_t stream) {
   static bool attr = false;
   if (!attr) {
     GP_CUDA(cudaFuncSetAttribute(dc_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DcSmem)));
     attr = true;
   }
-  double* Qa = ws;
-  double* Qb = ws + (long)nmat * n * ldx;
-  dc_cluster_kernel<<<DC_CLUSTER * nmat, DC_THREADS, sizeof(DcSmem), (cudaStream_t)stream>>>(n, d, e, Qa, Qb, ldx, W, XT, ldx);
+  dc_cluster_kernel<<<DC_CLUSTER * nmat, DC_THREADS, sizeof(DcSmem), stream>>>(n, d, e, Qa, Qb, ldq, W, XT, ldx, Cmat, ldc);
   GP_CUDA(cudaGetLastError());
   return 0;
+}
+
+int gpcsd_tridiag_eig(int n, int nmat, const double* d, const double* e, double* W, double* XT, long ldx, double* ws,
+                      long ws_doubles, void* stream) {
+  if (n < 2 || n > DC_MAXN) return gp_fail("gpcsd_tridiag_eig: order must be in 2..256");
+  if (ws_doubles < gpcsd_tridiag_eig_ws_doubles(n, ldx, nmat)) return gp_fail("gpcsd_tridiag_eig: workspace too small");
+  return dc_launch(n, nmat, d, e, ws, ws + (long)nmat * n * ldx, ldx, W, XT, ldx, nullptr, 0, (cudaStream_t)stream);
 }
 
 // Full symmetric eigen-decomposition of `nmat` stacked matrices M[nmat][n][ldm] (3 <= n <= 256): QT[nmat][n][ldq] rows =
 // eigenvectors, W[nmat][n] ascending.  Replaces np.linalg.eigh of utility_functions.py:58-59 for the factor orders that
 // dominate GPCSD evaluations.  M is not modified.  ws: gpcsd_eigh_dc_ws_doubles(n, ldq, nmat) doubles.
-long gpcsd_eigh_dc_ws_doubles(int n, long ldq, int nmat) { return (long)nmat * (3L * n * ldq + 3L * n); }
+//
+// Orders above DC_EXTERNAL_MIN take the long tail off the critical path: while the divide-and-conquer kernel runs, a side
+// stream forms H^T explicitly (the reflectors applied to the identity); the top-level merge and the back-transformation
+// then are two full-GPU DMMA GEMMs,  QT = (C * Q_below) * H^T.  The side stream and its events are per host thread.
+constexpr int DC_EXTERNAL_MIN = 97;
+
+long gpcsd_eigh_dc_ws_doubles(int n, long ldq, int nmat) { return (long)nmat * (6L * n * ldq + 3L * n); }
+
+struct EighSide {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
 
 int gpcsd_eigh_dc(int n, int nmat, const double* M, long ldm, double* QT, long ldq, double* W, double* ws, long ws_doubles,
                   void* stream) {
   if (n < 3 || n > DC_MAXN) return gp_fail("gpcsd_eigh_dc: order must be in 3..256");
   if (ws_doubles < gpcsd_eigh_dc_ws_doubles(n, ldq, nmat)) return gp_fail("gpcsd_eigh_dc: workspace too small");
-  double* V = ws;                                  // reflectors [nmat][n][ldq]
-  double* Qab = V + (long)nmat * n * ldq;          // D&C ping-pong, 2 x [nmat][n][ldq]
-  double* d = Qab + 2L * nmat * n * ldq;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long slab = (long)nmat * n * ldq, mstride = (long)n * ldq;
+  double* V = ws;                     // reflectors
+  double* Qa = V + slab;              // D&C ping-pong
+  double* Qb = Qa + slab;
+  double* Cm = Qb + slab;             // top-level coefficient matrix
+  double* T1 = Cm + slab;             // eigenvectors of T
+  double* R = T1 + slab;              // H^T
+  double* d = R + slab;
   double* e = d + (long)nmat * n;
   double* tau = e + (long)nmat * n;
   if (gpcsd_tridiag(n, nmat, M, ldm, d, e, V, ldq, tau, stream)) return 1;
-  if (gpcsd_tridiag_eig(n, nmat, d, e, W, QT, ldq, Qab, 2L * nmat * n * ldq, stream)) return 1;
-  return gpcsd_backtransform(n, nmat, V, ldq, tau, QT, ldq, stream);
+  if (n < DC_EXTERNAL_MIN) {
+    if (dc_launch(n, nmat, d, e, Qa, Qb, ldq, W, QT, ldq, nullptr, 0, st)) return 1;
+    return gpcsd_backtransform(n, nmat, V, ldq, tau, QT, ldq, stream);
+  }
+  thread_local EighSide side;
+  if (!side.stream) {
+    GP_CUDA(cudaStreamCreateWithFlags(&side.stream, cudaStreamNonBlocking));
+    GP_CUDA(cudaEventCreateWithFlags(&side.fork, cudaEventDisableTiming));
+    GP_CUDA(cudaEventCreateWithFlags(&side.join, cudaEventDisableTiming));
+  }
+  // side stream: R = H^T (rows H e_i)
+  GP_CUDA(cudaEventRecord(side.fork, st));
+  GP_CUDA(cudaStreamWaitEvent(side.stream, side.fork, 0));
+  {
+    const long total = (long)nmat * n * ldq;
+    identity_rows_kernel<<<(int)((total + 255) / 256), 256, 0, side.stream>>>(n, ldq, total, R);
+    GP_CUDA(cudaGetLastError());
+  }
+  if (gpcsd_backtransform(n, nmat, V, ldq, tau, R, ldq, side.stream)) return 1;
+  GP_CUDA(cudaEventRecord(side.join, side.stream));
+  // main stream: divide and conquer up to the top-level coefficients, then the two GEMMs
+  if (dc_launch(n, nmat, d, e, Qa, Qb, ldq, W, nullptr, ldq, Cm, ldq, st)) return 1;
+  const double* Qbelow = (dc::num_levels(n) & 1) ? Qa : Qb;
+  if (gpcsd_dgemm(0, n, n, n, Cm, ldq, mstride, Qbelow, ldq, mstride, T1, ldq, mstride, nmat, stream)) return 1;
+  GP_CUDA(cudaStreamWaitEvent(st, side.join, 0));
+  return gpcsd_dgemm(0, n, n, n, T1, ldq, mstride, R, ldq, mstride, QT, ldq, mstride, nmat, stream);
 }
 
 }  // extern "C"

@@ -339,6 +339,8 @@ class KronEngine:
         nws = L.query("gpcsd_eigh_dc_ws_doubles", n, ld, nmat)
         ws = self._buf("eigdcws_" + tag, nws)
         self._call("gpcsd_eigh_dc", n, nmat, self._p(stack), ld, self._p(QT), ld, self._p(W), self._p(ws), nws, self._stream())
+        if n >= 97:
+            self.n_launches += 3      # H^T formation (2 kernels) + one more GEMM on the large-order path
         return QT, W
 
     def _eigh_pair(self, S, A, m, ld, tag, side):
@@ -435,6 +437,13 @@ class KronEngine:
         with torch.cuda.stream(side):
             side.wait_event(ks_ready)
             st["QsT"], st["ls"], infos_s = self._eigh_spatial(st["Ks"], allow_split=not hp.vector_noise)
+            if self.Y is not None:
+                # Z = Qs^T Y needs the spatial factor only: run it here, underneath the (longer) temporal eigensolve
+                if self._y_ready is not None:
+                    side.wait_event(self._y_ready)
+                st["Z"] = self._buf("Z", self.nx, self.nt, self.ldn)
+                self.gemm(0, self.nx, self.nt * self.ldn, self.nx, st["QsT"], self.ldx, 0, self.Y, self.nt * self.ldn, 0,
+                          st["Z"], self.nt * self.ldn, 0)
             s_done = torch.cuda.Event()
             s_done.record(side)
         st["Kt"] = self._temporal_cov(hp)
@@ -460,10 +469,7 @@ class KronEngine:
         if self.Y is None:
             raise RuntimeError("no LFP uploaded: call set_lfp first")
         nx, nt, ldn = self.nx, self.nt, self.ldn
-        if self._y_ready is not None:
-            torch.cuda.current_stream(self.device).wait_event(self._y_ready)
-        Z = self._buf("Z", nx, nt, ldn)
-        self.gemm(0, nx, nt * ldn, nx, st["QsT"], self.ldx, 0, self.Y, nt * ldn, 0, Z, nt * ldn, 0)
+        Z = st["Z"]                                  # computed on the spatial side stream by _factorize
         Bm = self._buf("Bm", nx, nt, ldn)
         nws = L.query("gpcsd_project_quad_ws_doubles", nx, nt, max(self.ntrials, 1))
         part = self._buf("quad_part", nws)
