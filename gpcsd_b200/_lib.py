@@ -39,9 +39,9 @@ SIGNATURES = {
     "gpcsd_tridiag": (c_int, [c_int, c_int, _P, c_long, _P, _P, _P, c_long, _P, _P]),
     "gpcsd_backtransform": (c_int, [c_int, c_int, _P, c_long, _P, _P, c_long, _P]),
     "gpcsd_tridiag_eig_ws_doubles": (c_long, [c_int, c_long, c_int]),
-    "gpcsd_tridiag_eig": (c_int, [c_int, c_int, _P, _P, _P, _P, c_long, _P, c_long, _P]),
+    "gpcsd_tridiag_eig": (c_int, [c_int, c_int, _P, _P, _P, _P, c_long, _P, c_long, _P, _P]),
     "gpcsd_eigh_dc_ws_doubles": (c_long, [c_int, c_long, c_int]),
-    "gpcsd_eigh_dc": (c_int, [c_int, c_int, _P, c_long, _P, c_long, _P, _P, c_long, _P]),
+    "gpcsd_eigh_dc": (c_int, [c_int, c_int, _P, c_long, _P, c_long, _P, _P, c_long, _P, _P]),
     "gpcsd_centro_split": (c_int, [c_int, _P, c_long, _P, c_long, _P, c_long, _P]),
     "gpcsd_centro_assemble": (c_int, [c_int, _P, c_long, _P, _P, c_long, _P, _P, c_long, _P, _P]),
     "gpcsd_pairsym_split": (c_int, [c_int, _P, c_long, _P, _P, _P, c_long, _P, c_long, _P]),

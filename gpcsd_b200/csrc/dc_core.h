@@ -24,6 +24,25 @@ namespace dc {
 constexpr double EPS = 1.1102230246251565e-16;   // 2^-53 (LAPACK dlamch('E'))
 constexpr int MAX_ITER = 80;
 
+// reciprocal: on the device the IEEE-rounded MUFU.RCP64H + Newton sequence (~8 instructions) instead of the ~30-instruction
+// division; every quotient below is a * rcp(b), within 1.5 ulp, which is all the Gu-Eisenstat argument needs
+DC_HD double rcp(double x) {
+#ifdef __CUDA_ARCH__
+  return __drcp_rn(x);
+#else
+  return 1.0 / x;
+#endif
+}
+
+// sqrt for x >= 0: x * rsqrt(x) on the device (MUFU.RSQ64H + Newton, ~10 instructions instead of ~30)
+DC_HD double fsqrt(double x) {
+#ifdef __CUDA_ARCH__
+  return (x > 0.0) ? x * rsqrt(x) : 0.0;
+#else
+  return sqrt(x);
+#endif
+}
+
 // ---- lane policies: how many cooperating lanes evaluate one sum ---------------------------------------------------------
 struct OneLane {
   static constexpr int L = 1;
@@ -55,10 +74,10 @@ DC_HD int num_levels(int n) {
   return l;
 }
 // first index of node p when [0, n) is cut into `nodes` nearly equal consecutive ranges
-DC_HD int node_start(int n, int nodes, int p) { return (int)(((long long)p * n) / nodes); }
+DC_HD int node_start(int n, int nodes, int p) { return (p * n) / nodes; }      // n, nodes < 2^15
 // node containing position g
 DC_HD int node_of(int n, int nodes, int g) {
-  int p = (int)(((long long)g * nodes) / n);
+  int p = (g * nodes) / n;
   if (node_start(n, nodes, p + 1) <= g) ++p;
   return p;
 }
@@ -72,7 +91,7 @@ DC_HD void secular_eval(int k, int isplit, int org, double mu, const double* dl,
   double ps = 0.0, ph = 0.0, dps = 0.0, dph = 0.0;
   for (int j = X::lane(); j < k; j += X::L) {
     const double del = (dl[j] - dlo) - mu;
-    const double t = w[j] / del;
+    const double t = w[j] * rcp(del);
     const double wt = w[j] * t, tt = t * t;
     if (j <= isplit) {
       ps += wt;
@@ -91,8 +110,8 @@ DC_HD void secular_eval(int k, int isplit, int org, double mu, const double* dl,
 // next point strictly inside the bracket (lo, hi): arithmetic midpoint, or the geometric one when the ends have the same
 // sign and differ by orders of magnitude (roots that sit extremely close to their pole)
 DC_HD double bracket_mid(double lo, double hi) {
-  if (lo > 0.0 && hi > 16.0 * lo) return sqrt(lo) * sqrt(hi);
-  if (hi < 0.0 && lo < 16.0 * hi) return -sqrt(-lo) * sqrt(-hi);
+  if (lo > 0.0 && hi > 16.0 * lo) return fsqrt(lo) * fsqrt(hi);
+  if (hi < 0.0 && lo < 16.0 * hi) return -fsqrt(-lo) * fsqrt(-hi);
   if (lo == 0.0 && hi > 0.0) return hi * 9.765625e-4;     // 2^-10: walk towards the pole geometrically
   if (hi == 0.0 && lo < 0.0) return lo * 9.765625e-4;
   return 0.5 * (lo + hi);
@@ -102,7 +121,7 @@ DC_HD double bracket_mid(double lo, double hi) {
 // and receive identical results.
 template <class X>
 DC_HD void secular_root(int k, int i, const double* dl, const double* w, double rho, double& mu_out, int& org_out) {
-  const double rhoinv = 1.0 / rho;
+  const double rhoinv = rcp(rho);
   if (k == 1) {
     org_out = 0;
     mu_out = rho * w[0] * w[0];
@@ -120,17 +139,18 @@ DC_HD void secular_root(int k, int i, const double* dl, const double* w, double 
     const double fm = rhoinv + psi + phi;
     const double wl2 = w[pl] * w[pl], wr2 = w[pr] * w[pr];
     // value of everything but the two nearest poles at the midpoint
-    const double c0 = fm - wl2 / (-half) - wr2 / half;
+    const double rhalf = rcp(half);
+    const double c0 = fm + wl2 * rhalf - wr2 * rhalf;
     if (fm > 0.0) {            // root in the left half: origin = left pole
       org = pl; lo = 0.0; hi = half;
       const double A = c0 * gap + wl2 + wr2, B = wl2 * gap;
-      const double s = sqrt(fabs(A * A - 4.0 * B * c0));
-      mu = (A > 0.0) ? 2.0 * B / (A + s) : (A - s) / (2.0 * c0);
+      const double s = fsqrt(fabs(A * A - 4.0 * B * c0));
+      mu = (A > 0.0) ? 2.0 * B * rcp(A + s) : (A - s) * rcp(2.0 * c0);
     } else {                   // right half: origin = right pole, mu < 0
       org = pr; lo = -half; hi = 0.0;
       const double A = -c0 * gap + wl2 + wr2, B = wr2 * gap;
-      const double s = sqrt(fabs(A * A + 4.0 * B * c0));
-      mu = (A > 0.0) ? -2.0 * B / (A + s) : (A - s) / (2.0 * c0);
+      const double s = fsqrt(fabs(A * A + 4.0 * B * c0));
+      mu = (A > 0.0) ? -2.0 * B * rcp(A + s) : (A - s) * rcp(2.0 * c0);
     }
   } else {
     double wsq = 0.0;
@@ -143,10 +163,10 @@ DC_HD void secular_root(int k, int i, const double* dl, const double* w, double 
     if (fm > 0.0) hi = half; else lo = half;
     const double g = dl[pr] - dl[pl];
     const double wl2 = w[pl] * w[pl], wr2 = w[pr] * w[pr];
-    const double c0 = fm - wl2 / (-g - half) - wr2 / (-half);
+    const double c0 = fm + wl2 * rcp(g + half) + wr2 * rcp(half);
     const double A = -c0 * g + wl2 + wr2, B = wr2 * g;
-    const double s = sqrt(fabs(A * A + 4.0 * B * c0));
-    mu = (A < 0.0) ? 2.0 * B / (s - A) : (A + s) / (2.0 * c0);
+    const double s = fsqrt(fabs(A * A + 4.0 * B * c0));
+    mu = (A < 0.0) ? 2.0 * B * rcp(s - A) : (A + s) * rcp(2.0 * c0);
   }
   if (!(mu > lo && mu < hi)) mu = bracket_mid(lo, hi);
 
@@ -162,15 +182,15 @@ DC_HD void secular_root(int k, int i, const double* dl, const double* w, double 
     const double A = (D0 + D1) * f - D0 * D1 * dw;
     const double B = D0 * D1 * f;
     double eta;
-    const double s = sqrt(fabs(A * A - 4.0 * B * C));
+    const double s = fsqrt(fabs(A * A - 4.0 * B * C));
     if (C == 0.0) {
-      eta = B / A;
+      eta = B * rcp(A);
     } else if (!last) {
-      eta = (A <= 0.0) ? (A - s) / (2.0 * C) : 2.0 * B / (A + s);
+      eta = (A <= 0.0) ? (A - s) * rcp(2.0 * C) : 2.0 * B * rcp(A + s);
     } else {
-      eta = (A >= 0.0) ? (A + s) / (2.0 * C) : 2.0 * B / (A - s);
+      eta = (A >= 0.0) ? (A + s) * rcp(2.0 * C) : 2.0 * B * rcp(A - s);
     }
-    if (!(f * eta < 0.0)) eta = -f / dw;          // wrong direction (or NaN): Newton step
+    if (!(f * eta < 0.0)) eta = -f * rcp(dw);     // wrong direction (or NaN): Newton step
     double munew = mu + eta;
     if (!(munew > lo && munew < hi)) munew = bracket_mid(lo, hi);
     if (!(munew > lo && munew < hi) || munew == mu) break;       // bracket exhausted
@@ -190,10 +210,10 @@ DC_HD double zhat_component(int k, int j, const double* dl, const double* w, con
   double p = 1.0;
   for (int i = X::lane(); i < k; i += X::L) {
     const double del = delta_ji(dl, j, org[i], mu[i]);
-    p *= (i == j) ? fabs(del) : fabs(del / (dl[j] - dl[i]));
+    p *= (i == j) ? fabs(del) : fabs(del * rcp(dl[j] - dl[i]));
   }
   p = X::prod(p);
-  return copysign(sqrt(p), w[j]);
+  return copysign(fsqrt(p), w[j]);
 }
 
 // 1 / |u_i| for the eigenvector u_i[j] = zhat[j] / (dl[j] - lambda_i)
@@ -201,76 +221,88 @@ template <class X>
 DC_HD double inv_norm(int k, int org_i, double mu_i, const double* dl, const double* zhat) {
   double s = 0.0;
   for (int j = X::lane(); j < k; j += X::L) {
-    const double t = zhat[j] / delta_ji(dl, j, org_i, mu_i);
+    const double t = zhat[j] * rcp(delta_ji(dl, j, org_i, mu_i));
     s += t * t;
   }
-  return 1.0 / sqrt(X::sum(s));
+  return rcp(fsqrt(X::sum(s)));
 }
 
 // ---- deflation (LAPACK dlaed2 logic) ------------------------------------------------------------------------------------
-// One caller per merge node.  Position-indexed arrays are addressed [a, a+m); d, z are indexed by eigenvector ROW (global).
-//   in : srt[a+s] = row with the s-th smallest d;  d[row], z[row] (|z| = 1 over the node), rho, and the node's
-//        dmax = max |d|, zmax = max |z|
+// One caller per merge node; a serial scan whose loop-carried state (the last kept candidate) stays in registers and whose
+// inputs are read from contiguous, sorted arrays (prefetched one element ahead).  Position-indexed arrays are addressed
+// [a, a+m).
+//   in : srt[a+s] = eigenvector row with the s-th smallest d, dS[a+s], zS[a+s] its d and z (|z| = 1 over the node), rho, and
+//        the node's dmax = max |d|, zmax = max |z|
 //   out: k; row_out[a+r], dl[a+r], w[a+r] for the k kept entries (ascending), row_out[a+pos], dl[a+pos] (final eigenvalue)
 //        for the deflated ones, pos = k..m-1; Givens rotations (rows rp, rn; c, s) in application order, nrot of them.
-// d and z are updated in place by the rotations.
-DC_HD void deflate(int a, int m, const int* srt, double* d, double* z, double rho, double dmax, double zmax, int* row_out,
-                   double* dl, double* w, int* rot_p, int* rot_n, double* rot_c, double* rot_s, int& k_out, int& nrot_out) {
+DC_HD void deflate(int a, int m, const int* srt, const double* dS, const double* zS, double rho, double dmax, double zmax,
+                   int* row_out, double* dl, double* w, int* rot_p, int* rot_n, double* rot_c, double* rot_s, int& k_out,
+                   int& nrot_out) {
   const double tol = 8.0 * EPS * fmax(dmax, zmax);
   int k = 0, k2 = m, nrot = 0;
   if (!(rho * zmax > tol)) {
     for (int s = 0; s < m; ++s) {
-      const int r = srt[a + s];
-      row_out[a + s] = r;
-      dl[a + s] = d[r];
+      row_out[a + s] = srt[a + s];
+      dl[a + s] = dS[a + s];
     }
     k_out = 0;
     nrot_out = 0;
     return;
   }
   int pj = -1;
+  double dp = 0.0, zp = 0.0;                  // d and z of the candidate pj (as modified by earlier rotations)
+  double dnx = dS[a], znx = zS[a];
+  int rnx = srt[a];
   for (int s = 0; s < m; ++s) {
-    const int nj = srt[a + s];
-    if (!(rho * fabs(z[nj]) > tol)) {          // negligible coupling: eigenpair unchanged
+    const double dc = dnx, zc = znx;
+    const int nj = rnx;
+    if (s + 1 < m) {
+      dnx = dS[a + s + 1];
+      znx = zS[a + s + 1];
+      rnx = srt[a + s + 1];
+    }
+    if (!(rho * fabs(zc) > tol)) {            // negligible coupling: eigenpair unchanged
       --k2;
       row_out[a + k2] = nj;
-      dl[a + k2] = d[nj];
+      dl[a + k2] = dc;
       continue;
     }
     if (pj < 0) {
       pj = nj;
+      dp = dc;
+      zp = zc;
       continue;
     }
-    const double zs = z[pj], zc = z[nj], t = d[nj] - d[pj];
-    const double h2 = zc * zc + zs * zs;
-    if (fabs(t * zc * zs) <= tol * h2) {       // |t c s| <= tol: rotate the pair so that z[pj] = 0 and deflate pj
-      const double tau = sqrt(h2), c = zc / tau, sn = -zs / tau;
-      z[nj] = tau;
-      z[pj] = 0.0;
+    const double t = dc - dp;
+    const double h2 = zc * zc + zp * zp;
+    if (fabs(t * zc * zp) <= tol * h2) {      // |t c s| <= tol: rotate the pair so that z[pj] = 0 and deflate pj
+      const double tau = fsqrt(h2), rt = rcp(tau), c = zc * rt, sn = -zp * rt;
       rot_p[a + nrot] = pj;
       rot_n[a + nrot] = nj;
       rot_c[a + nrot] = c;
       rot_s[a + nrot] = sn;
       ++nrot;
-      const double dp = d[pj] * c * c + d[nj] * sn * sn;
-      d[nj] = d[pj] * sn * sn + d[nj] * c * c;
-      d[pj] = dp;
+      const double dpn = dp * c * c + dc * sn * sn;
       --k2;
       row_out[a + k2] = pj;
-      dl[a + k2] = dp;
+      dl[a + k2] = dpn;
+      dp = dp * sn * sn + dc * c * c;
+      zp = tau;
       pj = nj;
     } else {
       row_out[a + k] = pj;
-      dl[a + k] = d[pj];
-      w[a + k] = z[pj];
+      dl[a + k] = dp;
+      w[a + k] = zp;
       ++k;
       pj = nj;
+      dp = dc;
+      zp = zc;
     }
   }
   if (pj >= 0) {
     row_out[a + k] = pj;
-    dl[a + k] = d[pj];
-    w[a + k] = z[pj];
+    dl[a + k] = dp;
+    w[a + k] = zp;
     ++k;
   }
   k_out = k;

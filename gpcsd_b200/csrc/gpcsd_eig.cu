@@ -376,7 +376,7 @@ constexpr int DC_DIRECT_MAX = 32;                     // merge nodes up to this 
 
 struct DcSmem {
   // replicated in every CTA (each CTA runs the O(n) bookkeeping redundantly, bit-identically)
-  double d[DC_MAXN], dn[DC_MAXN], z[DC_MAXN], dl[DC_MAXN], w[DC_MAXN], rot_c[DC_MAXN], rot_s[DC_MAXN];
+  double d[DC_MAXN], dn[DC_MAXN], z[DC_MAXN], dS[DC_MAXN], zS[DC_MAXN], dl[DC_MAXN], w[DC_MAXN], rot_c[DC_MAXN], rot_s[DC_MAXN];
   int srt[DC_MAXN], row[DC_MAXN], rot_p[DC_MAXN], rot_n[DC_MAXN], pid[DC_MAXN];
   int na[DC_MAXNODES], nc[DC_MAXNODES], nb[DC_MAXNODES], nk[DC_MAXNODES], nrot[DC_MAXNODES];
   double nrho[DC_MAXNODES];
@@ -391,6 +391,74 @@ struct DcSmem {
   double red[DC_WARPS];
 };
 
+// G adjacent lanes cooperate on one secular root / one z component: G = 32 for the large merges, 4 and 1 for the small ones
+// at the bottom of the tree, where a 5-stage warp reduction per sum would cost more than the sums themselves
+template <int G>
+struct GroupLanes {
+  static constexpr int L = G;
+  __device__ __forceinline__ static int lane() { return threadIdx.x & (G - 1); }
+  __device__ __forceinline__ static unsigned mask() {
+    return G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
+  }
+  __device__ __forceinline__ static double sum(double x) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) x += __shfl_xor_sync(mask(), x, o);
+    return x;
+  }
+  __device__ __forceinline__ static double prod(double x) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) x *= __shfl_xor_sync(mask(), x, o);
+    return x;
+  }
+};
+
+// Secular roots of the merge nodes covering positions [glo, ghi), spread over lane groups of G lanes.  `nshare` CTAs share
+// the range (this one is number `me` of them); with nshare == 1 the results stay in this CTA's shared memory, otherwise
+// (mu, org) are stored into every CTA of the cluster.
+template <int G>
+__device__ __forceinline__ void dc_secular_phase(DcSmem& S, cg::cluster_group& cluster, int glo, int ghi, int me, int nshare) {
+  const int gid = (me * DC_THREADS + (int)threadIdx.x) / G, ngroups = nshare * DC_THREADS / G;
+  const int gl = threadIdx.x & (G - 1);
+  for (int g = glo + gid; g < ghi; g += ngroups) {
+    const int p = S.pid[g], a = S.na[p], r = g - a, k = S.nk[p];
+    if (r < k) {
+      double mu;
+      int org;
+      dc::secular_root<GroupLanes<G>>(k, r, &S.dl[a], &S.w[a], S.nrho[p], mu, org);
+      if (nshare == 1) {
+        if (gl == 0) {
+          S.mu[g] = mu;
+          S.org[g] = org;
+        }
+      } else {
+        for (int c = gl; c < DC_CLUSTER; c += G) {
+          DcSmem* pr = cluster.map_shared_rank(&S, c);
+          pr->mu[g] = mu;
+          pr->org[g] = org;
+        }
+      }
+    }
+  }
+}
+
+// Gu-Eisenstat z of the same nodes
+template <int G>
+__device__ __forceinline__ void dc_zhat_phase(DcSmem& S, cg::cluster_group& cluster, int glo, int ghi, int me, int nshare) {
+  const int gid = (me * DC_THREADS + (int)threadIdx.x) / G, ngroups = nshare * DC_THREADS / G;
+  const int gl = threadIdx.x & (G - 1);
+  for (int g = glo + gid; g < ghi; g += ngroups) {
+    const int p = S.pid[g], a = S.na[p], r = g - a, k = S.nk[p];
+    if (r < k) {
+      const double zh = dc::zhat_component<GroupLanes<G>>(k, r, &S.dl[a], &S.w[a], &S.mu[a], &S.org[a]);
+      if (nshare == 1) {
+        if (gl == 0) S.zh[g] = zh;
+      } else {
+        for (int c = gl; c < DC_CLUSTER; c += G) cluster.map_shared_rank(&S, c)->zh[g] = zh;
+      }
+    }
+  }
+}
+
 // grid = 8 * nmat CTAs, cluster (8,1,1).  d_in[nmat][n], e_in[nmat][n] with e_in[k] = T[k+1][k].  Qa, Qb: [nmat][n][ldq]
 // workspaces.  Out: W[nmat][n] ascending, XT[nmat][n][ldx] rows = eigenvectors of T in the order of W.
 // With Cmat != nullptr the LAST merge is left to the caller as a full-GPU GEMM: the kernel stops after the secular solve of
@@ -398,7 +466,8 @@ struct DcSmem {
 // rows = unit vectors) so that XT = Cmat * Q, Q = the level below (in Qa if ceil(log2 n) is odd, else Qb).
 __global__ void __cluster_dims__(DC_CLUSTER, 1, 1) __launch_bounds__(DC_THREADS, 1)
     dc_cluster_kernel(int n, const double* __restrict__ d_in, const double* __restrict__ e_in, double* Qa, double* Qb, long ldq,
-                      double* __restrict__ W, double* XT, long ldx, double* __restrict__ Cmat, long ldc) {
+                      double* __restrict__ W, double* XT, long ldx, double* __restrict__ Cmat, long ldc,
+                      int* __restrict__ info) {
   extern __shared__ __align__(16) unsigned char dc_raw[];
   DcSmem& S = *reinterpret_cast<DcSmem*>(dc_raw);
   cg::cluster_group cluster = cg::this_cluster();
@@ -414,8 +483,26 @@ __global__ void __cluster_dims__(DC_CLUSTER, 1, 1) __launch_bounds__(DC_THREADS,
   W += (long)mat * n;
   XT += (long)mat * n * ldx;
   if (Cmat) Cmat += (long)mat * n * ldc;
-  DcSmem* peer = cluster.map_shared_rank(&S, lane & (DC_CLUSTER - 1));
 
+  // ---- non-finite input (the reference lets NaN/inf flow and numpy.linalg.eigh then raises LinAlgError): every index
+  //      computation below assumes a total order, so report it (info = 1, NaN outputs) and stop.  All CTAs agree.
+  {
+    int bad = 0;
+    for (int i = tid; i < n; i += DC_THREADS) bad |= !isfinite(d_in[i]) || (i < n - 1 && !isfinite(e_in[i]));
+    bad = __syncthreads_or(bad);
+    if (info && rank == 0 && tid == 0) info[mat] = bad ? 1 : 0;
+    if (bad) {
+      const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+      double* out = Cmat ? Cmat : XT;
+      const long ldo = Cmat ? ldc : ldx;
+      for (int idx = rank * DC_THREADS + tid; idx < n * n; idx += DC_CLUSTER * DC_THREADS) {
+        const int r = idx / n, c = idx - r * n;
+        out[(long)r * ldo + c] = qnan;
+      }
+      if (rank == 0 && tid < n) W[tid] = qnan;
+      return;
+    }
+  }
   // ---- scale to unit max-norm, tear every off-diagonal (leaves of size 1), Q = I
   double v = 0.0;
   for (int i = tid; i < n; i += DC_THREADS) v = fmax(v, fmax(fabs(d_in[i]), (i < n - 1) ? fabs(e_in[i]) : 0.0));
@@ -443,69 +530,95 @@ __global__ void __cluster_dims__(DC_CLUSTER, 1, 1) __launch_bounds__(DC_THREADS,
   EIG_PROF2(0)
 
   const int levels = dc::num_levels(n);
+  bool shared_mode = false;
+  int glo_prev = 0, ghi_prev = 0;
   for (int L = 1; L <= levels; ++L) {
 #ifdef GPCSD_EIG_PROF
     const long long lvl_t0 = clock64();
 #endif
     const int nodes = 1 << (levels - L);
     const int mmax = (n + nodes - 1) / nodes;
-    // ---- node table
-    if (tid < nodes) {
-      const int a = dc::node_start(n, 2 * nodes, 2 * tid), c = dc::node_start(n, 2 * nodes, 2 * tid + 1),
-                b = dc::node_start(n, 2 * nodes, 2 * tid + 2);
-      S.na[tid] = a;
-      S.nc[tid] = c;
-      S.nb[tid] = b;
-      S.nrho[tid] = (c == a || c == b) ? 0.0 : 2.0 * fabs(e_in[c - 1] / scale);
-      S.ndmax[tid] = 0ull;
-      S.nzmax[tid] = 0ull;
+    // While the level has at least one node per CTA, every CTA merges its own contiguous share of the nodes with no
+    // communication at all (CTA barriers only); the levels above are shared by the whole cluster.
+    const bool local = nodes >= DC_CLUSTER;
+    if (!local && !shared_mode) {
+      // first shared level: every CTA publishes the eigenvalues of its share (the eigenvector blocks are in global memory)
+      if (tid < ghi_prev - glo_prev) {
+        const double dv = S.d[glo_prev + tid];
+        for (int c = 0; c < DC_CLUSTER; ++c) cluster.map_shared_rank(&S, c)->d[glo_prev + tid] = dv;
+      }
+      cluster.sync();
+      shared_mode = true;
     }
-    if (tid < n) S.pid[tid] = dc::node_of(n, nodes, tid);
+    const int plo = local ? rank * (nodes / DC_CLUSTER) : 0, phi = local ? plo + nodes / DC_CLUSTER : nodes;
+    const int glo = dc::node_start(n, nodes, plo), ghi = dc::node_start(n, nodes, phi);
+    const int me = local ? 0 : rank, nshare = local ? 1 : DC_CLUSTER;
+    glo_prev = glo;
+    ghi_prev = ghi;
+    const int g_own = glo + tid;                 // the position this thread looks after in the per-position phases
+    const bool has_g = g_own < ghi;
+    // ---- node table
+    if (tid < phi - plo) {
+      const int p = plo + tid;
+      const int a = dc::node_start(n, 2 * nodes, 2 * p), c = dc::node_start(n, 2 * nodes, 2 * p + 1),
+                b = dc::node_start(n, 2 * nodes, 2 * p + 2);
+      S.na[p] = a;
+      S.nc[p] = c;
+      S.nb[p] = b;
+      S.nrho[p] = (c == a || c == b) ? 0.0 : 2.0 * fabs(e_in[c - 1] / scale);
+      S.ndmax[p] = 0ull;
+      S.nzmax[p] = 0ull;
+    }
+    if (has_g) S.pid[g_own] = dc::node_of(n, nodes, g_own);
     __syncthreads();
     // ---- z = [last component of the left child's eigenvectors; sign(e_c) * first component of the right child's] / sqrt 2
-    if (tid < n) {
-      const int p = S.pid[tid], c = S.nc[p];
+    if (has_g) {
+      const int p = S.pid[g_own], c = S.nc[p];
       double zz = 0.0;
       if (S.nrho[p] != 0.0) {
-        const double q = __ldcg(Qold + (long)tid * ldq + ((tid < c) ? c - 1 : c));
-        zz = ((tid < c || e_in[c - 1] >= 0.0) ? q : -q) * 0.70710678118654752440;
+        const double q = __ldcg(Qold + (long)g_own * ldq + ((g_own < c) ? c - 1 : c));
+        zz = ((g_own < c || e_in[c - 1] >= 0.0) ? q : -q) * 0.70710678118654752440;
       }
-      S.z[tid] = zz;
-      atomicMax(&S.ndmax[p], (unsigned long long)__double_as_longlong(fabs(S.d[tid])));
+      S.z[g_own] = zz;
+      atomicMax(&S.ndmax[p], (unsigned long long)__double_as_longlong(fabs(S.d[g_own])));
       atomicMax(&S.nzmax[p], (unsigned long long)__double_as_longlong(fabs(zz)));
     }
     __syncthreads();
     EIG_PROF2(1)
     // ---- counting sort of the node's eigenvalues
-    if (tid < n) {
-      const int p = S.pid[tid], a = S.na[p], b = S.nb[p];
-      const double dg = S.d[tid];
+    if (has_g) {
+      const int p = S.pid[g_own], a = S.na[p], b = S.nb[p];
+      const double dg = S.d[g_own];
       int r = 0;
       for (int h = a; h < b; ++h) {
         const double dh = S.d[h];
-        r += (dh < dg) || (dh == dg && h < tid);
+        r += (dh < dg) || (dh == dg && h < g_own);
       }
-      S.srt[a + r] = tid;
+      S.srt[a + r] = g_own;
+      S.dS[a + r] = dg;
+      S.zS[a + r] = S.z[g_own];
     }
     __syncthreads();
     EIG_PROF2(2)
     // ---- deflation, one thread per node
-    if (tid < nodes) {
-      const int a = S.na[tid], m = S.nb[tid] - a;
+    if (tid < phi - plo) {
+      const int p = plo + tid;
+      const int a = S.na[p], m = S.nb[p] - a;
       int k = 0, nrot = 0;
       if (m > 0)
-        dc::deflate(a, m, S.srt, S.d, S.z, S.nrho[tid], __longlong_as_double((long long)S.ndmax[tid]),
-                    __longlong_as_double((long long)S.nzmax[tid]), S.row, S.dl, S.w, S.rot_p, S.rot_n, S.rot_c, S.rot_s, k,
+        dc::deflate(a, m, S.srt, S.dS, S.zS, S.nrho[p], __longlong_as_double((long long)S.ndmax[p]),
+                    __longlong_as_double((long long)S.nzmax[p]), S.row, S.dl, S.w, S.rot_p, S.rot_n, S.rot_c, S.rot_s, k,
                     nrot);
-      S.nk[tid] = k;
-      S.nrot[tid] = nrot;
+      S.nk[p] = k;
+      S.nrot[p] = nrot;
     }
     __syncthreads();
     EIG_PROF2(3)
     // ---- deflating Givens rotations on the rows of Qold: one thread per column, the running row stays in a register
-    if (warp == 0) {
-      const int col = rank * 32 + lane;
-      if (col < n) {
+    {
+      // shared level: 32 columns per CTA (n <= 256); local level: the CTA's own columns
+      const int col = local ? g_own : ((warp == 0) ? rank * 32 + lane : n);
+      if (col < (local ? ghi : n)) {
         const int p = S.pid[col], a = S.na[p], nr = S.nrot[p];
         if (nr > 0) {
           double* Q = Qold + col;
@@ -532,37 +645,36 @@ __global__ void __cluster_dims__(DC_CLUSTER, 1, 1) __launch_bounds__(DC_THREADS,
         }
       }
     }
-    cluster.sync();
+    if (local) __syncthreads(); else cluster.sync();
     EIG_PROF2(4)
-    // ---- secular roots: one warp per root, broadcast (mu, org) to every CTA
-    for (int g = gw; g < n; g += GW) {
-      const int p = S.pid[g], a = S.na[p], r = g - a, k = S.nk[p];
-      if (r < k) {
-        double mu;
-        int org;
-        dc::secular_root<dc::WarpLanes>(k, r, &S.dl[a], &S.w[a], S.nrho[p], mu, org);
-        if (lane < DC_CLUSTER) {
-          peer->mu[g] = mu;
-          peer->org[g] = org;
-        }
-      }
+    // ---- secular roots
+    if (local) {
+      if (mmax <= 2) dc_secular_phase<1>(S, cluster, glo, ghi, me, nshare);
+      else if (mmax <= 8) dc_secular_phase<4>(S, cluster, glo, ghi, me, nshare);
+      else dc_secular_phase<16>(S, cluster, glo, ghi, me, nshare);
+    } else {
+      if (mmax <= 4) dc_secular_phase<1>(S, cluster, glo, ghi, me, nshare);
+      else if (mmax <= 32) dc_secular_phase<4>(S, cluster, glo, ghi, me, nshare);
+      else dc_secular_phase<32>(S, cluster, glo, ghi, me, nshare);
     }
-    cluster.sync();
+    if (local) __syncthreads(); else cluster.sync();
     EIG_PROF2(5)
     // ---- Gu-Eisenstat z
-    for (int g = gw; g < n; g += GW) {
-      const int p = S.pid[g], a = S.na[p], r = g - a, k = S.nk[p];
-      if (r < k) {
-        const double zh = dc::zhat_component<dc::WarpLanes>(k, r, &S.dl[a], &S.w[a], &S.mu[a], &S.org[a]);
-        if (lane < DC_CLUSTER) peer->zh[g] = zh;
-      }
+    if (local) {
+      if (mmax <= 2) dc_zhat_phase<1>(S, cluster, glo, ghi, me, nshare);
+      else if (mmax <= 8) dc_zhat_phase<4>(S, cluster, glo, ghi, me, nshare);
+      else dc_zhat_phase<16>(S, cluster, glo, ghi, me, nshare);
+    } else {
+      if (mmax <= 4) dc_zhat_phase<1>(S, cluster, glo, ghi, me, nshare);
+      else if (mmax <= 32) dc_zhat_phase<4>(S, cluster, glo, ghi, me, nshare);
+      else dc_zhat_phase<32>(S, cluster, glo, ghi, me, nshare);
     }
-    cluster.sync();
+    if (local) __syncthreads(); else cluster.sync();
     EIG_PROF2(6)
     // ---- new eigenvalues (every CTA, identical)
-    if (tid < n) {
-      const int p = S.pid[tid], a = S.na[p], r = tid - a;
-      S.dn[tid] = (r < S.nk[p]) ? S.dl[a + S.org[tid]] + S.mu[tid] : S.dl[tid];
+    if (has_g) {
+      const int p = S.pid[g_own], a = S.na[p], r = g_own - a;
+      S.dn[g_own] = (r < S.nk[p]) ? S.dl[a + S.org[g_own]] + S.mu[g_own] : S.dl[g_own];
     }
     if (Cmat != nullptr && L == levels) {
       // ---- top level handed to the caller: final order, eigenvalues, coefficient matrix (one warp per output row)
@@ -587,13 +699,13 @@ __global__ void __cluster_dims__(DC_CLUSTER, 1, 1) __launch_bounds__(DC_THREADS,
           const double mu_i = S.mu[g];
           double nrm = 0.0;
           for (int j = lane; j < k; j += 32) {
-            const double cf = S.zh[j] / dc::delta_ji(S.dl, j, org_i, mu_i);
+            const double cf = S.zh[j] * dc::rcp(dc::delta_ji(S.dl, j, org_i, mu_i));
             nrm += cf * cf;
           }
-          const double inv = 1.0 / sqrt(warp_sum(nrm));
+          const double inv = rsqrt(warp_sum(nrm));
           for (int c = lane; c < n; c += 32) {
             const int pos = S.pid[c];
-            out[c] = (pos < k) ? S.zh[pos] / dc::delta_ji(S.dl, pos, org_i, mu_i) * inv : 0.0;
+            out[c] = (pos < k) ? S.zh[pos] * dc::rcp(dc::delta_ji(S.dl, pos, org_i, mu_i)) * inv : 0.0;
           }
         } else {
           for (int c = lane; c < n; c += 32) out[c] = (S.pid[c] == g) ? 1.0 : 0.0;
@@ -603,25 +715,27 @@ __global__ void __cluster_dims__(DC_CLUSTER, 1, 1) __launch_bounds__(DC_THREADS,
     }
     // ---- eigenvector update: new row a+i = sum_j zh_j / (dl_j - lambda_i) / |.| * old row row[a+j]; deflated rows are copied
     if (mmax <= DC_DIRECT_MAX) {
-      for (int g = gw; g < n; g += GW) {
+      // small nodes: one thread per output element
+      for (int idx = me * DC_THREADS + tid; idx < (ghi - glo) * mmax; idx += nshare * DC_THREADS) {
+        const int g = glo + idx / mmax, cc = idx - (g - glo) * mmax;
         const int p = S.pid[g], a = S.na[p], m = S.nb[p] - a, r = g - a, k = S.nk[p];
-        const bool active = lane < m;
-        const int col = a + (active ? lane : 0);
+        if (cc >= m) continue;
+        const int col = a + cc;
         double out;
         if (r < k) {
           const int org_i = S.org[g];
           const double mu_i = S.mu[g];
           double acc = 0.0, nrm = 0.0;
           for (int j = 0; j < k; ++j) {
-            const double cf = S.zh[a + j] / dc::delta_ji(&S.dl[a], j, org_i, mu_i);
+            const double cf = S.zh[a + j] * dc::rcp(dc::delta_ji(&S.dl[a], j, org_i, mu_i));
             nrm += cf * cf;
             acc += cf * __ldcg(Qold + (long)S.row[a + j] * ldq + col);
           }
-          out = acc / sqrt(nrm);
+          out = acc * rsqrt(nrm);
         } else {
           out = __ldcg(Qold + (long)S.row[g] * ldq + col);
         }
-        if (active) Qnew[(long)g * ldq + col] = out;
+        Qnew[(long)g * ldq + col] = out;
       }
     } else {
       const int tr = (mmax + DC_TM - 1) / DC_TM, tc = (mmax + DC_TN - 1) / DC_TN;
@@ -648,7 +762,7 @@ __global__ void __cluster_dims__(DC_CLUSTER, 1, 1) __launch_bounds__(DC_THREADS,
           for (int h = 0; h < 2; ++h) {
             const int kk = kq + 8 * h, j = j0 + kk;
             double cf = 0.0;
-            if (vi && j < k) cf = S.zh[a + j] / dc::delta_ji(&S.dl[a], j, org_i, mu_i);
+            if (vi && j < k) cf = S.zh[a + j] * dc::rcp(dc::delta_ji(&S.dl[a], j, org_i, mu_i));
             S.As[kk][ii] = cf;
             nrm_part += cf * cf;
           }
@@ -676,7 +790,7 @@ __global__ void __cluster_dims__(DC_CLUSTER, 1, 1) __launch_bounds__(DC_THREADS,
           double s = 0.0;
 #pragma unroll
           for (int q = 0; q < DC_THREADS / DC_TM; ++q) s += S.nrm[q][tid];
-          S.inv[tid] = (s > 0.0) ? 1.0 / sqrt(s) : 0.0;
+          S.inv[tid] = (s > 0.0) ? rsqrt(s) : 0.0;
         }
         __syncthreads();
 #pragma unroll
@@ -694,8 +808,8 @@ __global__ void __cluster_dims__(DC_CLUSTER, 1, 1) __launch_bounds__(DC_THREADS,
         __syncthreads();
       }
     }
-    cluster.sync();
-    if (tid < n) S.d[tid] = S.dn[tid];
+    if (local) __syncthreads(); else cluster.sync();
+    if (has_g) S.d[g_own] = S.dn[g_own];
     double* t = Qold;
     Qold = Qnew;
     Qnew = t;
@@ -821,25 +935,26 @@ int gpcsd_backtransform(int n, int nmat, const double* V, long ldv, const double
 
 // Eigen-decomposition of `nmat` symmetric tridiagonal matrices (d[nmat][n], e[nmat][n], e[k] = T[k+1][k]) by divide and
 // conquer on 8-CTA clusters: W[nmat][n] ascending, XT[nmat][n][ldx] rows = eigenvectors.  ws: 2*nmat*n*ldx doubles.
+// info[nmat] (device, may be null): 0, or 1 when the matrix holds a non-finite entry (outputs are then NaN).
 long gpcsd_tridiag_eig_ws_doubles(int n, long ldx, int nmat) { return 2L * nmat * n * ldx; }
 
 static int dc_launch(int n, int nmat, const double* d, const double* e, double* Qa, double* Qb, long ldq, double* W, double* XT,
-                     long ldx, double* Cmat, long ldc, cudaStream_t stream) {
+                     long ldx, double* Cmat, long ldc, int* info, cudaStream_t stream) {
   static bool attr = false;
   if (!attr) {
     GP_CUDA(cudaFuncSetAttribute(dc_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DcSmem)));
     attr = true;
   }
-  dc_cluster_kernel<<<DC_CLUSTER * nmat, DC_THREADS, sizeof(DcSmem), stream>>>(n, d, e, Qa, Qb, ldq, W, XT, ldx, Cmat, ldc);
+  dc_cluster_kernel<<<DC_CLUSTER * nmat, DC_THREADS, sizeof(DcSmem), stream>>>(n, d, e, Qa, Qb, ldq, W, XT, ldx, Cmat, ldc, info);
   GP_CUDA(cudaGetLastError());
   return 0;
 }
 
 int gpcsd_tridiag_eig(int n, int nmat, const double* d, const double* e, double* W, double* XT, long ldx, double* ws,
-                      long ws_doubles, void* stream) {
+                      long ws_doubles, int* info, void* stream) {
   if (n < 2 || n > DC_MAXN) return gp_fail("gpcsd_tridiag_eig: order must be in 2..256");
   if (ws_doubles < gpcsd_tridiag_eig_ws_doubles(n, ldx, nmat)) return gp_fail("gpcsd_tridiag_eig: workspace too small");
-  return dc_launch(n, nmat, d, e, ws, ws + (long)nmat * n * ldx, ldx, W, XT, ldx, nullptr, 0, (cudaStream_t)stream);
+  return dc_launch(n, nmat, d, e, ws, ws + (long)nmat * n * ldx, ldx, W, XT, ldx, nullptr, 0, info, (cudaStream_t)stream);
 }
 
 // Full symmetric eigen-decomposition of `nmat` stacked matrices M[nmat][n][ldm] (3 <= n <= 256): QT[nmat][n][ldq] rows =
@@ -859,7 +974,7 @@ struct EighSide {
 };
 
 int gpcsd_eigh_dc(int n, int nmat, const double* M, long ldm, double* QT, long ldq, double* W, double* ws, long ws_doubles,
-                  void* stream) {
+                  int* info, void* stream) {
   if (n < 3 || n > DC_MAXN) return gp_fail("gpcsd_eigh_dc: order must be in 3..256");
   if (ws_doubles < gpcsd_eigh_dc_ws_doubles(n, ldq, nmat)) return gp_fail("gpcsd_eigh_dc: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
@@ -875,7 +990,7 @@ int gpcsd_eigh_dc(int n, int nmat, const double* M, long ldm, double* QT, long l
   double* tau = e + (long)nmat * n;
   if (gpcsd_tridiag(n, nmat, M, ldm, d, e, V, ldq, tau, stream)) return 1;
   if (n < DC_EXTERNAL_MIN) {
-    if (dc_launch(n, nmat, d, e, Qa, Qb, ldq, W, QT, ldq, nullptr, 0, st)) return 1;
+    if (dc_launch(n, nmat, d, e, Qa, Qb, ldq, W, QT, ldq, nullptr, 0, info, st)) return 1;
     return gpcsd_backtransform(n, nmat, V, ldq, tau, QT, ldq, stream);
   }
   thread_local EighSide side;
@@ -895,7 +1010,7 @@ int gpcsd_eigh_dc(int n, int nmat, const double* M, long ldm, double* QT, long l
   if (gpcsd_backtransform(n, nmat, V, ldq, tau, R, ldq, side.stream)) return 1;
   GP_CUDA(cudaEventRecord(side.join, side.stream));
   // main stream: divide and conquer up to the top-level coefficients, then the two GEMMs
-  if (dc_launch(n, nmat, d, e, Qa, Qb, ldq, W, nullptr, ldq, Cm, ldq, st)) return 1;
+  if (dc_launch(n, nmat, d, e, Qa, Qb, ldq, W, nullptr, ldq, Cm, ldq, info, st)) return 1;
   const double* Qbelow = (dc::num_levels(n) & 1) ? Qa : Qb;
   if (gpcsd_dgemm(0, n, n, n, Cm, ldq, mstride, Qbelow, ldq, mstride, T1, ldq, mstride, nmat, stream)) return 1;
   GP_CUDA(cudaStreamWaitEvent(st, side.join, 0));

@@ -189,7 +189,11 @@ def eigh(K):
     if 3 <= n <= 256:
         nws = L.query("gpcsd_eigh_dc_ws_doubles", n, ld, 1)
         ws = torch.empty(nws, dtype=F64, device="cuda")
-        L.call("gpcsd_eigh_dc", n, 1, Kd.data_ptr(), ld, QT.data_ptr(), ld, W.data_ptr(), ws.data_ptr(), nws, _stream())
+        info = torch.zeros(1, dtype=torch.int32, device="cuda")
+        L.call("gpcsd_eigh_dc", n, 1, Kd.data_ptr(), ld, QT.data_ptr(), ld, W.data_ptr(), ws.data_ptr(), nws, info.data_ptr(),
+               _stream())
+        if int(info.item()) != 0:
+            raise np.linalg.LinAlgError("Eigenvalues did not converge")
         return W.cpu().numpy(), QT[:, :n].cpu().numpy().T.copy()
     nws = L.query("gpcsd_eigh_ws_doubles", n, ld)
     ws = torch.zeros(max(nws, 1), dtype=F64, device="cuda")

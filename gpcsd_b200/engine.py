@@ -315,8 +315,8 @@ class KronEngine:
         """Eigen-factors of one symmetric matrix (eigenvectors as rows, eigenvalues ascending): the in-house cluster
         solver up to order 256, cuSOLVER syevd above."""
         if 3 <= n <= self.DC_EIGH_MAX:
-            QTs, Ws = self._eigh_dc(K, n, ld, 1, tag, QT=QT, W=W)
-            return QTs[0], Ws[0], self._zero_info()
+            QTs, Ws, info = self._eigh_dc(K, n, ld, 1, tag, QT=QT, W=W)
+            return QTs[0], Ws[0], info
         QT = self._buf("QT_" + tag, n, ld) if QT is None else QT
         W = self._buf("W_" + tag, n) if W is None else W
         nws = L.query("gpcsd_eigh_ws_doubles", n, ld)
@@ -326,11 +326,6 @@ class KronEngine:
                    self._stream())
         return QT, W, info
 
-    def _zero_info(self):
-        if getattr(self, "_info0", None) is None:
-            self._info0 = torch.zeros(1, dtype=torch.int32, device=self.device)
-        return self._info0
-
     def _eigh_dc(self, stack, n, ld, nmat, tag, QT=None, W=None):
         """`nmat` stacked symmetric matrices [nmat][n][ld] -> (QT [nmat][n][ld] rows = eigenvectors, W [nmat][n] ascending)
         in one launch sequence of the cluster solver (one 8-CTA cluster per matrix); the input is left untouched."""
@@ -338,18 +333,20 @@ class KronEngine:
         W = self._buf("Wdc_" + tag, nmat, n) if W is None else W.view(nmat, n)
         nws = L.query("gpcsd_eigh_dc_ws_doubles", n, ld, nmat)
         ws = self._buf("eigdcws_" + tag, nws)
-        self._call("gpcsd_eigh_dc", n, nmat, self._p(stack), ld, self._p(QT), ld, self._p(W), self._p(ws), nws, self._stream())
+        info = self._buf("infodc_" + tag, nmat, dtype=torch.int32)
+        self._call("gpcsd_eigh_dc", n, nmat, self._p(stack), ld, self._p(QT), ld, self._p(W), self._p(ws), nws, info.data_ptr(),
+                   self._stream())
         if n >= 97:
             self.n_launches += 3      # H^T formation (2 kernels) + one more GEMM on the large-order path
-        return QT, W
+        return QT, W, info
 
     def _eigh_pair(self, S, A, m, ld, tag, side):
         """Eigen-factors of two independent symmetric matrices of order m (leading dimension ld).  Order <= 256: one
         batched call of the cluster solver (S and A must then be the two slabs of one [2][m][ld] stack); larger: two
         syevd on two streams."""
         if 3 <= m <= self.DC_EIGH_MAX and A.data_ptr() == S.data_ptr() + 8 * m * ld:
-            QT, W = self._eigh_dc(S, m, ld, 2, tag)
-            return QT[0], W[0], QT[1], W[1], [self._zero_info()]
+            QT, W, info = self._eigh_dc(S, m, ld, 2, tag)
+            return QT[0], W[0], QT[1], W[1], [info]
         main = torch.cuda.current_stream(self.device)
         ready = torch.cuda.Event()
         ready.record(main)
@@ -402,11 +399,11 @@ class KronEngine:
             stack = self._buf("cs_stack", 2, m, lds)
             self._call("gpcsd_centro_split", nt, self._p(Kt), ldt, self._p(stack), lds, self._p(stack, m * lds), lds,
                        self._stream())
-            U, Wb = self._eigh_dc(stack, m, lds, 2, "t")
+            U, Wb, info = self._eigh_dc(stack, m, lds, 2, "t")
             QT, W = self._buf("QT_t", nt, ldt), self._buf("W_t", nt)
             self._call("gpcsd_centro_assemble", nt, self._p(U), lds, self._p(Wb), self._p(U, m * lds), lds,
                        self._p(Wb, m), self._p(QT), ldt, self._p(W), self._stream())
-            return QT, W, [self._zero_info()]
+            return QT, W, [info]
         S, A = self._buf("cs_S", ms, lds), self._buf("cs_A", m, lda)
         self._call("gpcsd_centro_split", nt, self._p(Kt), ldt, self._p(S), lds, self._p(A), lda, self._stream())
         main = torch.cuda.current_stream(self.device)

@@ -100,10 +100,12 @@ int gpcsd_eigh_batched(int n, int batch, double* A, long ld, double* W, void* ws
 
 /* In-house symmetric eigensolver for orders 3..256 (gpcsd_eig.cu), one 8-CTA thread-block cluster per matrix, batched:
  * replaces np.linalg.eigh of comp_eig_D (utility_functions.py:58-59) where cuSOLVER syevd is latency-bound.
- * M[nmat][n][ldm] symmetric (not modified) -> QT[nmat][n][ldq] (rows = eigenvectors), W[nmat][n] ascending. */
+ * M[nmat][n][ldm] symmetric (not modified) -> QT[nmat][n][ldq] (rows = eigenvectors), W[nmat][n] ascending.
+ * info[nmat] (device int array, may be NULL): 0 = ok, 1 = non-finite input (outputs are NaN; numpy.linalg.eigh raises
+ * LinAlgError in that case, the Python layer does the same). */
 long gpcsd_eigh_dc_ws_doubles(int n, long ldq, int nmat);
 int gpcsd_eigh_dc(int n, int nmat, const double* M, long ldm, double* QT, long ldq, double* W, double* ws, long ws_doubles,
-                  void* stream);
+                  int* info, void* stream);
 
 /* Its three stages, exported for tests and reuse:
  * (1) Householder tridiagonalisation M = H T H^T (matrix resident in distributed shared memory): d[nmat][n], e[nmat][n]
@@ -115,7 +117,7 @@ int gpcsd_tridiag(int n, int nmat, const double* M, long ldm, double* d, double*
                   void* stream);
 long gpcsd_tridiag_eig_ws_doubles(int n, long ldx, int nmat);
 int gpcsd_tridiag_eig(int n, int nmat, const double* d, const double* e, double* W, double* XT, long ldx, double* ws,
-                      long ws_doubles, void* stream);
+                      long ws_doubles, int* info, void* stream);
 int gpcsd_backtransform(int n, int nmat, const double* V, long ldv, const double* tau, double* XT, long ldx, void* stream);
 
 /* Exact centrosymmetric split of a symmetric Toeplitz (more generally J K J = K) matrix -- every stationary

@@ -30,7 +30,7 @@ extern "C" long dc_host_eig(int n, const double* d_in, const double* e_in, doubl
   }
   std::vector<double> Qa((size_t)n * n, 0.0), Qb((size_t)n * n, 0.0);
   for (int i = 0; i < n; ++i) Qa[(size_t)i * n + i] = 1.0;
-  std::vector<double> dnew(n), z(n), dl(n), w(n), rot_c(n), rot_s(n), mu(n), zh(n);
+  std::vector<double> dnew(n), z(n), dS(n), zS(n), dl(n), w(n), rot_c(n), rot_s(n), mu(n), zh(n);
   std::vector<int> srt(n), row(n), rot_p(n), rot_n(n), org(n);
   long kept = 0;
   const int levels = num_levels(n);
@@ -55,6 +55,8 @@ extern "C" long dc_host_eig(int n, const double* d_in, const double* e_in, doubl
         int r = 0;
         for (int h = a; h < b; ++h) r += (d[h] < d[g]) || (d[h] == d[g] && h < g);
         srt[a + r] = g;
+        dS[a + r] = d[g];
+        zS[a + r] = z[g];
       }
       int k, nrot;
       double dmax = 0.0, zmax = 0.0;
@@ -62,7 +64,7 @@ extern "C" long dc_host_eig(int n, const double* d_in, const double* e_in, doubl
         dmax = std::max(dmax, std::fabs(d[g]));
         zmax = std::max(zmax, std::fabs(z[g]));
       }
-      deflate(a, m, srt.data(), d.data(), z.data(), rho, dmax, zmax, row.data(), dl.data(), w.data(), rot_p.data(), rot_n.data(),
+      deflate(a, m, srt.data(), dS.data(), zS.data(), rho, dmax, zmax, row.data(), dl.data(), w.data(), rot_p.data(), rot_n.data(),
               rot_c.data(), rot_s.data(), k, nrot);
       for (int q = 0; q < nrot; ++q) {
         double* xp = &Qa[(size_t)rot_p[a + q] * n];
@@ -83,7 +85,7 @@ extern "C" long dc_host_eig(int n, const double* d_in, const double* e_in, doubl
         for (int col = a; col < b; ++col) {
           double acc = 0.0;
           for (int j = 0; j < k; ++j)
-            acc += zh[a + j] / delta_ji(&dl[a], j, org[a + i], mu[a + i]) * Qa[(size_t)row[a + j] * n + col];
+            acc += zh[a + j] * rcp(delta_ji(&dl[a], j, org[a + i], mu[a + i])) * Qa[(size_t)row[a + j] * n + col];
           Qb[(size_t)(a + i) * n + col] = acc * inv;
         }
       }

@@ -403,7 +403,7 @@ def test_tridiag_eig_divide_and_conquer(cuda_lib, n):
     nws = L.query("gpcsd_tridiag_eig_ws_doubles", n, ld, nmat)
     ws = torch.full((nws,), float("nan"), dtype=F64, device="cuda")      # the workspace may hold anything
     L.call("gpcsd_tridiag_eig", n, nmat, d.data_ptr(), e.data_ptr(), W.data_ptr(), XT.data_ptr(), ld, ws.data_ptr(), nws,
-           _stream())
+           0, _stream())
     torch.cuda.synchronize()
     for b, (dh, eh) in enumerate(cases):
         T = np.diag(dh) + np.diag(eh, 1) + np.diag(eh, -1)
@@ -443,7 +443,7 @@ def test_eigh_dc_full(cuda_lib, n, nmat):
     W = torch.zeros((nmat, n), dtype=F64, device="cuda")
     nws = L.query("gpcsd_eigh_dc_ws_doubles", n, ld, nmat)
     ws = torch.full((nws,), float("nan"), dtype=F64, device="cuda")      # the workspace may hold anything
-    L.call("gpcsd_eigh_dc", n, nmat, stack.data_ptr(), ld, QT.data_ptr(), ld, W.data_ptr(), ws.data_ptr(), nws, _stream())
+    L.call("gpcsd_eigh_dc", n, nmat, stack.data_ptr(), ld, QT.data_ptr(), ld, W.data_ptr(), ws.data_ptr(), nws, 0, _stream())
     torch.cuda.synchronize()
     assert torch.equal(stack, keep)
     for b in range(nmat):
@@ -453,3 +453,30 @@ def test_eigh_dc_full(cuda_lib, n, nmat):
         assert np.max(np.abs(Wh - lam)) <= 1e-13 * sc * max(1, n / 16)
         assert np.max(np.abs(Q.T @ Q - np.eye(n))) <= 1e-12
         assert np.max(np.abs(Ms[b] @ Q - Q * Wh)) <= 1e-13 * sc * n
+
+
+@pytest.mark.parametrize("n", [24, 30, 125, 250])
+def test_eigh_dc_nonfinite_input_is_reported(cuda_lib, n):
+    """NaN/inf in the matrix (the reference lets them flow, numpy.linalg.eigh then raises): info = 1, NaN outputs, no fault;
+    the healthy matrix of the same batch is still solved."""
+    from gpcsd_b200 import _lib as L
+    ld = _ld(n)
+    t = np.arange(n) * 0.5
+    K = np.exp(-0.5 * (t[:, None] - t[None, :]) ** 2 / 9.0)
+    stack = torch.zeros((3, n, ld), dtype=F64, device="cuda")
+    stack[:, :, :n] = torch.from_numpy(K).cuda()
+    stack[0, n // 2, n // 3] = float("nan")
+    stack[0, n // 3, n // 2] = float("nan")
+    stack[2, 1, 1] = float("inf")
+    QT = torch.zeros((3, n, ld), dtype=F64, device="cuda")
+    W = torch.zeros((3, n), dtype=F64, device="cuda")
+    info = torch.full((3,), -1, dtype=torch.int32, device="cuda")
+    nws = L.query("gpcsd_eigh_dc_ws_doubles", n, ld, 3)
+    ws = torch.zeros(nws, dtype=F64, device="cuda")
+    L.call("gpcsd_eigh_dc", n, 3, stack.data_ptr(), ld, QT.data_ptr(), ld, W.data_ptr(), ws.data_ptr(), nws, info.data_ptr(),
+           _stream())
+    torch.cuda.synchronize()
+    assert info.cpu().tolist() == [1, 0, 1]
+    assert torch.isnan(W[0]).all() and torch.isnan(W[2]).all()
+    lam = np.linalg.eigvalsh(K)
+    assert np.max(np.abs(W[1].cpu().numpy() - lam)) <= 1e-13 * lam.max() * max(1, n / 16)
