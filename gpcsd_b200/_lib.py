@@ -30,6 +30,7 @@ SIGNATURES = {
                             c_int, _P]),
     "gpcsd_project_quad_ws_doubles": (c_long, [c_int, c_int, c_int]),
     "gpcsd_project_quad": (c_int, [c_int, c_int, c_int, _P, c_long, _P, c_long, _P, c_long, _P, _P, _P, _P]),
+    "gpcsd_project_quad_strided": (c_int, [c_int, c_int, c_int, _P, c_long, _P, c_long, c_long, _P, c_long, _P, _P, _P, _P]),
     "gpcsd_wsyrk_ws_doubles": (c_long, [c_int, c_int, c_int]),
     "gpcsd_wsyrk": (c_int, [c_int, c_int, c_int, _P, c_long, c_long, _P, _P, c_long, _P, _P]),
     "gpcsd_eigh_ws_doubles": (c_long, [c_int, c_long]),
@@ -44,6 +45,7 @@ SIGNATURES = {
     "gpcsd_eigh_dc": (c_int, [c_int, c_int, _P, c_long, _P, c_long, _P, _P, c_long, _P, _P]),
     "gpcsd_centro_split": (c_int, [c_int, _P, c_long, _P, c_long, _P, c_long, _P]),
     "gpcsd_centro_assemble": (c_int, [c_int, _P, c_long, _P, _P, c_long, _P, _P, c_long, _P, _P]),
+    "gpcsd_centro_fold": (c_int, [c_int, c_int, c_long, _P, _P, _P]),
     "gpcsd_pairsym_split": (c_int, [c_int, _P, c_long, _P, _P, _P, c_long, _P, c_long, _P]),
     "gpcsd_pairsym_assemble": (c_int, [c_int, _P, _P, _P, c_long, _P, _P, c_long, _P, _P, c_long, _P, _P]),
     "gpcsd_eig_D": (c_int, [c_int, c_int, _P, _P, _P, c_int, _P, c_long, _P, _P, _P, _P, _P, _P]),

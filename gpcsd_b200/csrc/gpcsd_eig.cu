@@ -210,7 +210,9 @@ __global__ void __cluster_dims__(TRD_CLUSTER, 1, 1) __launch_bounds__(32 * TRD_W
     EIG_PROF(0)
     const int pb = k & 1;               // exchange k: p of column k-1 and row k
     const bool build = k < n - 2;
-    if (last_row < k) break;
+    // (a warp whose last row is exactly k has nothing left to send either -- nobody waits for it, so it must not wait on
+    //  barriers that may run ahead of it; the owner of row n-2 stays for the final update, after which nothing runs ahead)
+    if (last_row < k || (last_row == k && k < n - 2)) break;
     if (armer && build)                 // arm exchange k+1: p of column k (rows i > k) and row k+1 (entries j >= k+1)
       mbar_expect_tx(&S.bar[pb ^ 1], 8u * (uint32_t)(n - k - 1) +
                                          ((k + 1 < n - 2) ? 8u * (uint32_t)(((n + 1) & ~1) - ((k + 1) & ~1)) : 0u));

@@ -382,6 +382,22 @@ int gpcsd_project_quad(int nx, int nt, int ntrials, const double* QtT, long ldq,
   return 0;
 }
 
+// Same contraction for a sub-block of the temporal eigenbasis (centrosymmetric fold): order m, operands are views into the
+// parent [nx][nt][ldn] arrays whose per-electrode stride is bstride.
+int gpcsd_project_quad_strided(int nx, int m, int ntrials, const double* AT, long lda, const double* Z, long ldn, long bstride,
+                               const double* rD, long ldrd, double* Bout, double* partials, double* out2, void* stream) {
+  GemmArgs p{};
+  p.A = AT; p.B = Z; p.C = Bout;
+  p.lda = lda; p.ldb = ldn; p.ldc = ldn;
+  p.sA = 0; p.sB = bstride; p.sC = bstride;
+  p.M = m; p.N = ntrials; p.K = m;
+  p.rD = rD; p.ldrd = ldrd; p.partials = partials;
+  if (int e = dispatch_gemm<EPI_QUAD>(p, 0, nx, (cudaStream_t)stream)) return e;
+  reduce_pairs_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partials, project_quad_ctas(nx, m, ntrials), out2);
+  GP_CUDA(cudaGetLastError());
+  return 0;
+}
+
 long gpcsd_wsyrk_ws_doubles(int M, int nseg, int seglen) {
   int bmn, t1, kbps, nsplit;
   long total;

@@ -367,6 +367,30 @@ __global__ void centro_assemble_kernel(int n, const double* __restrict__ UsT, lo
   if (c == 0) W[a] = (a < ms) ? Ws[a] : Wa[a - ms];
 }
 
+// Centrosymmetric fold of the time axis of a trial block X[nblk][n][rowlen] (rowlen even, trials contiguous):
+//   Xf[b][j]      = (X[b][j] + X[b][n-1-j]) / sqrt 2   j < n/2        (for odd n: Xf[b][n/2] = X[b][n/2])
+//   Xf[b][ms + j] = (X[b][j] - X[b][n-1-j]) / sqrt 2   j < n/2,  ms = n/2 + n%2
+// With the eigenvectors of a centrosymmetric Kt stored as [symmetric block; skew block] (centro_assemble_kernel) this turns
+// Qt^T X_b into two independent products of order ~n/2 (Us^T Xf[b][:ms], Ua^T Xf[b][ms:]): half the flops of the projection.
+__global__ void centro_fold_kernel(int n, long rowlen2, long total, const double2* __restrict__ X, double2* __restrict__ Xf) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;        // over [nblk][ms][rowlen/2]
+  if (idx >= total) return;
+  const int m = n / 2, ms = m + (n & 1);
+  const long c = idx % rowlen2, bj = idx / rowlen2;
+  const int j = (int)(bj % ms);
+  const long b = bj / ms;
+  const double2* xb = X + b * n * rowlen2;
+  double2* fb = Xf + b * n * rowlen2;
+  const double h = 0.70710678118654752;
+  if (j < m) {
+    const double2 u = xb[(long)j * rowlen2 + c], v = xb[(long)(n - 1 - j) * rowlen2 + c];
+    fb[(long)j * rowlen2 + c] = make_double2(h * (u.x + v.x), h * (u.y + v.y));
+    fb[(long)(ms + j) * rowlen2 + c] = make_double2(h * (u.x - v.x), h * (u.y - v.y));
+  } else {
+    fb[(long)j * rowlen2 + c] = xb[(long)j * rowlen2 + c];
+  }
+}
+
 __global__ void copy_matrix_kernel(int n, const double* __restrict__ in, long ldi, double* __restrict__ out, long ldo) {
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long)n * n) return;
@@ -625,6 +649,16 @@ int gpcsd_centro_split(int n, const double* K, long ldk, double* S, long lds, do
 int gpcsd_centro_assemble(int n, const double* UsT, long lds, const double* Ws, const double* UaT, long lda,
                           const double* Wa, double* QT, long ldq, double* W, void* stream) {
   centro_assemble_kernel<<<GRID1D((long)n * n), 0, (cudaStream_t)stream>>>(n, UsT, lds, Ws, UaT, lda, Wa, QT, ldq, W);
+  GP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int gpcsd_centro_fold(int nblk, int n, long rowlen, const double* X, double* Xf, void* stream) {
+  if (rowlen & 1L) return gp_fail("centro_fold: row length must be even");
+  if (((uintptr_t)X | (uintptr_t)Xf) & 15) return gp_fail("centro_fold: pointers must be 16-byte aligned");
+  if (nblk <= 0 || n <= 0 || rowlen <= 0) return 0;
+  const long ms = n / 2 + (n & 1), total = (long)nblk * ms * (rowlen / 2);
+  centro_fold_kernel<<<GRID1D(total), 0, (cudaStream_t)stream>>>(n, rowlen / 2, total, (const double2*)X, (double2*)Xf);
   GP_CUDA(cudaGetLastError());
   return 0;
 }

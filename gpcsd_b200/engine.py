@@ -384,12 +384,22 @@ class KronEngine:
             self._sides = [torch.cuda.Stream(device=self.device) for _ in range(3)]
         return self._sides
 
+    def _t_split(self):
+        """Uniform time grid: Kt is centrosymmetric, its eigenproblem splits into a symmetric and a skew half and -- in the
+        folded time basis (gpcsd_centro_fold) -- Qt is block diagonal."""
+        return bool(self.t_uniform and self.nt >= 32)
+
+    def _t_fold(self):
+        """Whether the trial data are moved to the folded time basis (same condition as the split)."""
+        return self._t_split()
+
     def _eigh_temporal(self, Kt):
         """Eigen-factors of Kt.  On a uniform time grid Kt is symmetric Toeplitz, hence centrosymmetric, and the
         order-nt problem splits exactly into two independent problems of order ~nt/2 (one batched call of the cluster
         solver up to nt = 512, two concurrent syevd above); otherwise one solve of order nt.  The eigenvalues come back unsorted in the split case (nothing downstream needs an order)."""
         nt, ldt = self.nt, self.ldt
-        if not (self.t_uniform and nt >= 32):
+        self._t_blocks = None
+        if not self._t_split():
             QT, W, info = self._eigh(Kt, nt, ldt, "t")
             return QT, W, [info]
         m, ms = nt // 2, nt // 2 + (nt & 1)
@@ -403,6 +413,7 @@ class KronEngine:
             QT, W = self._buf("QT_t", nt, ldt), self._buf("W_t", nt)
             self._call("gpcsd_centro_assemble", nt, self._p(U), lds, self._p(Wb), self._p(U, m * lds), lds,
                        self._p(Wb, m), self._p(QT), ldt, self._p(W), self._stream())
+            self._t_blocks = (U[0], lds, U[1], lds)
             return QT, W, [info]
         S, A = self._buf("cs_S", ms, lds), self._buf("cs_A", m, lda)
         self._call("gpcsd_centro_split", nt, self._p(Kt), ldt, self._p(S), lds, self._p(A), lda, self._stream())
@@ -420,6 +431,7 @@ class KronEngine:
         QT, W = self._buf("QT_t", nt, ldt), self._buf("W_t", nt)
         self._call("gpcsd_centro_assemble", nt, self._p(UsT), lds, self._p(Ws), self._p(UaT), lda, self._p(Wa),
                    self._p(QT), ldt, self._p(W), self._stream())
+        self._t_blocks = (UsT, lds, UaT, lda)
         return QT, W, [info_s, info_a]
 
     def _factorize(self, hp, jitter, want_grad):
@@ -441,6 +453,12 @@ class KronEngine:
                 st["Z"] = self._buf("Z", self.nx, self.nt, self.ldn)
                 self.gemm(0, self.nx, self.nt * self.ldn, self.nx, st["QsT"], self.ldx, 0, self.Y, self.nt * self.ldn, 0,
                           st["Z"], self.nt * self.ldn, 0)
+                if self._t_fold() and self.ntrials > 0:
+                    # folded time basis: the temporal projection and the temporal SYRK then run on two blocks of order
+                    # ~nt/2 (half the flops); also hidden underneath the temporal eigensolve
+                    Zf = self._buf("Zf", self.nx, self.nt, self.ldn)
+                    self._call("gpcsd_centro_fold", self.nx, self.nt, self.ldn, self._p(st["Z"]), self._p(Zf), self._stream())
+                    st["Z"] = Zf
             s_done = torch.cuda.Event()
             s_done.record(side)
         st["Kt"] = self._temporal_cov(hp)
@@ -468,9 +486,22 @@ class KronEngine:
         nx, nt, ldn = self.nx, self.nt, self.ldn
         Z = st["Z"]                                  # computed on the spatial side stream by _factorize
         Bm = self._buf("Bm", nx, nt, ldn)
-        nws = L.query("gpcsd_project_quad_ws_doubles", nx, nt, max(self.ntrials, 1))
+        # (the block calls of the folded basis may take another kernel path than order nt: size for all three orders)
+        nws = max(L.query("gpcsd_project_quad_ws_doubles", nx, o, max(self.ntrials, 1)) for o in {nt, nt // 2, nt - nt // 2})
         part = self._buf("quad_part", nws)
-        if self.ntrials > 0:
+        st["sums_b"] = None
+        if self.ntrials > 0 and self._t_blocks is not None and self._t_fold():
+            # Z is in the folded time basis: Qt^T Z_i = [Us^T Zf_i[:ms]; Ua^T Zf_i[ms:]]
+            UsT, lds, UaT, lda = self._t_blocks
+            m = nt // 2
+            ms = nt - m
+            st["sums_b"] = self._buf("res_b", 2)
+            self._call("gpcsd_project_quad_strided", nx, ms, self.ntrials, self._p(UsT), lds, self._p(Z), ldn, nt * ldn,
+                       self._p(st["rD"]), self.ldt, self._p(Bm), self._p(part), self._p(st["sums"], 0), self._stream())
+            self._call("gpcsd_project_quad_strided", nx, m, self.ntrials, self._p(UaT), lda, self._p(Z, ms * ldn), ldn,
+                       nt * ldn, self._p(st["rD"], ms), self.ldt, self._p(Bm, ms * ldn), self._p(part),
+                       self._p(st["sums_b"], 0), self._stream())
+        elif self.ntrials > 0:
             self._call("gpcsd_project_quad", nx, nt, self.ntrials, self._p(st["QtT"]), self.ldt, self._p(Z), ldn,
                        self._p(st["rD"]), self.ldt, self._p(Bm), self._p(part), self._p(st["sums"], 0), self._stream())
         else:
@@ -488,6 +519,8 @@ class KronEngine:
         st = self._factorize(hp, jitter=True, want_grad=False)
         self._project(st)
         res = st["sums"][:4].cpu().numpy()
+        if st["sums_b"] is not None:
+            res[:2] += st["sums_b"].cpu().numpy()
         self._check_info(st)
         f = self.shard.det_fraction()
         part = np.array([-0.5 * self.ntrials_total * f * res[2] - 0.5 * res[0]])
@@ -507,12 +540,24 @@ class KronEngine:
         # --- segment-weighted SYRKs over the trial batch
         Mt = self._buf("Mt", nt, self.ldt)
         Ms = self._buf("Ms", nx, self.ldx)
-        wst = self._buf("ws_syrk_t", max(L.query("gpcsd_wsyrk_ws_doubles", nt, nx, max(N, 1)), 2))
+        wst = self._buf("ws_syrk_t", max(max(L.query("gpcsd_wsyrk_ws_doubles", o, nx, max(N, 1))
+                                             for o in {nt, nt // 2, nt - nt // 2}), 2))
         wss = self._buf("ws_syrk_s", max(L.query("gpcsd_wsyrk_ws_doubles", nx, nt, max(N, 1)), 2))
         Ns = None
         if N > 0:
-            self._call("gpcsd_wsyrk", nt, nx, N, self._p(Bm), ldn, nt * ldn, self._p(st["ls"]), self._p(Mt), self.ldt,
-                       self._p(wst), stream())
+            if self._t_blocks is not None and self._t_fold():
+                # every dKt/dtheta is centrosymmetric too, i.e. block diagonal in the folded basis: only the two diagonal
+                # blocks of Mt enter <dL/dKt, dKt/dtheta> (the off-diagonal blocks of the buffer stay zero)
+                m = nt // 2
+                ms = nt - m
+                Mt.zero_()
+                self._call("gpcsd_wsyrk", ms, nx, N, self._p(Bm), ldn, nt * ldn, self._p(st["ls"]), self._p(Mt), self.ldt,
+                           self._p(wst), stream())
+                self._call("gpcsd_wsyrk", m, nx, N, self._p(Bm, ms * ldn), ldn, nt * ldn, self._p(st["ls"]),
+                           self._p(Mt, ms * self.ldt + ms), self.ldt, self._p(wst), stream())
+            else:
+                self._call("gpcsd_wsyrk", nt, nx, N, self._p(Bm), ldn, nt * ldn, self._p(st["ls"]), self._p(Mt), self.ldt,
+                           self._p(wst), stream())
             self._call("gpcsd_wsyrk", nx, nt, N, self._p(Bm), nt * ldn, ldn, self._p(st["lt"]), self._p(Ms), self.ldx,
                        self._p(wss), stream())
         else:
@@ -560,9 +605,13 @@ class KronEngine:
         pieces = [res[: 8 + 2 * ntc]]
         if vec:
             pieces += [st["rowC"], torch.diagonal(Ns[:, :nx])]
+        if st["sums_b"] is not None:
+            pieces.append(st["sums_b"])
         flat = torch.cat([p.reshape(-1) for p in pieces]).cpu().numpy()
         self._check_info(st)
         quad, bsq, slogD, srD = flat[0], flat[1], flat[2], flat[3]
+        if st["sums_b"] is not None:
+            quad, bsq = quad + flat[-2], bsq + flat[-1]
         ll = -0.5 * ntot * f * slogD - 0.5 * quad
         g = [2.0 * flat[4]] + [flat[5 + k] for k in range(len(hp.ells))] + list(flat[8: 8 + 2 * ntc])
         if vec:

@@ -66,6 +66,12 @@ int gpcsd_project_quad(int nx, int nt, int ntrials,
                        const double* rD, long ldrd,
                        double* Bout, double* partials, double* out2, void* stream);
 
+/* The same contraction restricted to one block of a block-diagonal temporal eigenbasis (see gpcsd_centro_fold): AT is the
+ * m x m transposed eigenvector block, Z / Bout / rD point at the block's first time row / eigen-index inside the parent
+ * [nx][nt][ldn] / [nx][ldrd] arrays, bstride = nt*ldn.  Workspace: gpcsd_project_quad_ws_doubles(nx, m, ntrials). */
+int gpcsd_project_quad_strided(int nx, int m, int ntrials, const double* AT, long lda, const double* Z, long ldn, long bstride,
+                               const double* rD, long ldrd, double* Bout, double* partials, double* out2, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Segment-weighted symmetric rank-k update (gradient of the quadratic form; replaces the autograd
  * tape of gpcsd1d.py:211 / gpcsd2d.py:250 over the trial loop):
@@ -128,6 +134,12 @@ int gpcsd_backtransform(int n, int nmat, const double* V, long ldv, const double
 int gpcsd_centro_split(int n, const double* K, long ldk, double* S, long lds, double* A, long lda, void* stream);
 int gpcsd_centro_assemble(int n, const double* UsT, long lds, const double* Ws, const double* UaT, long lda,
                           const double* Wa, double* QT, long ldq, double* W, void* stream);
+
+/* Centrosymmetric fold of the time axis of a trial block X[nblk][n][rowlen] (trials contiguous, rowlen even):
+ * Xf[b][j] = (X[b][j] + X[b][n-1-j])/sqrt2, Xf[b][ms+j] = (X[b][j] - X[b][n-1-j])/sqrt2 (j < n/2; middle row kept for odd n).
+ * In this basis the eigenvector matrix assembled by gpcsd_centro_assemble is block diagonal (Us^T, Ua^T), so the trial loop
+ * of loglik (gpcsd1d.py:124-126) and the temporal SYRK of its gradient cost half the flops. */
+int gpcsd_centro_fold(int nblk, int n, long rowlen, const double* X, double* Xf, void* stream);
 
 /* Same split for any fixed-point-free involution pi with K[pi(i)][pi(j)] == K[i][j] (n even): device int arrays
  * ra[n/2] (representatives) and rb[n/2] = pi(ra).  Used for the spatial factor of geometries that are invariant under the

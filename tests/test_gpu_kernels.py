@@ -480,3 +480,21 @@ def test_eigh_dc_nonfinite_input_is_reported(cuda_lib, n):
     assert torch.isnan(W[0]).all() and torch.isnan(W[2]).all()
     lam = np.linalg.eigvalsh(K)
     assert np.max(np.abs(W[1].cpu().numpy() - lam)) <= 1e-13 * lam.max() * max(1, n / 16)
+
+
+@pytest.mark.parametrize("n,nblk,rowlen", [(6, 2, 8), (7, 3, 16), (50, 4, 24), (501, 2, 40)])
+def test_centro_fold(cuda_lib, n, nblk, rowlen):
+    """Folded time basis: sums / differences of mirrored time rows, middle row kept for odd n."""
+    from gpcsd_b200 import _lib as L
+    rng = np.random.default_rng(n)
+    X = rng.standard_normal((nblk, n, rowlen))
+    Xd = torch.from_numpy(X).cuda()
+    Xf = torch.full_like(Xd, 7.0)
+    L.call("gpcsd_centro_fold", nblk, n, rowlen, Xd.data_ptr(), Xf.data_ptr(), _stream())
+    m, ms = n // 2, n - n // 2
+    ref = np.empty_like(X)
+    ref[:, :m] = (X[:, :m] + X[:, ::-1][:, :m]) / np.sqrt(2)
+    if n & 1:
+        ref[:, m] = X[:, m]
+    ref[:, ms:] = (X[:, :m] - X[:, ::-1][:, :m]) / np.sqrt(2)
+    assert relerr(Xf.cpu().numpy(), ref) < 1e-15
