@@ -300,6 +300,7 @@ def run_gpu(args):
         return ms
 
     last = {}
+    isolate = [False]
 
     # The two probes are independent models: evaluate them concurrently, one host thread + CUDA stream each,
     # so one probe's latency-bound cuSOLVER syevd overlaps the other's DMMA GEMMs (--serial disables this).
@@ -323,6 +324,8 @@ def run_gpu(args):
             for s in range(first, first + nsteps):
                 for p in range(len(models)):
                     last[p] = eval_probe(p, s, upload)
+                    if isolate[0]:
+                        torch.cuda.synchronize()           # per-kernel timing pass: nothing of the next evaluation overlaps
             return
 
         def worker(p):
@@ -360,6 +363,19 @@ def run_gpu(args):
         with torch.cuda.stream(streams[p]):
             m._get_engine()                                 # upload once
     torch.cuda.synchronize()
+
+    def serial_once(first, upload):
+        """First use of every code path strictly serial: CUDA loads kernels lazily on their first launch and workspaces,
+        streams and events are created on first use -- all of which may need the device to drain, which deadlocks if the
+        other probe's thread already sits in a blocking NCCL all-reduce whose peer rank does the same thing the other way
+        round.  After this step the concurrent phases launch nothing new."""
+        prev = args.serial
+        args.serial = True
+        run_steps(first, 1, upload)
+        torch.cuda.synchronize()
+        args.serial = prev
+
+    serial_once(0, False)
     timed_steps(W, 0, False)
     if args.profile_step:
         # one steady-state SERIAL step between cudaProfilerStart/Stop for `ncu --profile-from-start off`
@@ -387,8 +403,11 @@ def run_gpu(args):
     args.serial = True
     timed_steps(2, 0, False)                                # warm the main thread's cuSOLVER handles
     for e in engines:
-        e.timers = {"gpcsd_project_quad": [], "gpcsd_wsyrk": [], "gpcsd_eigh": [], "gpcsd_eigh_dc": [], "gpcsd_dgemm": []}
+        e.timers = {"gpcsd_project_quad": [], "gpcsd_project_quad_strided": [], "gpcsd_wsyrk": [], "gpcsd_eigh": [],
+                    "gpcsd_eigh_dc": [], "gpcsd_dgemm": []}
+    isolate[0] = True
     ms_serial = timed_steps(K, W, False)
+    isolate[0] = False
     clocks = sampler.stop() if rank == 0 else None
     kt = {}
     for name in engines[0].timers:
@@ -398,6 +417,7 @@ def run_gpu(args):
         e.timers = None
     args.serial = not concurrent
     # ---- end-to-end arm
+    serial_once(K + W, True)
     timed_steps(W, K + W, True)
     ms_e2e = timed_steps(K, K + 2 * W, True)
 
@@ -422,6 +442,10 @@ def run_gpu(args):
 
     for m, th in zip(models, thetas):
         m._set_tparams(th[0], False)
+    for to_host in (False, True):                          # first use serial (see serial_once)
+        for p in range(len(models)):
+            predict_probe(p, to_host)
+        torch.cuda.synchronize()
     timed(step_predict(False), 2, 0)
     ms_pred = timed(step_predict(False), KP, 0)
     timed(step_predict(True), 3, 0)                        # lets torch's pinned-host cache reach steady state
@@ -441,8 +465,13 @@ def run_gpu(args):
     P = 6 + NX
     if rank == 0:
         peak = measure_fp64_peak(torch, device)
-        algo_flops = 2.0 * NX * NT * NT * NTRIALS            # projection Qt^T Z_i for all i: SURVEY.md 8d
-        dur_ms = kt["gpcsd_project_quad"][0]
+        # projection Qt^T Z_i for all i.  On the uniform time grid of this workload Qt is block diagonal in
+        # the folded time basis, so the projection is two launches of order NT/2 -- half the flops of the reference's
+        # contraction; the roofline line is per launch of the dominant kernel as executed.
+        folded = kt["gpcsd_project_quad_strided"][1] > 0
+        mblk = NT // 2 if folded else NT
+        algo_flops = 2.0 * NX * mblk * mblk * NTRIALS
+        dur_ms = kt["gpcsd_project_quad_strided" if folded else "gpcsd_project_quad"][0]
         achieved = algo_flops / (dur_ms * 1e-3) * 1e-12 if dur_ms > 0 else None
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
@@ -461,11 +490,11 @@ def run_gpu(args):
                         "d2h_bytes_per_step": NPROBES * (8 + 2 * 2 + 2 * NX) * 8,
                         "api": "GPCSD1D.update_lfp(pinned lfp) + GPCSD1D.obj_fun_and_grad(tparams)"},
                 "gpu_launches": launches,
-                "roofline": {"bound": "tensor", "kernel": "tma_gemm_kernel<NN,EPI_QUAD,NTW=3> (gpcsd_project_quad: persistent TMA+mbarrier DMMA GEMM, 128x96 tiles, fused /D + quadratic form)",
+                "roofline": {"bound": "tensor", "kernel": "tma_gemm_kernel<NN,EPI_QUAD,NTW=3> (gpcsd_project_quad_strided, one of the two half-order blocks of the folded time basis: persistent TMA+mbarrier DMMA GEMM, 128x96 tiles, fused /D + quadratic form)",
                              "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                              "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                              "algorithmic_flops_per_launch": algo_flops, "avg_launch_ms": dur_ms,
-                             "timed_in": "serial pass (value_serial): CUDA events on the launching stream around every launch",
+                             "timed_in": "serial pass (value_serial: one evaluation at a time, device drained in between): CUDA events on the launching stream around every ABI call of the kernel (the span also holds its 1-CTA partial-sum reduction)",
                              "peak_source": "in-run cuBLAS DGEMM 4096^3 best-of-5 (FP64; MEASURED_PEAKS.json has only "
                                             "HBM and bf16); DMMA issue-rate microbenchmark: 37.0 TFLOP/s"},
                 "kernel_ms": {k: {"avg_ms": v[0], "calls": v[1]} for k, v in kt.items()},
@@ -494,6 +523,10 @@ def main():
     ap.add_argument("--serial", action="store_true", help="evaluate the two probes one after the other")
     ap.add_argument("--profile-step", action="store_true", help="run warm-up then ONE step inside cudaProfilerStart/Stop")
     args = ap.parse_args()
+    # watchdog: a hang (e.g. a collective one rank never enters) becomes a stack dump of every thread and a non-zero exit
+    # instead of a silent stall that holds the GPU box until the caller's timeout
+    import faulthandler
+    faulthandler.dump_traceback_later(float(os.environ.get("GPCSD_BENCH_WATCHDOG_S", "900")), exit=True)
     if args.impl == "reference":
         run_reference(args, int(os.environ.get("RANK", "0")))
         return

@@ -22,6 +22,9 @@
 #include <cooperative_groups.h>
 #include <stddef.h>
 
+#include <mutex>
+#include <unordered_map>
+
 #include "common.h"
 #include "dc_core.h"
 #include "dmma_gemm.cuh"
@@ -965,7 +968,7 @@ int gpcsd_tridiag_eig(int n, int nmat, const double* d, const double* e, double*
 //
 // Orders above DC_EXTERNAL_MIN take the long tail off the critical path: while the divide-and-conquer kernel runs, a side
 // stream forms H^T explicitly (the reflectors applied to the identity); the top-level merge and the back-transformation
-// then are two full-GPU DMMA GEMMs,  QT = (C * Q_below) * H^T.  The side stream and its events are per host thread.
+// then are two full-GPU DMMA GEMMs,  QT = (C * Q_below) * H^T.  The side stream and its events are per caller stream.
 constexpr int DC_EXTERNAL_MIN = 97;
 
 long gpcsd_eigh_dc_ws_doubles(int n, long ldq, int nmat) { return (long)nmat * (6L * n * ldq + 3L * n); }
@@ -995,11 +998,19 @@ int gpcsd_eigh_dc(int n, int nmat, const double* M, long ldm, double* QT, long l
     if (dc_launch(n, nmat, d, e, Qa, Qb, ldq, W, QT, ldq, nullptr, 0, info, st)) return 1;
     return gpcsd_backtransform(n, nmat, V, ldq, tau, QT, ldq, stream);
   }
-  thread_local EighSide side;
-  if (!side.stream) {
-    GP_CUDA(cudaStreamCreateWithFlags(&side.stream, cudaStreamNonBlocking));
-    GP_CUDA(cudaEventCreateWithFlags(&side.fork, cudaEventDisableTiming));
-    GP_CUDA(cudaEventCreateWithFlags(&side.join, cudaEventDisableTiming));
+  // one side stream + event pair per CALLER stream (created on first use, kept for the life of the process)
+  static std::mutex side_mutex;
+  static std::unordered_map<cudaStream_t, EighSide> sides;
+  EighSide side;
+  {
+    std::lock_guard<std::mutex> lock(side_mutex);
+    EighSide& slot = sides[st];
+    if (!slot.stream) {
+      GP_CUDA(cudaStreamCreateWithFlags(&slot.stream, cudaStreamNonBlocking));
+      GP_CUDA(cudaEventCreateWithFlags(&slot.fork, cudaEventDisableTiming));
+      GP_CUDA(cudaEventCreateWithFlags(&slot.join, cudaEventDisableTiming));
+    }
+    side = slot;
   }
   // side stream: R = H^T (rows H e_i)
   GP_CUDA(cudaEventRecord(side.fork, st));
