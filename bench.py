@@ -186,6 +186,8 @@ def make_models(device, world, torch, groups=None):
     from gpcsd_b200.priors import GPCSDHalfNormalPrior
     x, t = geometry()
     rank = int(os.environ.get("RANK", "0"))
+    from gpcsd_b200.parallel import CollectiveOrder
+    order = CollectiveOrder(NPROBES)
     models = []
     for probe in range(NPROBES):
         np.random.seed(10 + probe)
@@ -199,6 +201,10 @@ def make_models(device, world, torch, groups=None):
         m = GPCSD1D(placeholder, x, t, a=A_LO, b=B_HI, ngl=NGL, spatial_cov=spatial_cov, temporal_cov_list=[se, mat],
                     sig2n_prior=sig_pri, distributed=(groups[probe] if world > 1 else False))
         m.lfp_is_local = world > 1
+        if world > 1:
+            # the probes are evaluated from two host threads on two communicators: keep their collectives in ONE global
+            # order on every rank (probe 0, probe 1, probe 0, ...), otherwise two ranks can enqueue them crosswise
+            m._collective_order = (order, probe)
         m.R['value'] = th["R"]
         spatial_cov.params['ell']['value'] = th["ell"]
         Ks = spatial_cov.compKphi_1d(th["R"])
@@ -333,9 +339,16 @@ def run_gpu(args):
             for s in range(first, first + nsteps):
                 r = eval_probe(p, s, upload)
             return r
+        order = getattr(models[0], "_collective_order", (None,))[0]
+        if order is not None:
+            order.start()                                  # concurrent phase: collectives in one global rotation
         futs = [pool.submit(worker, p) for p in range(len(models))]
-        for p, f in enumerate(futs):
-            last[p] = f.result()
+        try:
+            for p, f in enumerate(futs):
+                last[p] = f.result()
+        finally:
+            if order is not None:
+                order.stop()
 
     def timed_steps(nsteps, first, upload):
         barrier()

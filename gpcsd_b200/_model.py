@@ -44,6 +44,8 @@ class GPCSDModelBase:
         if eng is None or self._engine_geom != geom_key:
             eng = KronEngine(self.DIM, self.x, self.t, self._quadrature(), group=getattr(self, "_group", None),
                              jitter=self.JITTER)
+            if getattr(self, "_collective_order", None) is not None:
+                eng.shard.set_order(*self._collective_order)      # models evaluated from several host threads (parallel.py)
             self._engine, self._engine_geom, self._engine_lfp = eng, geom_key, None
         if self._engine_lfp is not self.lfp:
             eng.set_lfp(self.lfp, local=getattr(self, "lfp_is_local", False))

@@ -514,17 +514,24 @@ class KronEngine:
         if any(bool(torch.any(i != 0).item()) for i in st["infos"]):
             raise np.linalg.LinAlgError("Eigenvalues did not converge")
 
+    @staticmethod
+    def _info_piece(st):
+        """The eigensolvers' info flags as one float64 device vector (>= 0 entries), so they travel with the result
+        instead of costing a device->host read each."""
+        return torch.cat([i.reshape(-1) for i in st["infos"]]).abs().to(F64)
+
     def loglik(self, hp):
         """Marginal log-likelihood (gpcsd1d.py:113-128 / gpcsd2d.py:136-151); all-reduced over trial shards."""
         st = self._factorize(hp, jitter=True, want_grad=False)
         self._project(st)
-        res = st["sums"][:4].cpu().numpy()
-        if st["sums_b"] is not None:
-            res[:2] += st["sums_b"].cpu().numpy()
-        self._check_info(st)
+        # every term is linear in the entries of `flat` (trial sums add up over the shards; the replicated log-det term is
+        # weighted 1/world), so the raw vector is all-reduced on the device and assembled once
+        pieces = [st["sums"][:4], st["sums_b"] if st["sums_b"] is not None else st["sums"][:2] * 0.0, self._info_piece(st)]
+        flat = self.shard.allreduce_device(torch.cat(pieces))
+        if np.any(flat[6:] != 0):
+            raise np.linalg.LinAlgError("Eigenvalues did not converge")
         f = self.shard.det_fraction()
-        part = np.array([-0.5 * self.ntrials_total * f * res[2] - 0.5 * res[0]])
-        return float(self.shard.allreduce_sum(part, self.device)[0])
+        return float(-0.5 * self.ntrials_total * f * flat[2] - 0.5 * (flat[0] + flat[4]))
 
     def loglik_grad(self, hp):
         """(loglik, d loglik / d natural parameters) in the order R, ell(s), (ell_t, sigma2_t)..., sig2n[...]."""
@@ -605,13 +612,17 @@ class KronEngine:
         pieces = [res[: 8 + 2 * ntc]]
         if vec:
             pieces += [st["rowC"], torch.diagonal(Ns[:, :nx])]
-        if st["sums_b"] is not None:
-            pieces.append(st["sums_b"])
-        flat = torch.cat([p.reshape(-1) for p in pieces]).cpu().numpy()
-        self._check_info(st)
-        quad, bsq, slogD, srD = flat[0], flat[1], flat[2], flat[3]
-        if st["sums_b"] is not None:
-            quad, bsq = quad + flat[-2], bsq + flat[-1]
+        ninfo = sum(int(i.numel()) for i in st["infos"])
+        pieces.append(st["sums_b"] if st["sums_b"] is not None else res[:2] * 0.0)
+        pieces.append(self._info_piece(st))
+        # every term below is linear in the entries of `flat` (trial sums add up over the shards, the replicated
+        # trial-independent terms carry the weight f = 1/world): all-reduce the raw vector on the device (NCCL, on this
+        # stream), ONE device->host read, then the O(P) host assembly
+        flat = self.shard.allreduce_device(torch.cat([p.reshape(-1) for p in pieces]))
+        if np.any(flat[-ninfo:] != 0):
+            raise np.linalg.LinAlgError("Eigenvalues did not converge")
+        flat = flat[:-ninfo]
+        quad, bsq, slogD, srD = flat[0] + flat[-2], flat[1] + flat[-1], flat[2], flat[3]
         ll = -0.5 * ntot * f * slogD - 0.5 * quad
         g = [2.0 * flat[4]] + [flat[5 + k] for k in range(len(hp.ells))] + list(flat[8: 8 + 2 * ntc])
         if vec:
@@ -620,8 +631,7 @@ class KronEngine:
             g += list(-0.5 * ntot * f * rowC + 0.5 * dNs)
         else:
             g.append(-0.5 * ntot * f * srD + 0.5 * bsq)
-        out = self.shard.allreduce_sum(np.array([ll] + g, dtype=np.float64), self.device)
-        return float(out[0]), out[1:]
+        return float(ll), np.array(g, dtype=np.float64)
 
     def _rotate(self, X, QT, n, ld, tag):
         """G = Q X Q^T from QT = Q^T (row-major):  T1 = X QT ;  G = Q T1."""

@@ -16,6 +16,65 @@ def shard_bounds(ntrials, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+class CollectiveOrder:
+    """Turnstile for models that are evaluated from different host threads of one process, each on its own communicator.
+
+    Collectives of DIFFERENT communicators on one device still have to be issued in the same order on every rank (NCCL
+    kernels of one device are not guaranteed to run concurrently): two free-running threads would issue
+    (comm0, comm1) on one rank and (comm1, comm0) on another and dead-lock.  `turn(i)` lets member i enqueue its next
+    collective only when it is its turn in the fixed rotation 0, 1, ..., n-1, 0, ... -- every member must therefore issue
+    the same sequence of collectives between start() and stop() (true for models evaluated in lock step, as in bench.py).
+    Only the ENQUEUE is inside the turn; waiting for the result happens outside."""
+
+    def __init__(self, n):
+        import threading
+        self.n = int(n)
+        self.seq = 0
+        self.enabled = False
+        self.cv = threading.Condition()
+
+    def start(self):
+        """Begin a phase in which the members run on concurrent threads (call from the coordinating thread while no
+        member is evaluating).  Outside such phases -- members driven one after the other by a single thread, whose order is
+        the same on every rank anyway -- turn() does not wait."""
+        with self.cv:
+            self.seq, self.enabled = 0, True
+
+    def stop(self):
+        with self.cv:
+            self.enabled = False
+            self.cv.notify_all()
+
+    def turn(self, idx):
+        return _Turn(self, int(idx)) if self.enabled else _NoTurn()
+
+
+class _Turn:
+    def __init__(self, order, idx):
+        self.order, self.idx = order, idx
+
+    def __enter__(self):
+        o = self.order
+        with o.cv:
+            while o.seq % o.n != self.idx:
+                o.cv.wait()
+
+    def __exit__(self, *exc):
+        o = self.order
+        with o.cv:
+            o.seq += 1
+            o.cv.notify_all()
+        return False
+
+
+class _NoTurn:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
 class TrialShard:
     """group: None/False -> single process (no sharding); True -> the default process group;
     otherwise a torch.distributed process group."""
@@ -27,6 +86,14 @@ class TrialShard:
         self.group = None if (group is True or not self.enabled) else group
         self.rank = dist.get_rank(self.group) if self.enabled else 0
         self.world = dist.get_world_size(self.group) if self.enabled else 1
+        self.order, self.order_index = None, 0
+
+    def set_order(self, order, index):
+        """Join a CollectiveOrder rotation (models driven from several host threads of one process)."""
+        self.order, self.order_index = order, int(index)
+
+    def _turn(self):
+        return self.order.turn(self.order_index) if self.order is not None else _NoTurn()
 
     def bounds(self, ntrials):
         return shard_bounds(ntrials, self.rank, self.world)
@@ -45,8 +112,19 @@ class TrialShard:
         t = torch.from_numpy(vec.copy())
         if backend == "nccl":
             t = t.to(device)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        with self._turn():
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         return t.cpu().numpy()
+
+    def allreduce_device(self, t):
+        """Sum a small float64 DEVICE vector over the ranks and return it on the host: with NCCL the all-reduce runs in
+        place on the caller's stream (no host round trip before the collective), then ONE device->host read; with gloo
+        (CPU tests) or a single rank the vector is read first."""
+        if self.enabled and self.world > 1 and dist.get_backend(self.group) == "nccl":
+            with self._turn():
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            return t.cpu().numpy()
+        return self.allreduce_sum(t.cpu().numpy())
 
 
 class RestartShard:

@@ -127,3 +127,28 @@ def test_dropin_alias_package():
            "assert callable(fwd_model_1d) and callable(b_fwd_2d) and GPCSDInvGammaPrior; print('ok')" % (ROOT, os.path.join(ROOT, "dropin"))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_collective_order_rotation():
+    """parallel.CollectiveOrder: concurrent members enqueue in the fixed rotation 0,1,0,1,...; outside a started phase
+    turn() never waits (a single thread driving the members one after the other must not dead-lock)."""
+    import threading
+    from gpcsd_b200.parallel import CollectiveOrder
+    order = CollectiveOrder(2)
+    log = []
+    for idx in (0, 0, 1, 1):                      # not started: free
+        with order.turn(idx):
+            log.append(idx)
+    assert log == [0, 0, 1, 1]
+    log.clear()
+    order.start()
+
+    def member(idx):
+        for _ in range(50):
+            with order.turn(idx):
+                log.append(idx)
+    ths = [threading.Thread(target=member, args=(i,)) for i in (1, 0)]
+    [t.start() for t in ths]
+    [t.join(timeout=20) for t in ths]
+    order.stop()
+    assert log == [0, 1] * 50
