@@ -48,6 +48,7 @@ SIGNATURES = {
     "gpcsd_centro_fold": (c_int, [c_int, c_int, c_long, _P, _P, _P]),
     "gpcsd_pairsym_split": (c_int, [c_int, _P, c_long, _P, _P, _P, c_long, _P, c_long, _P]),
     "gpcsd_pairsym_assemble": (c_int, [c_int, _P, _P, _P, c_long, _P, _P, c_long, _P, _P, c_long, _P, _P]),
+    "gpcsd_pairsym_fold": (c_int, [c_int, _P, _P, c_long, _P, _P, _P]),
     "gpcsd_eig_D": (c_int, [c_int, c_int, _P, _P, _P, c_int, _P, c_long, _P, _P, _P, _P, _P, _P]),
     "gpcsd_fwd_weights_1d": (c_int, [c_int, _P, c_int, _P, _P, c_double, _P, _P, c_long, _P]),
     "gpcsd_fwd_weights_2d": (c_int, [c_int, _P, c_int, c_int, _P, _P, _P, _P, c_double, c_double, _P, _P, c_long, _P]),

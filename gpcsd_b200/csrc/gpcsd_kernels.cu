@@ -432,6 +432,21 @@ __global__ void pairsym_assemble_kernel(int m, const int* __restrict__ ra, const
   if (c == 0) W[a] = (a < m) ? Ws[a] : Wa[a - m];
 }
 
+// Fold of the channel axis under the involution pi (see pairsym_split_kernel): X[n][rowlen] -> Xf[n][rowlen],
+//   Xf[c] = (X[ra[c]] + X[rb[c]]) / sqrt 2,   Xf[m + c] = (X[ra[c]] - X[rb[c]]) / sqrt 2,   c < m = n/2.
+// In this basis the eigenvector matrix assembled by pairsym_assemble_kernel is block diagonal (Us^T, Ua^T): Qs^T Y becomes two
+// products of order n/2, and only the two diagonal blocks of the spatial SYRK enter the gradient.
+__global__ void pairsym_fold_kernel(int m, long rowlen2, const int* __restrict__ ra, const int* __restrict__ rb,
+                                    const double2* __restrict__ X, double2* __restrict__ Xf) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;      // over [m][rowlen/2]
+  if (idx >= (long)m * rowlen2) return;
+  const long c = idx / rowlen2, col = idx - c * rowlen2;
+  const double h = 0.70710678118654752;
+  const double2 u = X[(long)ra[c] * rowlen2 + col], v = X[(long)rb[c] * rowlen2 + col];
+  Xf[c * rowlen2 + col] = make_double2(h * (u.x + v.x), h * (u.y + v.y));
+  Xf[(m + c) * rowlen2 + col] = make_double2(h * (u.x - v.x), h * (u.y - v.y));
+}
+
 }  // namespace gpcsd
 
 using namespace gpcsd;
@@ -677,6 +692,17 @@ int gpcsd_pairsym_assemble(int n, const int* ra, const int* rb, const double* Us
   if (n < 2 || (n & 1)) return gp_fail("pairsym_assemble: n must be even and >= 2");
   const long m = n / 2;
   pairsym_assemble_kernel<<<GRID1D(2 * m * m), 0, (cudaStream_t)stream>>>((int)m, ra, rb, UsT, lds, Ws, UaT, lda, Wa, QT, ldq, W);
+  GP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int gpcsd_pairsym_fold(int n, const int* ra, const int* rb, long rowlen, const double* X, double* Xf, void* stream) {
+  if (n < 2 || (n & 1)) return gp_fail("pairsym_fold: n must be even and >= 2");
+  if (rowlen & 1L) return gp_fail("pairsym_fold: row length must be even");
+  if (((uintptr_t)X | (uintptr_t)Xf) & 15) return gp_fail("pairsym_fold: pointers must be 16-byte aligned");
+  const long m = n / 2;
+  pairsym_fold_kernel<<<GRID1D(m * (rowlen / 2)), 0, (cudaStream_t)stream>>>((int)m, rowlen / 2, ra, rb, (const double2*)X,
+                                                                             (double2*)Xf);
   GP_CUDA(cudaGetLastError());
   return 0;
 }

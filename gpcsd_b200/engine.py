@@ -72,6 +72,7 @@ class KronEngine:
         self.ntrials = 0
         self.n_launches = 0
         self._sides = None
+        self._yf, self._yf_version, self._lfp_version = None, -1, 0
         self._copy_stream = None
         self._y_ready = None
         self.timers = None      # {abi_name: [(start_event, end_event), ...]} when bench.py profiles a kernel
@@ -83,6 +84,7 @@ class KronEngine:
             raise ValueError("engines have different geometry")
         self.Y, self.ntrials, self.ntrials_total, self.ldn = other.Y, other.ntrials, other.ntrials_total, other.ldn
         self._y_ready = other._y_ready
+        self._lfp_version += 1
 
     # ------------------------------------------------------------------ plumbing
     def _dev(self, arr):
@@ -241,6 +243,7 @@ class KronEngine:
                 self._y_ready.record(self._copy_stream)
             nbytes = slab.numel() * 8
         self.ntrials_total, self.ntrials, self.ldn = ntot, n, ldn
+        self._lfp_version += 1
         return nbytes
 
     # ------------------------------------------------------------------ covariance construction
@@ -364,6 +367,7 @@ class KronEngine:
         scalar noise) the problem is split into two of order nx/2; orders <= 128 go through the batched small-matrix path
         (batch 2 -- batch 1 would fall back to the latency-bound syevd); everything else is one syevd."""
         nx, ld = self.nx, self.ldx
+        self._s_blocks = None
         if allow_split and self.s_pairs is not None and nx >= 64:
             ra, rb = self.s_pairs
             m = nx // 2
@@ -375,6 +379,7 @@ class KronEngine:
             QT, W = self._buf("QT_s", nx, ld), self._buf("W_s", nx)
             self._call("gpcsd_pairsym_assemble", nx, ra.data_ptr(), rb.data_ptr(), self._p(UsT), ldm, self._p(Ws),
                        self._p(UaT), ldm, self._p(Wa), self._p(QT), ld, self._p(W), self._stream())
+            self._s_blocks = (UsT, UaT, ldm)
             return QT, W, infos
         QT, W, info = self._eigh(Ks, nx, ld, "s")
         return QT, W, [info]
@@ -383,6 +388,18 @@ class KronEngine:
         if self._sides is None:
             self._sides = [torch.cuda.Stream(device=self.device) for _ in range(3)]
         return self._sides
+
+    def _folded_lfp(self):
+        """The uploaded LFP in the channel-folded basis of gpcsd_pairsym_fold; recomputed only after a new upload.  Runs on
+        the caller's (side) stream, after the upload event."""
+        if self._yf is None or self._yf_version != self._lfp_version or self._yf.shape != self.Y.shape:
+            ra, rb = self.s_pairs
+            if self._yf is None or self._yf.shape != self.Y.shape:
+                self._yf = torch.zeros_like(self.Y)
+            self._call("gpcsd_pairsym_fold", self.nx, ra.data_ptr(), rb.data_ptr(), self.nt * self.ldn, self._p(self.Y),
+                       self._p(self._yf), self._stream())
+            self._yf_version = self._lfp_version
+        return self._yf
 
     def _t_split(self):
         """Uniform time grid: Kt is centrosymmetric, its eigenproblem splits into a symmetric and a skew half and -- in the
@@ -451,8 +468,18 @@ class KronEngine:
                 if self._y_ready is not None:
                     side.wait_event(self._y_ready)
                 st["Z"] = self._buf("Z", self.nx, self.nt, self.ldn)
-                self.gemm(0, self.nx, self.nt * self.ldn, self.nx, st["QsT"], self.ldx, 0, self.Y, self.nt * self.ldn, 0,
-                          st["Z"], self.nt * self.ldn, 0)
+                row = self.nt * self.ldn
+                if self._s_blocks is not None and self.ntrials > 0:
+                    # reflection-symmetric geometry: Qs is block diagonal on the channel-folded LFP (folded once per upload)
+                    UsT, UaT, ldm = self._s_blocks
+                    m = self.nx // 2
+                    Yf = self._folded_lfp()
+                    self._call("gpcsd_dgemm", 0, m, row, m, self._p(UsT), ldm, 0, self._p(Yf), row, 0, self._p(st["Z"]), row, 0,
+                               1, self._stream())
+                    self._call("gpcsd_dgemm", 0, m, row, m, self._p(UaT), ldm, 0, self._p(Yf, m * row), row, 0,
+                               self._p(st["Z"], m * row), row, 0, 1, self._stream())
+                else:
+                    self.gemm(0, self.nx, row, self.nx, st["QsT"], self.ldx, 0, self.Y, row, 0, st["Z"], row, 0)
                 if self._t_fold() and self.ntrials > 0:
                     # folded time basis: the temporal projection and the temporal SYRK then run on two blocks of order
                     # ~nt/2 (half the flops); also hidden underneath the temporal eigensolve
@@ -549,7 +576,7 @@ class KronEngine:
         Ms = self._buf("Ms", nx, self.ldx)
         wst = self._buf("ws_syrk_t", max(max(L.query("gpcsd_wsyrk_ws_doubles", o, nx, max(N, 1))
                                              for o in {nt, nt // 2, nt - nt // 2}), 2))
-        wss = self._buf("ws_syrk_s", max(L.query("gpcsd_wsyrk_ws_doubles", nx, nt, max(N, 1)), 2))
+        wss = self._buf("ws_syrk_s", max(max(L.query("gpcsd_wsyrk_ws_doubles", o, nt, max(N, 1)) for o in {nx, max(nx // 2, 1)}), 2))
         Ns = None
         if N > 0:
             if self._t_blocks is not None and self._t_fold():
@@ -565,8 +592,18 @@ class KronEngine:
             else:
                 self._call("gpcsd_wsyrk", nt, nx, N, self._p(Bm), ldn, nt * ldn, self._p(st["ls"]), self._p(Mt), self.ldt,
                            self._p(wst), stream())
-            self._call("gpcsd_wsyrk", nx, nt, N, self._p(Bm), nt * ldn, ldn, self._p(st["lt"]), self._p(Ms), self.ldx,
-                       self._p(wss), stream())
+            if self._s_blocks is not None:
+                # same argument on the channel axis: every dKs/dtheta shares the geometry's reflection symmetry, so only the
+                # two diagonal blocks of Ms enter the spatial contractions
+                mh = nx // 2
+                Ms.zero_()
+                self._call("gpcsd_wsyrk", mh, nt, N, self._p(Bm), nt * ldn, ldn, self._p(st["lt"]), self._p(Ms), self.ldx,
+                           self._p(wss), stream())
+                self._call("gpcsd_wsyrk", mh, nt, N, self._p(Bm, mh * nt * ldn), nt * ldn, ldn, self._p(st["lt"]),
+                           self._p(Ms, mh * self.ldx + mh), self.ldx, self._p(wss), stream())
+            else:
+                self._call("gpcsd_wsyrk", nx, nt, N, self._p(Bm), nt * ldn, ldn, self._p(st["lt"]), self._p(Ms), self.ldx,
+                           self._p(wss), stream())
         else:
             Mt.zero_()
             Ms.zero_()

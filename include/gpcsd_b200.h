@@ -149,6 +149,11 @@ int gpcsd_pairsym_split(int n, const double* K, long ldk, const int* ra, const i
 int gpcsd_pairsym_assemble(int n, const int* ra, const int* rb, const double* UsT, long lds, const double* Ws,
                            const double* UaT, long lda, const double* Wa, double* QT, long ldq, double* W, void* stream);
 
+/* Channel-axis analogue of gpcsd_centro_fold for that involution: X[n][rowlen] -> Xf[c] = (X[ra[c]] + X[rb[c]])/sqrt2,
+ * Xf[n/2 + c] = (X[ra[c]] - X[rb[c]])/sqrt2.  Qs (as assembled above) is block diagonal in this basis, so Qs^T Y (the spatial
+ * half of the trial loop gpcsd2d.py:147-149) and the spatial SYRK of the gradient cost half the flops. */
+int gpcsd_pairsym_fold(int n, const int* ra, const int* rb, long rowlen, const double* X, double* Xf, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * D and its reductions (utility_functions.py:54-63; gpcsd1d.py:122):
  *   D_ij = ls_i * lt_j + s_i  (s = sig2n[0] if n_sig2n == 1 else sig2n[i], i = ASCENDING spatial eigen-index)

@@ -200,6 +200,10 @@ def test_spatial_reflection_symmetry_split(cuda_lib):
     out = eng.predict(hp, X[::7], t, "both")
     ref = O.predict_kron(om, lfp, X[::7], t, "both")
     assert relerr(out["csd_pred"], ref["csd_pred"]) < TOL_PRED and relerr(out["lfp_pred"], ref["lfp_pred"]) < TOL_PRED
+    # a new upload must refresh the channel-folded copy of the LFP
+    eng.set_lfp(0.5 * lfp[:, :, ::-1].copy())
+    ll2_o = O.loglik(om, 0.5 * lfp[:, :, ::-1])
+    assert abs(eng.loglik(hp) - ll2_o) / abs(ll2_o) < TOL_LL
     # shifted box: not symmetric
     om_shift = synth.model_2d(X, t, ngl1=10, ngl2=40, a1=-16.0, b1=64.0, a2=-100.0, b2=ymax + 140.0, eps=1.0, sig2n=0.5)
     eng2, hp2 = engine_from_oracle(om_shift, lfp)

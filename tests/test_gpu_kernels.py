@@ -498,3 +498,19 @@ def test_centro_fold(cuda_lib, n, nblk, rowlen):
         ref[:, m] = X[:, m]
     ref[:, ms:] = (X[:, :m] - X[:, ::-1][:, :m]) / np.sqrt(2)
     assert relerr(Xf.cpu().numpy(), ref) < 1e-15
+
+
+def test_pairsym_fold(cuda_lib):
+    """Channel fold under an index pairing: sums / differences of paired rows."""
+    from gpcsd_b200 import _lib as L
+    rng = np.random.default_rng(5)
+    n, rowlen = 12, 40
+    perm = rng.permutation(n)
+    ra, rb = perm[: n // 2].astype(np.int32), perm[n // 2:].astype(np.int32)
+    X = rng.standard_normal((n, rowlen))
+    Xd = torch.from_numpy(X).cuda()
+    Xf = torch.zeros_like(Xd)
+    rad, rbd = torch.from_numpy(ra).cuda(), torch.from_numpy(rb).cuda()
+    L.call("gpcsd_pairsym_fold", n, rad.data_ptr(), rbd.data_ptr(), rowlen, Xd.data_ptr(), Xf.data_ptr(), _stream())
+    ref = np.concatenate([(X[ra] + X[rb]) / np.sqrt(2), (X[ra] - X[rb]) / np.sqrt(2)])
+    assert relerr(Xf.cpu().numpy(), ref) < 1e-15
