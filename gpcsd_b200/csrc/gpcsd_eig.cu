@@ -33,14 +33,11 @@ namespace cg = cooperative_groups;
 
 namespace gpcsd {
 
-// shared::cluster address of `ptr` (a shared-memory object of this CTA) in CTA `rank` of the cluster, and a remote store
+// shared::cluster address of `ptr` (a shared-memory object of this CTA) in CTA `rank` of the cluster
 __device__ __forceinline__ uint32_t dsmem_addr(const void* ptr, int rank) {
   uint32_t local = (uint32_t)__cvta_generic_to_shared(ptr), remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(remote) : "r"(local), "r"(rank));
   return remote;
-}
-__device__ __forceinline__ void dsmem_store(uint32_t addr, double v) {
-  asm volatile("st.shared::cluster.f64 [%0], %1;\n" ::"r"(addr), "d"(v) : "memory");
 }
 // remote store that also signals 8 transaction bytes on an mbarrier of the SAME remote CTA: data and "it has arrived" travel
 // together, so the consumer needs neither a cluster barrier nor a fence
@@ -377,7 +374,7 @@ constexpr int DC_WARPS = DC_THREADS / 32;
 constexpr int DC_MAXN = 256;
 constexpr int DC_MAXNODES = DC_MAXN / 2;
 constexpr int DC_TM = 64, DC_TN = 64, DC_TK = 16;     // eigenvector-update tile (rows = new eigenvectors, cols = components)
-constexpr int DC_DIRECT_MAX = 32;                     // merge nodes up to this size use the one-warp-per-row update
+constexpr int DC_DIRECT_MAX = 32;                     // merge nodes up to this size use the one-thread-per-element update
 
 struct DcSmem {
   // replicated in every CTA (each CTA runs the O(n) bookkeeping redundantly, bit-identically)
