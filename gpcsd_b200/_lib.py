@@ -46,6 +46,7 @@ SIGNATURES = {
     "gpcsd_centro_split": (c_int, [c_int, _P, c_long, _P, c_long, _P, c_long, _P]),
     "gpcsd_centro_assemble": (c_int, [c_int, _P, c_long, _P, _P, c_long, _P, _P, c_long, _P, _P]),
     "gpcsd_centro_fold": (c_int, [c_int, c_int, c_long, _P, _P, _P]),
+    "gpcsd_centro_unfold": (c_int, [c_int, c_int, c_long, _P, _P, _P]),
     "gpcsd_pairsym_split": (c_int, [c_int, _P, c_long, _P, _P, _P, c_long, _P, c_long, _P]),
     "gpcsd_pairsym_assemble": (c_int, [c_int, _P, _P, _P, c_long, _P, _P, c_long, _P, _P, c_long, _P, _P]),
     "gpcsd_pairsym_fold": (c_int, [c_int, _P, _P, c_long, _P, _P, _P]),

@@ -391,6 +391,27 @@ __global__ void centro_fold_kernel(int n, long rowlen2, long total, const double
   }
 }
 
+// Inverse of centro_fold_kernel (the fold matrix is orthogonal): X[b][j] = (Xf[b][j] + Xf[b][ms+j]) / sqrt 2,
+// X[b][n-1-j] = (Xf[b][j] - Xf[b][ms+j]) / sqrt 2 for j < n/2, middle row copied for odd n.
+__global__ void centro_unfold_kernel(int n, long rowlen2, long total, const double2* __restrict__ Xf, double2* __restrict__ X) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;        // over [nblk][ms][rowlen/2]
+  if (idx >= total) return;
+  const int m = n / 2, ms = m + (n & 1);
+  const long c = idx % rowlen2, bj = idx / rowlen2;
+  const int j = (int)(bj % ms);
+  const long b = bj / ms;
+  const double2* fb = Xf + b * n * rowlen2;
+  double2* xb = X + b * n * rowlen2;
+  const double h = 0.70710678118654752;
+  if (j < m) {
+    const double2 u = fb[(long)j * rowlen2 + c], v = fb[(long)(ms + j) * rowlen2 + c];
+    xb[(long)j * rowlen2 + c] = make_double2(h * (u.x + v.x), h * (u.y + v.y));
+    xb[(long)(n - 1 - j) * rowlen2 + c] = make_double2(h * (u.x - v.x), h * (u.y - v.y));
+  } else {
+    xb[(long)j * rowlen2 + c] = fb[(long)j * rowlen2 + c];
+  }
+}
+
 __global__ void copy_matrix_kernel(int n, const double* __restrict__ in, long ldi, double* __restrict__ out, long ldo) {
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long)n * n) return;
@@ -674,6 +695,16 @@ int gpcsd_centro_fold(int nblk, int n, long rowlen, const double* X, double* Xf,
   if (nblk <= 0 || n <= 0 || rowlen <= 0) return 0;
   const long ms = n / 2 + (n & 1), total = (long)nblk * ms * (rowlen / 2);
   centro_fold_kernel<<<GRID1D(total), 0, (cudaStream_t)stream>>>(n, rowlen / 2, total, (const double2*)X, (double2*)Xf);
+  GP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int gpcsd_centro_unfold(int nblk, int n, long rowlen, const double* Xf, double* X, void* stream) {
+  if (rowlen & 1L) return gp_fail("centro_unfold: row length must be even");
+  if (((uintptr_t)X | (uintptr_t)Xf) & 15) return gp_fail("centro_unfold: pointers must be 16-byte aligned");
+  if (nblk <= 0 || n <= 0 || rowlen <= 0) return 0;
+  const long ms = n / 2 + (n & 1), total = (long)nblk * ms * (rowlen / 2);
+  centro_unfold_kernel<<<GRID1D(total), 0, (cudaStream_t)stream>>>(n, rowlen / 2, total, (const double2*)Xf, (double2*)X);
   GP_CUDA(cudaGetLastError());
   return 0;
 }

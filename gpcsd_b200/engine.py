@@ -731,15 +731,35 @@ class KronEngine:
             V = self._buf("V", nz, nt, ldn)
             self.gemm(0, nz, nt * ldn, nx, Ps, ldz, 0, Bm, nt * ldn, 0, V, nt * ldn, 0)
             parts = []
+            # t* == t on a uniform grid (every caller of the reference): Kt*_k is centrosymmetric like Kt, so in the folded
+            # time basis Kt*_k Qt = blockdiag(Cs Us, Ca Ua): two half-order batched GEMMs + one unfold pass per output
+            folded = self._t_blocks is not None and self._t_fold() and N > 0 and np.array_equal(ts, self.t_host)
             for k, (knd, ell, s2) in enumerate(hp.temporal):
                 ntc1, kinds, ells, s2s = self._temporal_spec([(knd, ell, s2)])
                 KtsT = self._buf("KtsT", nt, self.ldt)      # KtsT[j][j'] = k(t_j - t*_j') = Kt*_k[j'][j]
                 self._call("gpcsd_kt_build", nt, self._p(self.t_dev), nt, self._p(ts_dev), ntc1, kinds, ells, s2s,
                            self._p(KtsT), self.ldt, self._stream())
-                Tk = self._buf("Tk", nt, self.ldt)           # Tk = Kt*_k^T Qt
-                self.gemm(0, nt, nt, nt, KtsT, self.ldt, 0, Qt, self.ldt, 0, Tk, self.ldt, 0)
                 out = torch.empty((nz, nt, ldn), dtype=F64, device=self.device)
-                self.gemm(0, nt, max(N, 1), nt, Tk, self.ldt, 0, V, ldn, nt * ldn, out, ldn, nt * ldn, batch=nz)
+                if folded:
+                    UsT, lds, UaT, lda = self._t_blocks
+                    m = nt // 2
+                    ms = nt - m
+                    Cs, Ca = self._buf("pred_Cs", ms, lds), self._buf("pred_Ca", max(m, 1), lda)
+                    self._call("gpcsd_centro_split", nt, self._p(KtsT), self.ldt, self._p(Cs), lds, self._p(Ca), lda,
+                               self._stream())
+                    Ts, Ta = self._buf("pred_Ts", ms, lds), self._buf("pred_Ta", max(m, 1), lda)
+                    self.gemm(1, ms, ms, ms, Cs, lds, 0, UsT, lds, 0, Ts, lds, 0)          # Cs Us
+                    self.gemm(1, m, m, m, Ca, lda, 0, UaT, lda, 0, Ta, lda, 0)             # Ca Ua
+                    outf = self._buf("pred_outf", nz, nt, ldn)
+                    self._call("gpcsd_dgemm", 0, ms, N, ms, self._p(Ts), lds, 0, self._p(V), ldn, nt * ldn, self._p(outf), ldn,
+                               nt * ldn, nz, self._stream())
+                    self._call("gpcsd_dgemm", 0, m, N, m, self._p(Ta), lda, 0, self._p(V, ms * ldn), ldn, nt * ldn,
+                               self._p(outf, ms * ldn), ldn, nt * ldn, nz, self._stream())
+                    self._call("gpcsd_centro_unfold", nz, nt, ldn, self._p(outf), self._p(out), self._stream())
+                else:
+                    Tk = self._buf("Tk", nt, self.ldt)           # Tk = Kt*_k^T Qt
+                    self.gemm(0, nt, nt, nt, KtsT, self.ldt, 0, Qt, self.ldt, 0, Tk, self.ldt, 0)
+                    self.gemm(0, nt, max(N, 1), nt, Tk, self.ldt, 0, V, ldn, nt * ldn, out, ldn, nt * ldn, batch=nz)
                 parts.append(self._maybe_download(out, N, to_host))
             tot = torch.empty((nz, nt, ldn), dtype=F64, device=self.device)
             ptrs = (ctypes.c_void_p * len(parts))(*[(p[0] if to_host else p).data_ptr() for p in parts])

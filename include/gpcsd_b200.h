@@ -140,6 +140,9 @@ int gpcsd_centro_assemble(int n, const double* UsT, long lds, const double* Ws, 
  * In this basis the eigenvector matrix assembled by gpcsd_centro_assemble is block diagonal (Us^T, Ua^T), so the trial loop
  * of loglik (gpcsd1d.py:124-126) and the temporal SYRK of its gradient cost half the flops. */
 int gpcsd_centro_fold(int nblk, int n, long rowlen, const double* X, double* Xf, void* stream);
+/* Its inverse (the fold is orthogonal): folded time rows back to the time axis.  predict (gpcsd1d.py:279-291) at t* = t applies
+ * Kt*_k Qt as two half-order products in the folded basis and unfolds the result. */
+int gpcsd_centro_unfold(int nblk, int n, long rowlen, const double* Xf, double* X, void* stream);
 
 /* Same split for any fixed-point-free involution pi with K[pi(i)][pi(j)] == K[i][j] (n even): device int arrays
  * ra[n/2] (representatives) and rb[n/2] = pi(ra).  Used for the spatial factor of geometries that are invariant under the

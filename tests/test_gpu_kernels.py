@@ -498,6 +498,9 @@ def test_centro_fold(cuda_lib, n, nblk, rowlen):
         ref[:, m] = X[:, m]
     ref[:, ms:] = (X[:, :m] - X[:, ::-1][:, :m]) / np.sqrt(2)
     assert relerr(Xf.cpu().numpy(), ref) < 1e-15
+    back = torch.full_like(Xd, 7.0)
+    L.call("gpcsd_centro_unfold", nblk, n, rowlen, Xf.data_ptr(), back.data_ptr(), _stream())
+    assert relerr(back.cpu().numpy(), X) < 1e-15        # the fold is orthogonal: unfold is its exact inverse up to rounding
 
 
 def test_pairsym_fold(cuda_lib):
