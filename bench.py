@@ -307,6 +307,7 @@ def run_gpu(args):
 
     last = {}
     isolate = [False]
+    stagger_s = [0.0]
 
     # The two probes are independent models: evaluate them concurrently, one host thread + CUDA stream each,
     # so one probe's latency-bound cuSOLVER syevd overlaps the other's DMMA GEMMs (--serial disables this).
@@ -335,6 +336,12 @@ def run_gpu(args):
             return
 
         def worker(p):
+            # Phase offset between the probes: an evaluation is a latency-bound eigensolve on 16 SMs followed by GEMMs that
+            # fill the GPU.  Started together, the two probes stay in lock step (both eigensolves, then both GEMM phases
+            # fighting for the SMs); started half an evaluation apart, one probe's eigensolve runs underneath the other's
+            # GEMMs for the whole region.  The offset is inside the timed region.
+            if p > 0 and stagger_s[0] > 0.0:
+                time.sleep(p * stagger_s[0] / len(models))
             r = None
             for s in range(first, first + nsteps):
                 r = eval_probe(p, s, upload)
@@ -389,6 +396,20 @@ def run_gpu(args):
         args.serial = prev
 
     serial_once(0, False)
+    if not args.no_stagger:
+        # one evaluation of one probe, wall clock (device drained before and after): the phase offset is half of it
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        eval_probe(0, 0, False)
+        torch.cuda.synchronize()
+        t_eval = time.perf_counter() - t0
+        if world > 1:
+            # every rank uses the same offset; the slowest rank's estimate
+            tt = torch.tensor([t_eval], dtype=torch.float64, device=device)
+            eval_probe(1, 0, False)                        # keep the probes' collective counts equal
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t_eval = float(tt.item())
+        stagger_s[0] = t_eval
     timed_steps(W, 0, False)
     if args.profile_step:
         # one steady-state SERIAL step between cudaProfilerStart/Stop for `ncu --profile-from-start off`
@@ -534,6 +555,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--serial", action="store_true", help="evaluate the two probes one after the other")
+    ap.add_argument("--no-stagger", action="store_true", help="start the probes' evaluation loops together (no phase offset)")
     ap.add_argument("--profile-step", action="store_true", help="run warm-up then ONE step inside cudaProfilerStart/Stop")
     args = ap.parse_args()
     # watchdog: a hang (e.g. a collective one rank never enters) becomes a stack dump of every thread and a non-zero exit
