@@ -561,7 +561,7 @@ def main():
     # watchdog: a hang (e.g. a collective one rank never enters) becomes a stack dump of every thread and a non-zero exit
     # instead of a silent stall that holds the GPU box until the caller's timeout
     import faulthandler
-    faulthandler.dump_traceback_later(float(os.environ.get("GPCSD_BENCH_WATCHDOG_S", "900")), exit=True)
+    faulthandler.dump_traceback_later(float(os.environ.get("GPCSD_BENCH_WATCHDOG_S", "600")), exit=True)
     if args.impl == "reference":
         run_reference(args, int(os.environ.get("RANK", "0")))
         return
