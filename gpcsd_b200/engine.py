@@ -66,6 +66,7 @@ class KronEngine:
         self.shard = TrialShard(group)
         self.jitter = (1e-8 if dim == 1 else 1e-7) if jitter is None else jitter   # gpcsd1d.py:17 / gpcsd2d.py:16
         self._ws = {}
+        self._qcache = {}
         self.set_geometry(x, t, quad)
         self.Y = None
         self.ntrials_total = 0
@@ -101,6 +102,14 @@ class KronEngine:
 
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _q(self, name, *args):
+        """Workspace-size queries are pure functions of their arguments: ask the library once per shape."""
+        key = (name,) + args
+        v = self._qcache.get(key)
+        if v is None:
+            v = self._qcache[key] = L.query(name, *args)
+        return v
 
     # kernels of OURS launched per ABI call (cuSOLVER's own launches inside gpcsd_eigh are not counted)
     _LAUNCHES = {"gpcsd_project_quad": 2, "gpcsd_wsyrk": 2, "gpcsd_eig_D": 2, "gpcsd_kt_grad": 2, "gpcsd_dot": 2,
@@ -322,7 +331,7 @@ class KronEngine:
             return QTs[0], Ws[0], info
         QT = self._buf("QT_" + tag, n, ld) if QT is None else QT
         W = self._buf("W_" + tag, n) if W is None else W
-        nws = L.query("gpcsd_eigh_ws_doubles", n, ld)
+        nws = self._q("gpcsd_eigh_ws_doubles", n, ld)
         ws = self._buf("eigws_" + tag, max(nws, 1))
         info = self._buf("info_" + tag, 1, dtype=torch.int32)
         self._call("gpcsd_eigh", n, self._p(K), ld, self._p(QT), ld, self._p(W), self._p(ws), nws, info.data_ptr(),
@@ -334,7 +343,7 @@ class KronEngine:
         in one launch sequence of the cluster solver (one 8-CTA cluster per matrix); the input is left untouched."""
         QT = self._buf("QTdc_" + tag, nmat, n, ld) if QT is None else QT.view(nmat, n, ld)
         W = self._buf("Wdc_" + tag, nmat, n) if W is None else W.view(nmat, n)
-        nws = L.query("gpcsd_eigh_dc_ws_doubles", n, ld, nmat)
+        nws = self._q("gpcsd_eigh_dc_ws_doubles", n, ld, nmat)
         ws = self._buf("eigdcws_" + tag, nws)
         info = self._buf("infodc_" + tag, nmat, dtype=torch.int32)
         self._call("gpcsd_eigh_dc", n, nmat, self._p(stack), ld, self._p(QT), ld, self._p(W), self._p(ws), nws, info.data_ptr(),
@@ -514,7 +523,7 @@ class KronEngine:
         Z = st["Z"]                                  # computed on the spatial side stream by _factorize
         Bm = self._buf("Bm", nx, nt, ldn)
         # (the block calls of the folded basis may take another kernel path than order nt: size for all three orders)
-        nws = max(L.query("gpcsd_project_quad_ws_doubles", nx, o, max(self.ntrials, 1)) for o in {nt, nt // 2, nt - nt // 2})
+        nws = max(self._q("gpcsd_project_quad_ws_doubles", nx, o, max(self.ntrials, 1)) for o in {nt, nt // 2, nt - nt // 2})
         part = self._buf("quad_part", nws)
         st["sums_b"] = None
         if self.ntrials > 0 and self._t_blocks is not None and self._t_fold():
@@ -574,9 +583,9 @@ class KronEngine:
         # --- segment-weighted SYRKs over the trial batch
         Mt = self._buf("Mt", nt, self.ldt)
         Ms = self._buf("Ms", nx, self.ldx)
-        wst = self._buf("ws_syrk_t", max(max(L.query("gpcsd_wsyrk_ws_doubles", o, nx, max(N, 1))
+        wst = self._buf("ws_syrk_t", max(max(self._q("gpcsd_wsyrk_ws_doubles", o, nx, max(N, 1))
                                              for o in {nt, nt // 2, nt - nt // 2}), 2))
-        wss = self._buf("ws_syrk_s", max(max(L.query("gpcsd_wsyrk_ws_doubles", o, nt, max(N, 1)) for o in {nx, max(nx // 2, 1)}), 2))
+        wss = self._buf("ws_syrk_s", max(max(self._q("gpcsd_wsyrk_ws_doubles", o, nt, max(N, 1)) for o in {nx, max(nx // 2, 1)}), 2))
         Ns = None
         if N > 0:
             if self._t_blocks is not None and self._t_fold():
@@ -628,13 +637,13 @@ class KronEngine:
 
         # --- temporal hyperparameters: <Gt, dKt_k/d(ell_k, sigma2_k)>
         ntc, kinds, ells, s2 = self._temporal_spec(hp.temporal)
-        wsk = self._buf("ws_ktgrad", L.query("gpcsd_kt_grad_ws_doubles", nt, ntc))
+        wsk = self._buf("ws_ktgrad", self._q("gpcsd_kt_grad_ws_doubles", nt, ntc))
         self._call("gpcsd_kt_grad", nt, self._p(self.t_dev), ntc, kinds, ells, s2, self._p(Gt), self.ldt, self._p(wsk),
                    self._p(res, 8), stream())
 
         # --- spatial hyperparameters.  With U = A Kg:  dL/dR = 2 <dA, Gs U>,  dL/dell_k = <A, (Gs A) dKg_k>
         G = self.G
-        wsd = self._buf("ws_dot", L.query("gpcsd_dot_ws_doubles", nx * G))
+        wsd = self._buf("ws_dot", self._q("gpcsd_dot_ws_doubles", nx * G))
         GU = self._buf("GU", nx, G)
         self.gemm(0, nx, G, nx, Gs, self.ldx, 0, st["U"], G, 0, GU, G, 0)
         self._call("gpcsd_dot", nx, G, self._p(st["dA"]), G, self._p(GU), G, self._p(wsd), self._p(res, 4), stream())
