@@ -415,9 +415,12 @@ class KronEngine:
         folded time basis (gpcsd_centro_fold) -- Qt is block diagonal."""
         return bool(self.t_uniform and self.nt >= 32)
 
+    FOLD_MIN_NT = 128           # below this the evaluation is launch-bound and the extra launches of the fold cost more
+
     def _t_fold(self):
-        """Whether the trial data are moved to the folded time basis (same condition as the split)."""
-        return self._t_split()
+        """Whether the trial data are moved to the folded time basis: the split applies and the temporal contractions are
+        big enough for halving their flops to matter (configs[0]-sized problems are bound by the number of launches)."""
+        return self._t_split() and self.nt >= self.FOLD_MIN_NT
 
     def _eigh_temporal(self, Kt):
         """Eigen-factors of Kt.  On a uniform time grid Kt is symmetric Toeplitz, hence centrosymmetric, and the

@@ -162,9 +162,21 @@ def test_single_trial_and_ragged_trial_counts(cuda_lib):
         assert np.max(np.abs(grad - grad_o) / np.abs(grad_o)) < TOL_GRAD
 
 
-@pytest.mark.parametrize("nt,uniform", [(41, True), (64, True), (40, False)])
-def test_temporal_eigh_paths_agree_with_oracle(cuda_lib, nt, uniform):
-    """Uniform grid (even / odd nt) -> centrosymmetric split on two streams; jittered grid -> single syevd."""
+@pytest.mark.parametrize("nt,uniform,fold", [(41, True, False), (64, True, False), (40, False, False), (41, True, True),
+                                             (64, True, True), (131, True, True), (130, True, True)])
+def test_temporal_eigh_paths_agree_with_oracle(cuda_lib, nt, uniform, fold):
+    """Uniform grid (even / odd nt) -> centrosymmetric split, and (nt >= FOLD_MIN_NT, or forced here) the folded time basis
+    for the projection, the temporal SYRK and predict's back-projection; jittered grid -> one solve of order nt."""
+    from gpcsd_b200.engine import KronEngine
+    old_min = KronEngine.FOLD_MIN_NT
+    KronEngine.FOLD_MIN_NT = 32 if fold else 10 ** 9
+    try:
+        _temporal_paths(nt, uniform)
+    finally:
+        KronEngine.FOLD_MIN_NT = old_min
+
+
+def _temporal_paths(nt, uniform):
     from oracle import gpcsd_oracle as O, synth
     x, t = synth.geometry_1d(24, nt)
     if not uniform:
