@@ -409,7 +409,7 @@ def run_gpu(args):
             eval_probe(1, 0, False)                        # keep the probes' collective counts equal
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             t_eval = float(tt.item())
-        stagger_s[0] = t_eval
+        stagger_s[0] = t_eval * float(os.environ.get("GPCSD_BENCH_STAGGER", "1.0"))
     timed_steps(W, 0, False)
     if args.profile_step:
         # one steady-state SERIAL step between cudaProfilerStart/Stop for `ncu --profile-from-start off`

@@ -53,6 +53,14 @@ def _worker(rank, world, port, q):
     lo, hi = sh.bounds(lfp.shape[2])
     part = _partial_eval(om, lfp[:, :, lo:hi], lfp.shape[2], sh.det_fraction())
     tot = sh.allreduce_sum(part)
+    # the device-vector entry point falls back to the host path on gloo, and joins a CollectiveOrder rotation transparently
+    from gpcsd_b200.parallel import CollectiveOrder
+    order = CollectiveOrder(1)
+    sh.set_order(order, 0)
+    order.start()
+    tot_dev = sh.allreduce_device(torch.from_numpy(part.copy()))
+    order.stop()
+    assert np.array_equal(tot_dev, tot)
     ntot = sh.allreduce_sum(np.array([float(hi - lo)]))
     ll, g = O.loglik_and_grad(om, lfp)
     ok = abs(tot[0] - ll) <= 1e-10 * abs(ll) and np.max(np.abs(tot[1:] - g) / np.abs(g)) < 1e-9 and int(ntot[0]) == 11
