@@ -80,7 +80,7 @@ constexpr int TRD_WARPS = 16;                      // warps per CTA
 constexpr int TRD_RPW = TRD_MAXN / (TRD_CLUSTER * TRD_WARPS);   // rows per warp (2): row i lives in CTA i % 8, slot i / 8
 constexpr int TRD_NR = TRD_MAXN / 32;              // row elements per lane
 
-// -DGPCSD_EIG_PROF: clock64 phase timers of the cluster kernels (developer builds only; scratch/ubench/trd_prof.py)
+// -DGPCSD_EIG_PROF: clock64 phase timers of the cluster kernels (developer builds only; scripts/eig_prof_tridiag.py, scripts/eig_prof_dc.py, scripts/eig_trace_tridiag.py)
 #ifdef GPCSD_EIG_PROF
 __device__ long long g_eig_prof[64];
 #define EIG_PROF_DECL long long prof_t[32] = {0}; long long prof_last = clock64();
