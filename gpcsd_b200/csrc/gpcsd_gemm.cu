@@ -334,8 +334,10 @@ static int syrk_plan(int M, int nseg, int seglen, int& bmn, int& tiles_1d, int& 
   const long ntiles = (long)tiles_1d * (tiles_1d + 1) / 2;
   kbps = (seglen + BK - 1) / BK;
   total_kb = (long)nseg * kbps;
-  // whole waves: ntiles * nsplit <= 2 CTAs-worth per SM (1 resident CTA/SM -> 2 full waves, no ragged tail)
-  long ns = (2L * gp_num_sms()) / ntiles;
+  // whole waves: ntiles * nsplit <= 2 CTAs-worth per SM (1 resident CTA/SM -> 2 full waves, no ragged tail); with very few
+  // tiles (the half-order blocks of the folded bases: 3 tiles) ONE wave divides just as evenly and halves the partial tiles
+  // the reduction kernel has to read back (38 MB -> 19 MB at M = 250)
+  long ns = ((ntiles <= 4 ? 1L : 2L) * gp_num_sms()) / ntiles;
   const long min_kb = 8;  // at least 8 k-blocks per split
   if (ns > total_kb / min_kb) ns = total_kb / min_kb;
   if (ns < 1) ns = 1;
