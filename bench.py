@@ -395,6 +395,9 @@ def run_gpu(args):
         torch.cuda.synchronize()
         args.serial = prev
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()         # nvidia-smi needs ~0.1 s to start streaming: begin before the warm-up, all of it is under load
     serial_once(0, False)
     if not args.no_stagger:
         # one evaluation of one probe, wall clock (device drained before and after): the phase offset is half of it
@@ -420,12 +423,10 @@ def run_gpu(args):
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         if rank == 0:
+            sampler.stop()
             print(json.dumps({"profile_step": "done"}))
         return
     engines = [m._get_engine() for m in models]
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     # pass 1 (headline): the two probes evaluated concurrently
     for e in engines:
         e.n_launches = 0
