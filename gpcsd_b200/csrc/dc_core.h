@@ -23,6 +23,7 @@ namespace dc {
 
 constexpr double EPS = 1.1102230246251565e-16;   // 2^-53 (LAPACK dlamch('E'))
 constexpr int MAX_ITER = 80;
+constexpr double STEP_TOL = 1e-9;
 
 // reciprocal: on the device the IEEE-rounded MUFU.RCP64H + Newton sequence (~8 instructions) instead of the ~30-instruction
 // division; every quotient below is a * rcp(b), within 1.5 ulp, which is all the Gu-Eisenstat argument needs
@@ -192,9 +193,13 @@ DC_HD void secular_root(int k, int i, const double* dl, const double* w, double 
     }
     if (!(f * eta < 0.0)) eta = -f * rcp(dw);     // wrong direction (or NaN): Newton step
     double munew = mu + eta;
-    if (!(munew > lo && munew < hi)) munew = bracket_mid(lo, hi);
+    const bool inside = (munew > lo && munew < hi);
+    if (!inside) munew = bracket_mid(lo, hi);
     if (!(munew > lo && munew < hi) || munew == mu) break;       // bracket exhausted
     mu = munew;
+    // the rational iteration converges at least quadratically: after a step this small relative to the distance from the
+    // origin pole the next residual is below rounding, so the confirming evaluation is skipped
+    if (inside && fabs(eta) <= STEP_TOL * fabs(mu)) break;
   }
   mu_out = mu;
   org_out = org;
