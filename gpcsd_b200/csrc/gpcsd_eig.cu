@@ -5,18 +5,23 @@
 // it is the Amdahl term of every GPCSD evaluation (the 250-order halves of a 500-point temporal factor, the 192-order halves
 // of a Neuropixels spatial factor, comp_eig_D utility_functions.py:44-64).  Three kernels replace it:
 //
-//   1. tridiag_cluster_kernel   Householder tridiagonalisation M = H T H^T.  The matrix lives in the cluster's shared memory
-//                               (row-cyclic slabs, <= 64 KB per CTA); the reflector and the symv result are exchanged through
-//                               distributed shared memory, two cluster barriers per column.
+//   1. tridiag_cluster_kernel   Householder tridiagonalisation M = H T H^T.  Every matrix row lives in the registers of one
+//                               warp (row i in CTA i mod 8); ONE exchange per column through distributed shared memory
+//                               (st.async / bulk copies that complete transaction bytes on an mbarrier of the receiver):
+//                               no cluster barrier in the loop.  ~2.1 us per column.
 //   2. dc_cluster_kernel        Cuppen divide and conquer on T down to 1x1 leaves (ceil(log2 n) merge levels): per merge
-//                               LAPACK-style deflation, secular roots by bracketed two-pole rational iteration (one warp per
-//                               root, roots spread over the 128 warps of the cluster), Gu-Eisenstat recomputation of z for
-//                               numerically orthogonal eigenvectors, eigenvector update as a shared-memory tiled GEMM whose
-//                               A operand (z_j / (d_j - lambda_i)) is generated on the fly.  Small per-merge vectors are
-//                               broadcast through distributed shared memory, the eigenvector matrices ping-pong through L2.
-//                               The numerical core (dc_core.h) also compiles for the host: tests/test_dc_host.py checks it
-//                               against LAPACK without a GPU.
-//   3. backtransform_kernel     apply the Householder reflectors to every eigenvector (one warp per vector).
+//                               LAPACK-style deflation, secular roots by a bracketed two-pole rational iteration (1 to 32
+//                               lanes per root depending on the merge size), Gu-Eisenstat recomputation of z for numerically
+//                               orthogonal eigenvectors, eigenvector update as a shared-memory tiled GEMM whose A operand
+//                               (z_j / (d_j - lambda_i)) is generated on the fly.  Bottom levels (at least one merge node
+//                               per CTA) run CTA-locally; above, small per-merge vectors are broadcast through distributed
+//                               shared memory and the eigenvector matrices ping-pong through L2.  The numerical core
+//                               (dc_core.h) also compiles for the host: tests/test_dc_host.py checks it against LAPACK
+//                               without a GPU.
+//   3. back-transformation      n < 97: backtransform_kernel applies the reflectors to every eigenvector (one warp per
+//                               vector).  n >= 97: the top-level merge and the back-transformation are two full-GPU DMMA
+//                               GEMMs, QT = (C * Q_below) * H^T, with H^T formed by backtransform_kernel on a side stream
+//                               while the divide-and-conquer kernel runs (gpcsd_eigh_dc below).
 //
 // All matrices row-major; eigenvectors are stored as ROWS (Q^T), the convention of gpcsd_eigh.
 #include <cooperative_groups.h>
