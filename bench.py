@@ -171,7 +171,7 @@ def workload_config(n_gpus):
     return {"workload": "BASELINE.json configs[1]: GPCSD1D auditory-shaped, 2 probes x 24 ch x 500 t x 2000 trials per GPU, "
                         "per-electrode noise (P=30), a=-200 b=2600 ngl=100, loglik+grad",
             "eval_unit": "one loglik+grad over a 24x500x2000 trial block", "trials_per_gpu_per_probe": NTRIALS,
-            "global_trials_per_probe": NTRIALS * n_gpus, "parallelism": "trial-shard x%d, 1 allreduce of P+1 f64 per eval; the 2 probes run concurrently on 2 streams" % n_gpus,
+            "global_trials_per_probe": NTRIALS * n_gpus, "parallelism": "trial-shard x%d, 1 allreduce of the raw result vector (~70 f64) per eval; the 2 probes run concurrently on 2 host threads / streams, started half an evaluation apart" % n_gpus,
             "cache": "working set per step 2 x (Y+Z+B) = 1.15 GB >> 126 MB L2 (inputs larger than L2)"}
 
 
@@ -310,7 +310,7 @@ def run_gpu(args):
     stagger_s = [0.0]
 
     # The two probes are independent models: evaluate them concurrently, one host thread + CUDA stream each,
-    # so one probe's latency-bound cuSOLVER syevd overlaps the other's DMMA GEMMs (--serial disables this).
+    # so one probe's latency-bound eigensolve (16 SMs) overlaps the other's DMMA GEMMs (--serial disables this).
     from concurrent.futures import ThreadPoolExecutor
     streams = [torch.cuda.Stream(device=device) for _ in models]
     pool = ThreadPoolExecutor(max_workers=len(models))
@@ -326,7 +326,7 @@ def run_gpu(args):
     def run_steps(first, nsteps, upload):
         """nsteps evaluations of every probe.  Serial mode: probes one after the other inside each step.
         Concurrent mode: one free-running host thread per probe (no per-step join), so in steady state one
-        probe's host->device upload / syevd overlaps the other probe's GEMMs."""
+        probe's host->device upload / eigensolve overlaps the other probe's GEMMs."""
         if args.serial:
             for s in range(first, first + nsteps):
                 for p in range(len(models)):
