@@ -172,7 +172,7 @@ def workload_config(n_gpus):
                         "per-electrode noise (P=30), a=-200 b=2600 ngl=100, loglik+grad",
             "eval_unit": "one loglik+grad over a 24x500x2000 trial block", "trials_per_gpu_per_probe": NTRIALS,
             "global_trials_per_probe": NTRIALS * n_gpus, "parallelism": "trial-shard x%d, 1 allreduce of the raw result vector (~70 f64) per eval; the 2 probes run concurrently on 2 host threads / streams, started half an evaluation apart" % n_gpus,
-            "cache": "working set per step 2 x (Y+Z+B) = 1.15 GB >> 126 MB L2 (inputs larger than L2)"}
+            "cache": "working set per step 2 x (Y+Z+Zf+B) = 1.5 GB >> 126 MB L2 (inputs larger than L2)"}
 
 
 # ----------------------------------------------------------------------------------------------------
