@@ -29,6 +29,12 @@ import sys
 import threading
 import time
 
+if "reference" in sys.argv[1:] or "--impl=reference" in sys.argv[1:]:
+    # The CPU arm uses every host core whatever launched it: torch.distributed.run exports OMP_NUM_THREADS=1 to its
+    # workers, which halved the round-1 denominator at N > 1.  Must happen before numpy loads its BLAS.
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -106,25 +112,48 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port on host cores
 # ----------------------------------------------------------------------------------------------------
-def cpu_eval_seconds(sample_trials, reps=1):
-    """Time the CPU restatement (oracle.gpcsd_oracle.loglik_and_grad: the reference's covariance build,
-    two LAPACK eigh, Kronecker projection of every trial and the closed-form gradient) on a bounded sample
-    of one probe block.  Returns (seconds per evaluation of the sample, cores)."""
+def blas_threads():
+    """(threads the BLAS behind numpy will use, library name) -- printed next to every CPU number."""
+    try:
+        from threadpoolctl import threadpool_info
+        infos = [i for i in threadpool_info() if i.get("user_api") == "blas"]
+        if infos:
+            return int(max(i.get("num_threads", 1) for i in infos)), str(infos[0].get("internal_api", "blas"))
+    except Exception:
+        pass
+    return int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1)), "unknown"
+
+
+_CPU_CASE = {}
+
+
+def cpu_case(ntrials=NTRIALS):
+    """One probe block of the workload for the CPU arm: the oracle model of probe 0 and a full 24 x 500 x ntrials block
+    (values do not change the arithmetic performed)."""
+    if ntrials not in _CPU_CASE:
+        from oracle import synth
+        x, t = geometry()
+        th = true_hyper(0)
+        om = synth.model_1d(x, t, a=A_LO, b=B_HI, ngl=NGL, sig2n=th["sig2n"])
+        lfp = np.random.default_rng(7).standard_normal((NX, NT, ntrials))
+        _CPU_CASE[ntrials] = (om, lfp)
+    return _CPU_CASE[ntrials]
+
+
+def cpu_eval_seconds(ntrials=NTRIALS, reps=1, seed0=100):
+    """Time the CPU restatement (oracle.gpcsd_oracle.loglik_and_grad: the reference's covariance build, two LAPACK eigh,
+    Kronecker projection of every trial and the closed-form gradient) on ONE FULL probe block -- no extrapolation.
+    Returns the list of seconds per evaluation."""
     from oracle import gpcsd_oracle as O
     from oracle import synth
-    x, t = geometry()
-    th = true_hyper(0)
-    om = synth.model_1d(x, t, a=A_LO, b=B_HI, ngl=NGL, sig2n=th["sig2n"])
-    rng = np.random.default_rng(7)
-    lfp = rng.standard_normal((NX, NT, sample_trials))
-    O.loglik_and_grad(om, lfp[:, :, : max(8, sample_trials // 8)])   # warm BLAS threads
+    om, lfp = cpu_case(ntrials)
     ts = []
     for r in range(reps):
-        om_r = synth.perturbed(om, 100 + r)
+        om_r = synth.perturbed(om, seed0 + r)           # new hyperparameters every evaluation, like the GPU arm
         t0 = time.perf_counter()
         O.loglik_and_grad(om_r, lfp)
         ts.append(time.perf_counter() - t0)
-    return float(np.median(ts)), os.cpu_count()
+    return ts
 
 
 def cpu_predict_baseline(sample_trials=250):
@@ -139,30 +168,39 @@ def cpu_predict_baseline(sample_trials=250):
     t0 = time.perf_counter()
     O.predict_kron(om, lfp, x, t, "csd")
     dt = time.perf_counter() - t0
-    return {"value": sample_trials / dt, "unit": "trials/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": "oracle predict_kron (Kronecker-form numpy port) on 24x500x%d trials" % sample_trials}
+    nthr, blas = blas_threads()
+    return {"value": sample_trials / dt, "unit": "trials/s", "cores": nthr, "host_cpus": os.cpu_count(), "kind": "port",
+            "sample": "oracle predict_kron (Kronecker-form numpy port) on 24x500x%d trials (linear in trials; not "
+                      "extrapolated: the value is the sample's own rate)" % sample_trials}
 
 
 def run_reference(args, rank):
+    """CPU arm: the reference algorithm's restatement (oracle/, numpy + all BLAS threads) on the SAME unit of work as the
+    GPU arm -- one step = one loglik+grad over a full 24 x 500 x 2000 block for each of the two probes, new hyperparameters
+    every evaluation.  Nothing is extrapolated: every timed evaluation runs in full.  The unit ("eval" = one 2000-trial
+    block) does not depend on the GPU count, so the same denominator applies at every N (weak scaling multiplies the blocks,
+    not the block size).  Rank 0 only."""
     if rank != 0:
         return
-    sample = 500
-    per_step = []
-    for _ in range(args.warmup):
-        cpu_eval_seconds(sample)
-    for _ in range(args.steps):
-        # one step = NPROBES evals of a full block; measured on a quarter block per probe and scaled
-        s, cores = cpu_eval_seconds(sample)
-        per_step.append(s * (NTRIALS / sample) * NPROBES)
-    ms = 1e3 * float(np.mean(per_step))
-    value = NPROBES / (ms * 1e-3)
+    nthr, blas = blas_threads()
+    cpu_case()
+    for w in range(args.warmup):
+        cpu_eval_seconds(reps=NPROBES, seed0=50 + NPROBES * w)
+    t0 = time.perf_counter()
+    n = 0
+    for s in range(args.steps):
+        n += len(cpu_eval_seconds(reps=NPROBES, seed0=100 + NPROBES * s))
+    total = time.perf_counter() - t0
+    ms = 1e3 * total / args.steps
+    value = n / total
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(args.gpus),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                             "sample": "oracle loglik_and_grad (numpy/LAPACK restatement of loglik + closed-form "
-                                       "gradient; HIPS autograd not installable) on 24x500x%d trials, time scaled x%d "
-                                       "to a 2000-trial block" % (sample, NTRIALS // sample)},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthr, "host_cpus": os.cpu_count(), "blas": blas,
+                             "kind": "port",
+                             "sample": "oracle loglik_and_grad (numpy/LAPACK restatement of loglik + closed-form gradient; "
+                                       "the reference is pure Python and HIPS autograd is not installable, so kind = port) "
+                                       "on FULL 24x500x2000 blocks, %d evaluations timed, none extrapolated" % n},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -178,6 +216,89 @@ def workload_config(n_gpus):
 # ----------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------
+def check_sharded_parity(models, thetas, streams, device, world, torch, dist):
+    """N > 1, during warm-up: the trial-sharded evaluation (one all-reduce of the raw result vector) must equal the sum over
+    ranks of UNSHARDED evaluations of every rank's own slab -- loglik and its gradient are sums over trials plus a log-det
+    term proportional to the trial count (gpcsd1d.py:122-128), so the per-rank values add up exactly.  The per-rank values are
+    all-gathered and summed in rank order on the host.  Asserts 1e-12 (loglik) / 1e-11 (gradient, floor 1e-6 of the largest
+    component); returns the measured figures for the JSON line."""
+    from gpcsd_b200.engine import KronEngine
+    out = {"loglik_rel": 0.0, "grad_rel": 0.0}
+    for p, m in enumerate(models):
+        with torch.cuda.stream(streams[p]):
+            m._set_tparams(thetas[p][0], False)
+            hp = m._hyperparams()
+            eng = m._get_engine()
+            ll, g = eng.loglik_grad(hp)                                   # sharded: all-reduced over the ranks
+            loc = KronEngine(1, m.x, m.t, m._quadrature(), group=None, jitter=m.JITTER)
+            loc.share_data_with(eng)
+            loc.ntrials_total = loc.ntrials                                # this rank's slab as a model of its own
+            ll_l, g_l = loc.loglik_grad(hp)
+            v = torch.tensor([ll_l] + list(g_l), dtype=torch.float64, device=device)
+            parts = [torch.zeros_like(v) for _ in range(world)]
+            dist.all_gather(parts, v)
+            tot = np.zeros(v.numel())
+            for q in parts:                                                # fixed rank order
+                tot += q.cpu().numpy()
+            del loc
+        rel_ll = abs(ll - tot[0]) / abs(tot[0])
+        rel_g = float(np.max(np.abs(g - tot[1:]) / np.maximum(np.abs(tot[1:]), 1e-6 * np.max(np.abs(tot[1:])))))
+        out["loglik_rel"], out["grad_rel"] = max(out["loglik_rel"], rel_ll), max(out["grad_rel"], rel_g)
+    if not (out["loglik_rel"] < 1e-12 and out["grad_rel"] < 1e-11):
+        raise SystemExit("sharded parity FAILED: %r" % (out,))
+    torch.cuda.synchronize()
+    return out
+
+
+def secondary_lines(torch, device, K):
+    """Driver-visible numbers for the other single-GPU configurations of BASELINE.json (N = 1 only): device-resident
+    loglik+grad through the public model classes, CUDA events around K evaluations after warm-up; hyperparameters change every
+    evaluation.  LFP is N(0,1) generated on the device (the arithmetic does not depend on the values)."""
+    from gpcsd_b200.gpcsd1d import GPCSD1D
+    from gpcsd_b200.gpcsd2d import GPCSD2D
+    out = []
+
+    def run(model, tp0, nsteps, label, extra):
+        rng = np.random.default_rng(99)
+        seq = [tp0 + 0.05 * rng.standard_normal(tp0.shape) for _ in range(nsteps + 3)]
+        for k in range(3):
+            model.obj_fun_and_grad(seq[k])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(nsteps):
+            model.obj_fun_and_grad(seq[3 + k])
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / nsteps
+        d = {"workload": label, "metric": METRIC, "value": 1e3 / ms, "unit": UNIT, "ms_per_eval": ms, "steps": nsteps}
+        d.update(extra)
+        out.append(d)
+
+    # configs[0]: GPCSD1D 24 x 50 x 50 (sim_from_gp_1D.py shapes and true parameters), scalar noise, P = 7
+    np.random.seed(3)
+    x = np.linspace(0.0, 2300.0, 24)[:, None]
+    t = np.linspace(0.0, 50.0, 50)[:, None]
+    lfp = torch.randn((24, 50, 50), dtype=torch.float64, device=device).cpu().numpy()
+    m0 = GPCSD1D(lfp, x, t)
+    tp0 = np.log(np.array([100.0 / 100, 200.0 / 100, 20.0, 0.5, 5.0, 0.7, 1e-2]))
+    run(m0, tp0, max(50, 10 * K), "BASELINE.json configs[0]: GPCSD1D 24 ch x 50 t x 50 trials, scalar noise (P=7), one model, "
+        "evaluations issued one after the other", {"flops_per_eval_algorithmic": 4.0 * 50 * 24 * 50 * (24 + 50)})
+    # configs[2]: GPCSD2D Neuropixels-shaped 384 ch (4 x 192 checkerboard) x 250 t x 500 trials, ngl 30 x 120, eps = 1, P = 8
+    ch = np.arange(384)
+    X = np.stack([np.array([16.0, 48.0, 0.0, 32.0])[ch % 4], 20.0 * np.floor(ch / 2)], axis=1)
+    t2 = (0.4 * np.arange(250, dtype=np.float64))[:, None]
+    lfp2 = torch.randn((384, 250, 500), dtype=torch.float64, device=device).cpu().numpy()
+    m2 = GPCSD2D(lfp2, X, t2, a1=-16.0, b1=64.0, a2=-100.0, b2=float(X[:, 1].max()) + 100.0, ngl1=30, ngl2=120, eps=1.0)
+    tp2 = np.log(np.array([100.0 / 100, 40.0 / 100, 200.0 / 100, 5.0, 0.5 / 300.0, 1.0, 0.7 / 300.0, 0.5]))
+    run(m2, tp2, max(5, K), "BASELINE.json configs[2]: GPCSD2D Neuropixels-shaped 384 ch x 250 t x 500 trials, ngl 30x120, eps=1, "
+        "scalar noise (P=8)", {"flops_per_eval_algorithmic": 4.0 * 500 * 384 * 250 * (384 + 250)})
+    out[-1]["tflops_algorithmic"] = out[-1]["flops_per_eval_algorithmic"] / (out[-1]["ms_per_eval"] * 1e-3) * 1e-12
+    del m0, m2
+    torch.cuda.empty_cache()
+    return out
+
+
 def make_models(device, world, torch, groups=None):
     """Two GPCSD1D models (one per probe) set up like fit_gpcsd_baseline.py:80-89, with model-matched
     synthetic LFP generated on the device (generator only; not part of the measured path)."""
@@ -399,6 +520,9 @@ def run_gpu(args):
     if rank == 0:
         sampler.start()         # nvidia-smi needs ~0.1 s to start streaming: begin before the warm-up, all of it is under load
     serial_once(0, False)
+    sharded_parity = None
+    if world > 1:
+        sharded_parity = check_sharded_parity(models, thetas, streams, device, world, torch, dist)
     if not args.no_stagger:
         # one evaluation of one probe, wall clock (device drained before and after): the phase offset is half of it
         torch.cuda.synchronize()
@@ -527,6 +651,40 @@ def run_gpu(args):
                             "api": "GPCSD1D.predict(x, t, type='csd') -> csd_pred + csd_pred_list as host arrays"},
                     "steps": KP, "config": "z = the 24 electrode sites, t* = t, per-component (SE, Matern) + summed CSD"}
 
+    # predict roofline: the temporal back-projection GEMM (two half-order blocks per temporal component and probe), timed
+    # with CUDA events in a serial pass (one probe at a time, device drained in between)
+    for e in engines:
+        e.timers = {"predict_backproject": []}
+    for _ in range(2):
+        for p in range(len(models)):
+            predict_probe(p, False)
+            torch.cuda.synchronize()
+    d = [a.elapsed_time(b) for e in engines for (a, b) in e.timers["predict_backproject"]]
+    for e in engines:
+        e.timers = None
+    pred_kernel_ms = float(np.mean(d)) if d else None
+    pred_flops = 2.0 * (NT // 2) ** 2 * NTRIALS * NX            # one block launch: nz = NX batched (NT/2)^2 x trials products
+
+    # strong scaling (what configs[1] literally says: 2000 trials split over the N GPUs): every rank keeps 2000/N trials
+    strong = None
+    if world > 1:
+        nloc = NTRIALS // world
+        for m in models:
+            m.lfp = np.ascontiguousarray(m.lfp[:, :, :nloc])
+            m._invalidate_lfp()
+        for p, m in enumerate(models):
+            with torch.cuda.stream(streams[p]):
+                m._get_engine()
+        torch.cuda.synchronize()
+        serial_once(0, False)
+        timed_steps(W, 0, False)
+        ms_strong = timed_steps(K, W, False)
+        strong = {"scaling": "strong", "value": NPROBES * K / (ms_strong * 1e-3), "unit": "evals/s of the full 2000-trial model",
+                  "ms_per_step": ms_strong / K, "trials_per_gpu_per_probe": nloc, "global_trials_per_probe": nloc * world,
+                  "amdahl_term": "covariance build + the two eigendecompositions are replicated on every rank and do not shrink "
+                                 "with N (gpcsd_eigh_dc %.3f ms per evaluation, see kernel_ms); the trial-proportional GEMM/SYRK "
+                                 "work divides by N" % kt["gpcsd_eigh_dc"][0]}
+
     evals_per_step = NPROBES * world
     value = evals_per_step * K / (ms_total * 1e-3)
     e2e_value = evals_per_step * K / (ms_e2e * 1e-3)
@@ -568,13 +726,28 @@ def run_gpu(args):
                 "kernel_ms": {k: {"avg_ms": v[0], "calls": v[1]} for k, v in kt.items()},
                 "last_nll": [float(last[p][0]) for p in range(NPROBES)],
                 "predict": predict_line}
+        if pred_kernel_ms:
+            ach = pred_flops / (pred_kernel_ms * 1e-3) * 1e-12
+            line["predict"]["roofline"] = {
+                "bound": "tensor", "kernel": "tma_gemm_kernel<NN,EPI_STORE> (gpcsd_dgemm: temporal back-projection (C_k U)(V_z) of one "
+                                             "half-order block of the folded time basis, batched over the nz = 24 output sites)",
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "algorithmic_flops_per_launch": pred_flops, "avg_launch_ms": pred_kernel_ms,
+                "peak_source": "in-run cuBLAS DGEMM 4096^3 (FP64)"}
+        if sharded_parity is not None:
+            line["sharded_parity_rel"] = sharded_parity
+        if strong is not None:
+            line["strong"] = strong
+        if world == 1 and not args.no_secondary:
+            line["secondary"] = secondary_lines(torch, device, K)
         if world == 1 and not args.no_cpu_baseline:
-            sample = 500
-            secs, cores = cpu_eval_seconds(sample, reps=3)
-            full = secs * NTRIALS / sample
-            line["cpu_baseline"] = {"value": 1.0 / full, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "oracle loglik_and_grad (numpy/LAPACK restatement; closed-form gradient) on "
-                                              "24x500x%d trials, median of 3, time scaled x%d to a 2000-trial block" % (sample, NTRIALS // sample)}
+            nthr, blas = blas_threads()
+            cpu_eval_seconds(reps=1, seed0=90)                      # warm the BLAS threads
+            secs = cpu_eval_seconds(reps=5)
+            line["cpu_baseline"] = {"value": 1.0 / float(np.median(secs)), "unit": UNIT, "cores": nthr, "host_cpus": os.cpu_count(),
+                                    "blas": blas, "kind": "port",
+                                    "sample": "oracle loglik_and_grad (numpy/LAPACK restatement; closed-form gradient) on one FULL "
+                                              "24x500x2000 block, median of 5 evaluations, nothing extrapolated"}
             line["predict"]["cpu_baseline"] = cpu_predict_baseline()
         print(json.dumps(line))
     if world > 1:
@@ -588,6 +761,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the configs[0]/[2] secondary lines (N = 1)")
     ap.add_argument("--serial", action="store_true", help="evaluate the two probes one after the other")
     ap.add_argument("--no-stagger", action="store_true", help="start the probes' evaluation loops together (no phase offset)")
     ap.add_argument("--profile-step", action="store_true", help="run warm-up then ONE step inside cudaProfilerStart/Stop")

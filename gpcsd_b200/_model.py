@@ -28,6 +28,16 @@ def _is_scalar(v):
     return np.isscalar(v) or np.ndim(v) == 0
 
 
+def _dlpdf(prior, v):
+    """d lpdf / d value.  The reference's prior protocol is lpdf + sample only (priors.py:14-54; autograd differentiates
+    lpdf): a user-supplied prior without the closed-form `dlpdf` gets a 4th-order central difference of its lpdf."""
+    f = getattr(prior, "dlpdf", None)
+    if f is not None:
+        return f(v)
+    h = 1e-4 * abs(v)
+    return (-prior.lpdf(v + 2 * h) + 8 * prior.lpdf(v + h) - 8 * prior.lpdf(v - h) + prior.lpdf(v - 2 * h)) / (12 * h)
+
+
 class GPCSDModelBase:
     DIM = None
     JITTER = None
@@ -156,7 +166,7 @@ class GPCSDModelBase:
         lp = 0.0
         for p, v in zip(pris, vals):
             lp = lp + p.lpdf(v)
-        dlp = np.array([p.dlpdf(v) if v > 0 else 0.0 for p, v in zip(pris, vals)])
+        dlp = np.array([_dlpdf(p, v) if v > 0 else 0.0 for p, v in zip(pris, vals)])
         return lp, dlp, np.array(vals, dtype=np.float64)
 
     def obj_fun(self, tparams, fix_R=False):
@@ -214,7 +224,7 @@ class GPCSDModelBase:
             lp = 0.0
             for p, v in zip(priors, vals):
                 lp = lp + p.lpdf(v)
-            dlp = np.array([p.dlpdf(v) if v > 0 else 0.0 for p, v in zip(priors, vals)])
+            dlp = np.array([_dlpdf(p, v) if v > 0 else 0.0 for p, v in zip(priors, vals)])
             temporal = [(kinds[k], float(vals[1 + nsp + 2 * k]), float(vals[2 + nsp + 2 * k])) for k in range(len(kinds))]
             sig = float(vals[nslots]) if noise_scalar else np.array(vals[nslots:])
             hp = HyperParams(R=float(vals[0]), ells=tuple(float(v) for v in vals[1:1 + nsp]), temporal=temporal, sig2n=sig, eps=eps)
@@ -240,6 +250,10 @@ class GPCSDModelBase:
         # from the same point whatever the world size) and optimises only its own share of them.
         shard = RestartShard(getattr(self, "_restart_group", None))
         starts = [self._sample_tparams0(fix_R) for _ in range(n_restarts)]
+        # Distributed runs: rank 0's starting points (and its R when fix_R) are THE starting points -- ranks whose numpy RNG
+        # state differs would otherwise optimise different trajectories (trial sharding: different numbers of collectives
+        # per rank, i.e. a hang; restart sharding: restart i not reproducible across world sizes).
+        starts = self._broadcast_from_rank0(starts, fix_R)
         mine = [i for i in range(n_restarts) if shard.mine(i)]
         # Restarts are independent: run up to n_workers of them concurrently, one host thread + CUDA stream + engine
         # workspace each (all sharing the uploaded LFP), so one restart's latency-bound syevd overlaps another's GEMMs.
@@ -310,6 +324,21 @@ class GPCSDModelBase:
             print('Best index termination message')
             print(term_msg[best_ind])
         self._set_tparams(params[best_ind], fix_R)
+
+    def _broadcast_from_rank0(self, starts, fix_R):
+        import torch.distributed as dist
+        for grp in (getattr(self, "_group", None), getattr(self, "_restart_group", None)):
+            if grp is None or grp is False or not (dist.is_available() and dist.is_initialized()):
+                continue
+            g = None if grp is True else grp
+            if dist.get_world_size(g) == 1:
+                continue
+            box = [(starts, float(self.R['value']))]
+            dist.broadcast_object_list(box, src=dist.get_global_rank(g, 0) if g is not None else 0, group=g)
+            starts, r0 = box[0]
+            if fix_R:
+                self.R['value'] = r0
+        return starts
 
     # ------------------------------------------------------------------ prediction
     def predict(self, z, t, type="csd"):

@@ -115,9 +115,9 @@ class KronEngine:
     _LAUNCHES = {"gpcsd_project_quad": 2, "gpcsd_wsyrk": 2, "gpcsd_eig_D": 2, "gpcsd_kt_grad": 2, "gpcsd_dot": 2,
                  "gpcsd_eigh_dc": 3}
 
-    def _call(self, name, *args):
+    def _call(self, name, *args, tag=None):
         self.n_launches += self._LAUNCHES.get(name, 1)
-        timers = self.timers.get(name) if self.timers else None
+        timers = self.timers.get(tag or name) if self.timers else None
         if timers is None:
             return L.call(name, *args)
         # bench.py roofline: CUDA events on the launching stream around this ABI call
@@ -463,11 +463,36 @@ class KronEngine:
         self._t_blocks = (UsT, lds, UaT, lda)
         return QT, W, [info_s, info_a]
 
-    def _factorize(self, hp, jitter, want_grad):
+    def _given_factors(self, st, factors):
+        """Caller-supplied eigen-factors (Qs, ls, Qt, lt) -- host arrays with eigenvectors as COLUMNS, as np.linalg.eigh
+        returns them in comp_eig_D (utility_functions.py:58-59) -- uploaded in place of the eigensolvers' output.  This is the
+        kernel-level entry of SURVEY.md section 6: with identical factors on both sides everything downstream of comp_eig_D
+        (projection, quadratic form, SYRKs, gradient cores, rotations, covariance-derivative contractions) must agree with
+        the oracle to rounding, per-electrode noise included."""
+        Qs, ls, Qt, lt = (np.asarray(a, dtype=np.float64) for a in factors)
+        if Qs.shape != (self.nx, self.nx) or Qt.shape != (self.nt, self.nt) or ls.shape != (self.nx,) or lt.shape != (self.nt,):
+            raise ValueError("factors must be (Qs (nx,nx), ls (nx,), Qt (nt,nt), lt (nt,))")
+        self._s_blocks = self._t_blocks = None
+        QsT, QtT = self._buf("QT_s", self.nx, self.ldx), self._buf("QT_t", self.nt, self.ldt)
+        QsT[:, :self.nx].copy_(self._dev(Qs.T))
+        QtT[:, :self.nt].copy_(self._dev(Qt.T))
+        st["QsT"], st["ls"], st["QtT"], st["lt"] = QsT, self._dev(ls), QtT, self._dev(lt)
+        st["infos"] = [torch.zeros(1, dtype=torch.int32, device=self.device)]
+        if self.Y is not None:
+            if self._y_ready is not None:
+                torch.cuda.current_stream(self.device).wait_event(self._y_ready)
+            st["Z"] = self._buf("Z", self.nx, self.nt, self.ldn)
+            row = self.nt * self.ldn
+            self.gemm(0, self.nx, row, self.nx, QsT, self.ldx, 0, self.Y, row, 0, st["Z"], row, 0)
+
+    def _factorize(self, hp, jitter, want_grad, factors=None):
         """Covariances -> eigen-factors -> 1/D and its reductions (comp_eig_D, utility_functions.py:44-64).
         The spatial and the temporal eigenproblems are independent and run on separate streams."""
         st = {}
         st["Ks"], st["A"], st["dA"], st["U"], st["kern"] = self._spatial_cov(hp, jitter, want_grad)
+        if factors is not None:
+            self._given_factors(st, factors)
+            return self._finish_factorize(st, hp)
         main = torch.cuda.current_stream(self.device)
         side = self._side_streams()[0]
         ks_ready = torch.cuda.Event()
@@ -504,6 +529,9 @@ class KronEngine:
         st["QtT"], st["lt"], infos_t = self._eigh_temporal(st["Kt"])
         main.wait_event(s_done)
         st["infos"] = infos_s + infos_t
+        return self._finish_factorize(st, hp)
+
+    def _finish_factorize(self, st, hp):
         s_host = np.atleast_1d(np.asarray(hp.sig2n, dtype=np.float64))
         if len(s_host) not in (1, self.nx):
             raise ValueError("sig2n must be a scalar or have one entry per electrode")
@@ -553,29 +581,57 @@ class KronEngine:
         if any(bool(torch.any(i != 0).item()) for i in st["infos"]):
             raise np.linalg.LinAlgError("Eigenvalues did not converge")
 
+    def _theta_check_piece(self, hp):
+        """Trial-sharded evaluations are only meaningful if every rank evaluates the SAME hyperparameters (ranks that seeded
+        numpy differently would silently sum likelihood terms of different models).  Two extra entries ride on the
+        evaluation's one all-reduce: c/world and c^2/world for a fixed weighted checksum c of the hyperparameters; after the
+        sum they are mean(c) and mean(c^2), and a non-zero variance means the ranks disagree.  None when not sharded."""
+        if not (self.shard.enabled and self.shard.world > 1):
+            return None
+        v = np.concatenate([[hp.R], np.asarray(hp.ells, dtype=np.float64), np.array([[e, s] for _, e, s in hp.temporal]).reshape(-1),
+                            np.atleast_1d(np.asarray(hp.sig2n, dtype=np.float64))])
+        c = float(np.dot(np.sin(1.0 + np.arange(v.size)), np.log(np.maximum(v, 1e-300))))
+        return self._dev(np.array([c, c * c]) / self.shard.world)
+
+    @staticmethod
+    def _theta_check(flat, have):
+        """Strip the checksum pair appended by _theta_check_piece and raise if the ranks' hyperparameters differ."""
+        if not have:
+            return flat
+        mean, meansq = flat[-2], flat[-1]
+        if abs(meansq - mean * mean) > 1e-9 * max(abs(meansq), 1e-300):
+            raise RuntimeError("trial-sharded evaluation: the ranks hold different hyperparameters (checksum variance %.3e); "
+                               "seed numpy identically on every rank or broadcast the parameters" % (meansq - mean * mean))
+        return flat[:-2]
+
     @staticmethod
     def _info_piece(st):
         """The eigensolvers' info flags as one float64 device vector (>= 0 entries), so they travel with the result
         instead of costing a device->host read each."""
         return torch.cat([i.reshape(-1) for i in st["infos"]]).abs().to(F64)
 
-    def loglik(self, hp):
-        """Marginal log-likelihood (gpcsd1d.py:113-128 / gpcsd2d.py:136-151); all-reduced over trial shards."""
-        st = self._factorize(hp, jitter=True, want_grad=False)
+    def loglik(self, hp, factors=None):
+        """Marginal log-likelihood (gpcsd1d.py:113-128 / gpcsd2d.py:136-151); all-reduced over trial shards.
+        factors: optional caller-supplied (Qs, ls, Qt, lt), see _given_factors."""
+        st = self._factorize(hp, jitter=True, want_grad=False, factors=factors)
         self._project(st)
         # every term is linear in the entries of `flat` (trial sums add up over the shards; the replicated log-det term is
         # weighted 1/world), so the raw vector is all-reduced on the device and assembled once
         pieces = [st["sums"][:4], st["sums_b"] if st["sums_b"] is not None else st["sums"][:2] * 0.0, self._info_piece(st)]
-        flat = self.shard.allreduce_device(torch.cat(pieces))
+        chk = self._theta_check_piece(hp)
+        if chk is not None:
+            pieces.append(chk)
+        flat = self._theta_check(self.shard.allreduce_device(torch.cat(pieces)), chk is not None)
         if np.any(flat[6:] != 0):
             raise np.linalg.LinAlgError("Eigenvalues did not converge")
         f = self.shard.det_fraction()
         return float(-0.5 * self.ntrials_total * f * flat[2] - 0.5 * (flat[0] + flat[4]))
 
-    def loglik_grad(self, hp):
-        """(loglik, d loglik / d natural parameters) in the order R, ell(s), (ell_t, sigma2_t)..., sig2n[...]."""
+    def loglik_grad(self, hp, factors=None):
+        """(loglik, d loglik / d natural parameters) in the order R, ell(s), (ell_t, sigma2_t)..., sig2n[...].
+        factors: optional caller-supplied (Qs, ls, Qt, lt) used instead of the eigensolvers (see _given_factors)."""
         nx, nt, ldn, N = self.nx, self.nt, self.ldn, self.ntrials
-        st = self._factorize(hp, jitter=True, want_grad=True)
+        st = self._factorize(hp, jitter=True, want_grad=True, factors=factors)
         Bm = self._project(st)
         res = st["sums"]
         stream = self._stream
@@ -664,10 +720,13 @@ class KronEngine:
         ninfo = sum(int(i.numel()) for i in st["infos"])
         pieces.append(st["sums_b"] if st["sums_b"] is not None else res[:2] * 0.0)
         pieces.append(self._info_piece(st))
+        chk = self._theta_check_piece(hp)
+        if chk is not None:
+            pieces.append(chk)
         # every term below is linear in the entries of `flat` (trial sums add up over the shards, the replicated
         # trial-independent terms carry the weight f = 1/world): all-reduce the raw vector on the device (NCCL, on this
         # stream), ONE device->host read, then the O(P) host assembly
-        flat = self.shard.allreduce_device(torch.cat([p.reshape(-1) for p in pieces]))
+        flat = self._theta_check(self.shard.allreduce_device(torch.cat([p.reshape(-1) for p in pieces])), chk is not None)
         if np.any(flat[-ninfo:] != 0):
             raise np.linalg.LinAlgError("Eigenvalues did not converge")
         flat = flat[:-ninfo]
@@ -692,7 +751,7 @@ class KronEngine:
         self.gemm(0, n, n, n, Q, ld, 0, T1, ld, 0, Gm, ld, 0)
         return Gm
 
-    def predict(self, hp, z, tstar, kind="csd", to_host=True):
+    def predict(self, hp, z, tstar, kind="csd", to_host=True, factors=None):
         """Posterior mean of CSD and/or LFP at (z, t*) per temporal component and summed
         (gpcsd1d.py:248-293 / gpcsd2d.py:289-334), in Kronecker form:
             out_k[:, :, r] = (Kc^T Qs) ((Qs^T Y_r Qt) / D) (Qt^T Kt*_k),   Kt*_k = Kt_k(t*, t)
@@ -705,7 +764,7 @@ class KronEngine:
         if ts.shape[0] != nt:
             raise ValueError("shapes (%d,%d) and (%d,%d) not aligned: dim 1 != dim 0"
                              % (nz * nt, nx * ts.shape[0], nx * nt, self.ntrials_total))
-        st = self._factorize(hp, jitter=False, want_grad=False)
+        st = self._factorize(hp, jitter=False, want_grad=False, factors=factors)
         Bm = self._project(st)
         Qs = self._buf("Q_s", nx, self.ldx)
         Qt = self._buf("Q_t", nt, self.ldt)
@@ -764,9 +823,9 @@ class KronEngine:
                     self.gemm(1, m, m, m, Ca, lda, 0, UaT, lda, 0, Ta, lda, 0)             # Ca Ua
                     outf = self._buf("pred_outf", nz, nt, ldn)
                     self._call("gpcsd_dgemm", 0, ms, N, ms, self._p(Ts), lds, 0, self._p(V), ldn, nt * ldn, self._p(outf), ldn,
-                               nt * ldn, nz, self._stream())
+                               nt * ldn, nz, self._stream(), tag="predict_backproject")
                     self._call("gpcsd_dgemm", 0, m, N, m, self._p(Ta), lda, 0, self._p(V, ms * ldn), ldn, nt * ldn,
-                               self._p(outf, ms * ldn), ldn, nt * ldn, nz, self._stream())
+                               self._p(outf, ms * ldn), ldn, nt * ldn, nz, self._stream(), tag="predict_backproject")
                     self._call("gpcsd_centro_unfold", nz, nt, ldn, self._p(outf), self._p(out), self._stream())
                 else:
                     Tk = self._buf("Tk", nt, self.ldt)           # Tk = Kt*_k^T Qt

@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import engine_from_oracle, relerr
+from helpers import engine_from_oracle, relerr, scaled_rel, ulp_sensitivity
 
 pytestmark = pytest.mark.gpu
 
@@ -28,6 +28,14 @@ def solver_spread(fn):
 def grad_tol(om, lfp):
     from oracle import gpcsd_oracle as O
     return max(TOL_GRAD, 10.0 * solver_spread(lambda e: O.loglik_and_grad(om, lfp, eigh=e)[1]))
+
+
+def vector_noise_grad_tol(om, lfp):
+    """Gate for the per-electrode-noise gradient: north_star's 1e-9, or 4 x the MEASURED sensitivity of the reference
+    formula's own result to 1-ulp perturbations of the matrices it hands to eigh (helpers.ulp_sensitivity) where that is
+    larger -- the function depends on eigenvector identity (utility_functions.py:54-57)."""
+    sens = ulp_sensitivity(om, lfp)
+    return max(TOL_GRAD, 4.0 * sens), sens
 
 
 def _model_from_golden_1d(g):
@@ -107,9 +115,9 @@ def test_grad_2d(cuda_lib, golden_dir):
     assert np.max(np.abs(grad - grad_o) / np.abs(grad_o)) < TOL_GRAD
 
 
-def test_grad_vector_noise_kernel_level(cuda_lib, golden_dir):
+def test_grad_vector_noise_end_to_end(cuda_lib, golden_dir):
     """Per-electrode noise enters by spatial EIGEN index (util:54-57) so loglik depends on eigenvector
-    identity; parity is checked against the oracle's closed form (same formula, numpy eigh)."""
+    identity; end-to-end parity (own eigensolver vs numpy eigh inside the oracle's closed form)."""
     from oracle import gpcsd_oracle as O
     g = np.load(os.path.join(golden_dir, "gpcsd1d_vecnoise.npz"))
     om = _model_from_golden_1d(g)
@@ -117,9 +125,13 @@ def test_grad_vector_noise_kernel_level(cuda_lib, golden_dir):
     ll, grad = eng.loglik_grad(hp)
     ll_o, grad_o = O.loglik_and_grad(om, g["lfp"])
     assert len(grad) == 6 + 24
-    assert abs(ll - ll_o) / abs(ll_o) < 1e-8
-    # eigenvector-identity conditioning: looser gate, stated
-    assert np.max(np.abs(grad - grad_o) / np.maximum(np.abs(grad_o), 1e-6 * np.max(np.abs(grad_o)))) < 1e-4
+    assert abs(ll - ll_o) / abs(ll_o) < TOL_LL
+    # eigenvector-identity conditioning: the gate follows the measured 1-ulp sensitivity of the
+    # reference formula on these inputs, not a constant; tests/test_gpu_factor_parity.py holds the identical-factor check
+    tol, sens = vector_noise_grad_tol(om, g["lfp"])
+    rel = scaled_rel(grad, grad_o)
+    print("\n[vector noise, golden] grad rel max %.2e; reference formula's 1-ulp sensitivity %.2e -> gate %.1e" % (rel.max(), sens, tol))
+    assert rel.max() < tol
 
 
 @pytest.mark.parametrize("name,is2d", [("gpcsd1d_cfg1", False), ("gpcsd1d_lownoise", False), ("gpcsd2d_small", True)])

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import engine_from_oracle, hp_from_oracle, relerr
+from helpers import engine_from_oracle, hp_from_oracle, relerr, scaled_rel, ulp_sensitivity
 
 pytestmark = pytest.mark.gpu
 
@@ -42,11 +42,29 @@ def test_config2_auditory_full_size(cuda_lib):
     dt = time.perf_counter() - t0
     ll_o = O.loglik(om2, lfp)                                   # the reference's literal trial loop
     assert abs(ll - ll_o) / abs(ll_o) < 1e-9
-    # full 30-component gradient against the oracle's closed form (per-electrode noise: eigenvector-identity
-    # conditioned, SURVEY.md section 6 -> 1e-4 on the noise components, 1e-7 on the kernel hyperparameters)
+    # full 30-component gradient against the oracle's closed form.  Per-electrode noise makes the function depend on
+    # eigenvector identity: the gate is north_star's 1e-9 or 4 x the MEASURED sensitivity of the
+    # reference formula itself to 1-ulp perturbations of the matrices handed to eigh (helpers.ulp_sensitivity; measured on a
+    # 250-trial subset to bound the CPU time), whichever is larger
+    sens = ulp_sensitivity(om2, lfp[:, :, :250], nseeds=3)
+    tol = max(1e-9, 4.0 * sens)
+    sc = scaled_rel
     _, grad_o = O.loglik_and_grad(om2, lfp)
-    rel = np.abs(grad - grad_o) / np.maximum(np.abs(grad_o), 1e-6 * np.max(np.abs(grad_o)))
-    assert np.max(rel[:6]) < 1e-7 and np.max(rel[6:]) < 1e-4, rel
+    rel = sc(grad, grad_o)
+    print("\n[config2] vector-noise grad rel max %.2e (kernel params %.2e, noise %.2e); reference formula's 1-ulp sensitivity "
+          "%.2e -> gate %.1e" % (rel.max(), rel[:6].max(), rel[6:].max(), sens, tol))
+    assert rel.max() < tol, rel
+    # identical factors on both sides (kernel level): 1e-12
+    fac = tuple(np.linalg.eigh(K) for K in (om2.Ks(jitter=True), om2.Kt()))
+    fac = (fac[0][1], fac[0][0], fac[1][1], fac[1][0])
+    ll_f, grad_f = eng.loglik_grad(hp, factors=fac)
+    ll_fo, grad_fo = O.loglik_and_grad(om2, lfp, eigh=lambda K: (fac[1], fac[0]) if K.shape[0] == 24 else (fac[3], fac[2]))
+    relf = sc(grad_f, grad_fo)
+    print("[config2] identical factors: loglik rel %.2e, grad rel max: spatial (R, ell) %.2e, all others %.2e"
+          % (abs(ll_f - ll_fo) / abs(ll_fo), relf[:2].max(), relf[2:].max()))
+    # (R, ell) in this mode are conditioning-limited in ANY float64 evaluation: numpy itself is 1.2e-9 away from an 80-bit
+    # evaluation at this shape (tests/test_gpu_factor_parity.py, oracle/extended.py)
+    assert abs(ll_f - ll_fo) <= 1e-12 * abs(ll_fo) and relf[2:].max() < 1e-12 and relf[:2].max() < 2e-8
     # trial additivity: loglik(all) == loglik(first 700) + loglik(remaining 1300)
     e1, _ = engine_from_oracle(om2, lfp[:, :, :700])
     e2, _ = engine_from_oracle(om2, lfp[:, :, 700:])
