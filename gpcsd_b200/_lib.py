@@ -5,7 +5,7 @@ raises -- there is no CPU fallback and nothing here imports ``oracle/``.
 """
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_double, c_int, c_long, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_int, c_long, c_uint, c_ulonglong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgpcsd_b200.so")
@@ -68,6 +68,15 @@ SIGNATURES = {
     "gpcsd_dot": (c_int, [c_int, c_int, _P, c_long, _P, c_long, _P, _P, _P]),
     "gpcsd_sum_arrays": (c_int, [c_long, c_int, POINTER(c_void_p), _P, _P]),
     "gpcsd_sum_vec": (c_int, [c_long, _P, _P, _P]),
+    "gpcsd_fwd_operator_1d": (c_int, [c_int, _P, c_int, _P, c_double, c_double, _P, c_long, _P]),
+    "gpcsd_fwd_operator_2d": (c_int, [c_int, _P, c_int, _P, c_int, _P, c_double, c_double, _P, c_long, _P]),
+    "gpcsd_cholesky": (c_int, [c_int, _P, c_long, _P, _P]),
+    "gpcsd_randn": (c_int, [c_long, c_long, c_long, c_ulonglong, c_uint, c_double, c_int, _P, _P]),
+    "gpcsd_philox_raw": (c_int, [c_long, c_ulonglong, c_uint, _P, _P]),
+    "gpcsd_shift_residual": (c_int, [c_int, c_int, c_int, c_long, _P, c_int, _P, _P, c_int, _P, _P, _P]),
+    "gpcsd_per_trial_ws_doubles": (c_long, [c_int, c_int, c_int, c_long, c_int]),
+    "gpcsd_quad_per_trial": (c_int, [c_int, c_int, c_int, c_long, _P, _P, c_long, _P, _P, _P]),
+    "gpcsd_shift_grad": (c_int, [c_int, c_int, c_int, c_long, _P, c_int, _P, _P, c_int, _P, _P, _P, _P]),
 }
 
 _STATUS_CALLS = {n for n, (r, _) in SIGNATURES.items() if r is c_int and n not in ("gpcsd_abi_version", "gpcsd_num_sms")}

@@ -354,6 +354,33 @@ class GPCSDModelBase:
         self.t_pred = t
         self.x_pred = z
 
+    # ------------------------------------------------------------------ per-trial evoked shifts (the step after predict)
+    def trial_shift_objective(self, mu, tau, mutau=0.0, sigtau=10.0, want_grad=True):
+        """nll_r(tau_r) (and its gradient) of auditory_lfp/fit_mean_function.py:311-321 for every trial of ``self.lfp`` in one
+        batched device evaluation.  mu: (nx, nt, nseg+1) background + evoked components, tau: (ntrials, nseg)."""
+        return self._get_engine().shift_objective(self._hyperparams(), mu, tau, mutau, sigtau, want_grad)
+
+    def fit_trial_shifts(self, mu, tau0=None, mutau=0.0, sigtau=10.0, maxiter=200, gtol=1e-5,
+                         ftol=1e7 * np.finfo(float).eps):
+        """Per-trial time shifts of the evoked components (fit_mean_function.py:323-335: one scipy L-BFGS-B per trial on
+        joblib workers in the reference).  Here all trials advance in lock step (batched_opt.batched_lbfgsb), each step one
+        batched evaluation of the objective and its closed-form gradient on the GPU.
+        Returns (tau_hat (ntrials, nseg), success (ntrials,) bool, status (ntrials,))."""
+        from .batched_opt import batched_lbfgsb
+        eng = self._get_engine()
+        hp = self._hyperparams()
+        N, nseg = eng.ntrials, np.asarray(mu).shape[2] - 1
+        T0 = np.zeros((N, nseg)) if tau0 is None else np.broadcast_to(np.asarray(tau0, dtype=np.float64), (N, nseg)).copy()
+        full = T0.copy()
+
+        def fun(T, idx):
+            full[idx] = T
+            f, g = eng.shift_objective(hp, mu, full, mutau, sigtau)
+            return f[idx], g[idx]
+        res = batched_lbfgsb(fun, T0, maxiter=maxiter, gtol=gtol, ftol=ftol)
+        ok = np.array([s in ("gtol", "ftol") for s in res["status"]])
+        return res["x"], ok, res["status"]
+
     # ------------------------------------------------------------------ prior sampling helpers
     def _kt_total(self):
         nt = self.t.shape[0]
@@ -362,8 +389,3 @@ class GPCSDModelBase:
             Kt += tc.compute_Kt()
         return Kt
 
-    @staticmethod
-    def _sample_trials(Ls, Lt, rand):
-        """out[:, :, r] = Ls rand[:, :, r] Lt^T for every trial, as two device GEMMs over the trial-fastest
-        layout (replaces the per-trial loop of gpcsd1d.py:307-308)."""
-        return devops.sandwich(Ls, rand, Lt)

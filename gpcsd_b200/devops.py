@@ -223,7 +223,7 @@ def comp_eig_D(Ks, Kt, sig2n):
 
 def sandwich(Ls, X, Lt):
     """out[:, :, r] = Ls X[:, :, r] Lt^T for all r: two DMMA GEMMs on the trial-fastest layout
-    (the per-trial product of sample_prior, gpcsd1d.py:307-308 / gpcsd2d.py:355-359)."""
+    (the per-trial product of sample_prior, gpcsd1d.py:307-308 / gpcsd2d.py:355-359); host in, host out."""
     _require_cuda()
     X = np.ascontiguousarray(np.atleast_3d(np.asarray(X, dtype=np.float64)))
     nx, nt, N = X.shape
@@ -238,3 +238,106 @@ def sandwich(Ls, X, Lt):
     L.call("gpcsd_dgemm", 0, nt, ldn, nt, Ltd.data_ptr(), Ltd.shape[1], 0, W.data_ptr(), ldn, nt * ldn,
            out.data_ptr(), ldn, nt * ldn, nx, _stream())
     return np.ascontiguousarray(out[:, :, :N].cpu().numpy())
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# forward-model operators (forward_models.py:20-39, 57-81): weight-matrix kernel + ONE DMMA GEMM
+# ------------------------------------------------------------------------------------------------------------------
+def fwd_apply_1d(arr, x, z, R, varsigma=1.0):
+    """R/(2 varsigma) * trapz_x b_fwd_1d(z_i - x, R) arr[:, t] for all (i, t): (nz, nt)."""
+    _require_cuda()
+    arr = np.asarray(arr, dtype=np.float64)
+    if arr.ndim == 1:
+        arr = arr[:, None]
+    xd, zd = _dev(np.asarray(x, dtype=np.float64).reshape(-1)), _dev(np.asarray(z, dtype=np.float64).reshape(-1))
+    nx, nz, nt = xd.shape[0], zd.shape[0], arr.shape[1]
+    if arr.shape[0] != nx:
+        raise ValueError("operands could not be broadcast together with shapes (%d,1) (%d,1)" % (nx, arr.shape[0]))
+    W = _mat(nz, nx)
+    L.call("gpcsd_fwd_operator_1d", nz, zd.data_ptr(), nx, xd.data_ptr(), float(R), float(R) / (2.0 * float(varsigma)),
+           W.data_ptr(), W.shape[1], _stream())
+    Ad = _upload_mat(arr)
+    out = _mat(nz, nt)
+    gemm(0, nz, nt, nx, W, W.shape[1], Ad, Ad.shape[1], out, out.shape[1])
+    return out[:, :nt].cpu().numpy()
+
+
+def fwd_apply_2d(arr, x1, x2, z, R, eps):
+    """Double trapezoid of b_fwd_2d * arr over the grid x1 x x2 for every z and time point: (nz, nt)."""
+    _require_cuda()
+    arr = np.asarray(arr, dtype=np.float64)
+    x1d, x2d = _dev(np.asarray(x1, dtype=np.float64).reshape(-1)), _dev(np.asarray(x2, dtype=np.float64).reshape(-1))
+    zd = _dev(np.asarray(z, dtype=np.float64).reshape(-1, 2))
+    n1, n2, nz = x1d.shape[0], x2d.shape[0], zd.shape[0]
+    arr = arr.reshape(n1 * n2, -1)
+    nt = arr.shape[1]
+    W = _mat(nz, n1 * n2)
+    L.call("gpcsd_fwd_operator_2d", nz, zd.data_ptr(), n1, x1d.data_ptr(), n2, x2d.data_ptr(), float(R), float(eps),
+           W.data_ptr(), W.shape[1], _stream())
+    Ad = _upload_mat(arr)
+    out = _mat(nz, nt)
+    gemm(0, nz, nt, n1 * n2, W, W.shape[1], Ad, Ad.shape[1], out, out.shape[1])
+    return out[:, :nt].cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# sample_prior on the device (gpcsd1d.py:295-309 / gpcsd2d.py:336-360): Cholesky, Philox normals, two GEMMs
+# ------------------------------------------------------------------------------------------------------------------
+def cholesky_device(K):
+    """Lower Cholesky factor of a host (or device [n][ld]) symmetric matrix, left on the device as [n][ld]."""
+    _require_cuda()
+    Ld = _upload_mat(K) if not isinstance(K, torch.Tensor) else K.clone()
+    n = Ld.shape[0]
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    L.call("gpcsd_cholesky", n, Ld.data_ptr(), Ld.shape[1], info.data_ptr(), _stream())
+    if int(info.item()) != 0:
+        raise np.linalg.LinAlgError("Matrix is not positive definite")
+    return Ld
+
+
+def cholesky(K):
+    """np.linalg.cholesky on the GPU (host in, host out)."""
+    K = np.asarray(K, dtype=np.float64)
+    return cholesky_device(K)[:, : K.shape[0]].cpu().numpy()
+
+
+def randn_device(nrows, ncols, seed, stream_id=0, ld=None, sd=1.0, out=None, accumulate=False):
+    """[nrows][ld] device array whose first ncols columns are N(0, sd^2) draws of the Philox4x32-10 stream (seed, stream_id)."""
+    _require_cuda()
+    ld = int(ld or ncols)
+    if out is None:
+        out = torch.zeros((int(nrows), ld), dtype=F64, device="cuda")
+    L.call("gpcsd_randn", int(nrows), int(ncols), ld, int(seed) & (2 ** 64 - 1), int(stream_id) & 0xFFFFFFFF, float(sd),
+           1 if accumulate else 0, out.data_ptr(), _stream())
+    return out
+
+
+def randn(shape, seed, stream_id=0):
+    """Host array of standard normals from the device generator; flat C-order element i is normal (i & 1) of counter i >> 1."""
+    n = int(np.prod(shape))
+    return randn_device(1, n, seed, stream_id)[0].cpu().numpy().reshape(shape)
+
+
+def sample_gp_device(Ls, Lt, ntrials, seed, noise_sd=0.0, rand=None):
+    """Device array [nx][nt][ldn] with out[:, :, r] = Ls Z_r Lt^T (+ noise_sd * E_r): Z from the Philox stream (seed, 0) -- or
+    the caller's `rand` (nx, nt, ntrials) host array --, E from stream (seed, 1) added in place without materialising it.
+    Ls, Lt: device [n][ld] lower factors (cholesky_device) or host matrices."""
+    _require_cuda()
+    Lsd = Ls if isinstance(Ls, torch.Tensor) else _upload_mat(Ls)
+    Ltd = Lt if isinstance(Lt, torch.Tensor) else _upload_mat(Lt)
+    nx, nt, N = Lsd.shape[0], Ltd.shape[0], int(ntrials)
+    ldn = (N + 7) // 8 * 8
+    if rand is None:
+        Z = randn_device(nx * nt, N, seed, 0, ld=ldn).view(nx, nt, ldn)
+    else:
+        Z = torch.zeros((nx, nt, ldn), dtype=F64, device="cuda")
+        Z[:, :, :N] = torch.from_numpy(np.ascontiguousarray(rand, dtype=np.float64)).cuda()
+    W = torch.empty_like(Z)
+    L.call("gpcsd_dgemm", 0, nx, nt * ldn, nx, Lsd.data_ptr(), Lsd.shape[1], 0, Z.data_ptr(), nt * ldn, 0,
+           W.data_ptr(), nt * ldn, 0, 1, _stream())
+    out = Z                                             # reuse: Z is dead after the first product
+    L.call("gpcsd_dgemm", 0, nt, ldn, nt, Ltd.data_ptr(), Ltd.shape[1], 0, W.data_ptr(), ldn, nt * ldn,
+           out.data_ptr(), ldn, nt * ldn, nx, _stream())
+    if noise_sd:
+        randn_device(nx * nt, N, seed, 1, ld=ldn, sd=noise_sd, out=out.view(nx * nt, ldn), accumulate=True)
+    return out, N

@@ -463,7 +463,7 @@ class KronEngine:
         self._t_blocks = (UsT, lds, UaT, lda)
         return QT, W, [info_s, info_a]
 
-    def _given_factors(self, st, factors):
+    def _given_factors(self, st, factors, Ydata=None):
         """Caller-supplied eigen-factors (Qs, ls, Qt, lt) -- host arrays with eigenvectors as COLUMNS, as np.linalg.eigh
         returns them in comp_eig_D (utility_functions.py:58-59) -- uploaded in place of the eigensolvers' output.  This is the
         kernel-level entry of SURVEY.md section 6: with identical factors on both sides everything downstream of comp_eig_D
@@ -478,20 +478,22 @@ class KronEngine:
         QtT[:, :self.nt].copy_(self._dev(Qt.T))
         st["QsT"], st["ls"], st["QtT"], st["lt"] = QsT, self._dev(ls), QtT, self._dev(lt)
         st["infos"] = [torch.zeros(1, dtype=torch.int32, device=self.device)]
-        if self.Y is not None:
+        Ydata = self.Y if Ydata is None else Ydata
+        if Ydata is not None:
             if self._y_ready is not None:
                 torch.cuda.current_stream(self.device).wait_event(self._y_ready)
             st["Z"] = self._buf("Z", self.nx, self.nt, self.ldn)
             row = self.nt * self.ldn
-            self.gemm(0, self.nx, row, self.nx, QsT, self.ldx, 0, self.Y, row, 0, st["Z"], row, 0)
+            self.gemm(0, self.nx, row, self.nx, QsT, self.ldx, 0, Ydata, row, 0, st["Z"], row, 0)
 
-    def _factorize(self, hp, jitter, want_grad, factors=None):
+    def _factorize(self, hp, jitter, want_grad, factors=None, data=None):
         """Covariances -> eigen-factors -> 1/D and its reductions (comp_eig_D, utility_functions.py:44-64).
         The spatial and the temporal eigenproblems are independent and run on separate streams."""
         st = {}
         st["Ks"], st["A"], st["dA"], st["U"], st["kern"] = self._spatial_cov(hp, jitter, want_grad)
+        Ydata = self.Y if data is None else data          # `data`: another [nx][nt][ldn] array to project (shift residuals)
         if factors is not None:
-            self._given_factors(st, factors)
+            self._given_factors(st, factors, Ydata)
             return self._finish_factorize(st, hp)
         main = torch.cuda.current_stream(self.device)
         side = self._side_streams()[0]
@@ -500,13 +502,15 @@ class KronEngine:
         with torch.cuda.stream(side):
             side.wait_event(ks_ready)
             st["QsT"], st["ls"], infos_s = self._eigh_spatial(st["Ks"], allow_split=not hp.vector_noise)
-            if self.Y is not None:
+            if Ydata is not None:
                 # Z = Qs^T Y needs the spatial factor only: run it here, underneath the (longer) temporal eigensolve
                 if self._y_ready is not None:
                     side.wait_event(self._y_ready)
+                if data is not None:
+                    side.wait_stream(main)                   # `data` was produced on the main stream
                 st["Z"] = self._buf("Z", self.nx, self.nt, self.ldn)
                 row = self.nt * self.ldn
-                if self._s_blocks is not None and self.ntrials > 0:
+                if self._s_blocks is not None and self.ntrials > 0 and data is None:
                     # reflection-symmetric geometry: Qs is block diagonal on the channel-folded LFP (folded once per upload)
                     UsT, UaT, ldm = self._s_blocks
                     m = self.nx // 2
@@ -516,7 +520,7 @@ class KronEngine:
                     self._call("gpcsd_dgemm", 0, m, row, m, self._p(UaT), ldm, 0, self._p(Yf, m * row), row, 0,
                                self._p(st["Z"], m * row), row, 0, 1, self._stream())
                 else:
-                    self.gemm(0, self.nx, row, self.nx, st["QsT"], self.ldx, 0, self.Y, row, 0, st["Z"], row, 0)
+                    self.gemm(0, self.nx, row, self.nx, st["QsT"], self.ldx, 0, Ydata, row, 0, st["Z"], row, 0)
                 if self._t_fold() and self.ntrials > 0:
                     # folded time basis: the temporal projection and the temporal SYRK then run on two blocks of order
                     # ~nt/2 (half the flops); also hidden underneath the temporal eigensolve
@@ -750,6 +754,56 @@ class KronEngine:
         Gm = self._buf("G_" + tag, n, ld)
         self.gemm(0, n, n, n, Q, ld, 0, T1, ld, 0, Gm, ld, 0)
         return Gm
+
+    def shift_objective(self, hp, mu, tau, mutau=0.0, sigtau=10.0, want_grad=True, factors=None):
+        """Per-trial evoked-shift objective of auditory_lfp/fit_mean_function.py:311-321 for ALL uploaded trials at once:
+            nll_r(tau_r) = 1/2 sum (Qs^T (Y_r - mu(tau_r)) Qt)^2 / D + 1/2 sum_s ((tau_rs - mutau) / sigtau)^2,
+            mu(tau) = mu[:, :, 0] + sum_s lerp(mu[:, :, s], t + tau_s)        (scipy interp1d, fill_value="extrapolate")
+        with the factors of the fitted model (Ks + JITTER I as at fit_mean_function.py:103).  mu: (nx, nt, nseg+1) host array,
+        tau: (ntrials_local, nseg).  The reference runs one scipy L-BFGS-B per trial on joblib workers (:323-328), each
+        evaluation a pair of tiny GEMMs; here one evaluation of the whole trial batch is the shifted-residual kernel, the
+        Kronecker projection with the fused /D epilogue (the same kernels as loglik), a per-trial column reduction, and --
+        for the analytic gradient the reference leaves to finite differences -- the back-projection K^-1 resid = Qs B Qt^T
+        and a per-trial contraction with the interpolant's slopes.  Returns (nll (N,), grad (N, nseg) or None)."""
+        nx, nt, ldn, N = self.nx, self.nt, self.ldn, self.ntrials
+        if self.Y is None:
+            raise RuntimeError("no LFP uploaded: call set_lfp first")
+        mu = np.ascontiguousarray(np.transpose(np.asarray(mu, dtype=np.float64), (2, 0, 1)))     # [nseg+1][nx][nt]
+        nseg = mu.shape[0] - 1
+        tau = np.ascontiguousarray(np.asarray(tau, dtype=np.float64).reshape(N, nseg))
+        if mu.shape[1:] != (nx, nt):
+            raise ValueError("mu must have shape (nx, nt, nseg+1)")
+        mu_d, tau_d = self._dev(mu), self._dev(tau)
+        Rb = self._buf("shift_resid", nx, nt, ldn)
+        if self._y_ready is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._y_ready)
+        self._call("gpcsd_shift_residual", nx, nt, N, ldn, self._p(self.Y), nseg, self._p(mu_d), self._p(self.t_dev),
+                   1 if self.t_uniform else 0, self._p(tau_d), self._p(Rb), self._stream())
+        st = self._factorize(hp, jitter=True, want_grad=False, factors=factors, data=Rb)
+        Bm = self._project(st)
+        nws = self._q("gpcsd_per_trial_ws_doubles", nx, nt, max(N, 1), ldn, max(nseg, 1))
+        ws = self._buf("per_trial_ws", nws)
+        quad = self._buf("shift_quad", max(N, 1))
+        self._call("gpcsd_quad_per_trial", nx, nt, N, ldn, self._p(Bm), self._p(st["rD"]), self.ldt, self._p(ws), self._p(quad),
+                   self._stream())
+        grad = None
+        if want_grad and nseg > 0:
+            # V = Qs B Qt^T: rows of Bm are ordered like the rows of QtT (both in the solver's block order), so the plain
+            # order-nt products are valid whether or not the projection ran in the folded basis
+            Qs, Qt = self._buf("Q_s", nx, self.ldx), self._buf("Q_t", nt, self.ldt)
+            self._call("gpcsd_transpose", nx, nx, self._p(st["QsT"]), self.ldx, self._p(Qs), self.ldx, self._stream())
+            self._call("gpcsd_transpose", nt, nt, self._p(st["QtT"]), self.ldt, self._p(Qt), self.ldt, self._stream())
+            Wb = self._buf("shift_W", nx, nt, ldn)
+            self.gemm(0, nt, max(N, 1), nt, Qt, self.ldt, 0, Bm, ldn, nt * ldn, Wb, ldn, nt * ldn, batch=nx)
+            V = Rb                                           # the residual is dead after the projection
+            self.gemm(0, nx, nt * ldn, nx, Qs, self.ldx, 0, Wb, nt * ldn, 0, V, nt * ldn, 0)
+            gd = self._buf("shift_grad", max(N, 1), nseg)
+            self._call("gpcsd_shift_grad", nx, nt, N, ldn, self._p(V), nseg, self._p(mu_d), self._p(self.t_dev),
+                       1 if self.t_uniform else 0, self._p(tau_d), self._p(ws), self._p(gd), self._stream())
+            grad = gd[:N].cpu().numpy() + (tau - mutau) / (sigtau * sigtau)
+        self._check_info(st)
+        nll = 0.5 * quad[:N].cpu().numpy() + 0.5 * np.sum(np.square((tau - mutau) / sigtau), axis=1)
+        return nll, grad
 
     def predict(self, hp, z, tstar, kind="csd", to_host=True, factors=None):
         """Posterior mean of CSD and/or LFP at (z, t*) per temporal component and summed

@@ -3,8 +3,8 @@
 
 ``b_fwd_1d`` / ``b_fwd_2d`` are the weight functions the covariance kernels fuse on the GPU
 (gpcsd_fwd_weights_{1d,2d}); the host versions here serve callers that use them directly.
-``fwd_model_1d`` / ``fwd_model_2d`` (synthetic-data generators) are restated as
-ONE weight-matrix product each instead of the reference's Python double loop over time x location.
+``fwd_model_1d`` / ``fwd_model_2d`` (synthetic-data generators) run on the device as ONE
+weight-matrix kernel + ONE DMMA GEMM each instead of the reference's Python double loop over time x location.
 """
 import numpy as np
 
@@ -15,22 +15,12 @@ def b_fwd_1d(r, R):
     return np.sqrt(q + 1) - np.sqrt(q)
 
 
-def _trapz_weights(x):
-    x = np.asarray(x, dtype=np.float64).reshape(-1)
-    w = np.zeros_like(x)
-    d = np.diff(x)
-    w[:-1] += 0.5 * d
-    w[1:] += 0.5 * d
-    return w
-
-
 def fwd_model_1d(arr, x, z, R, varsigma=1):
     """LFP at z from CSD ``arr`` (nx, nt) sampled at x: R/(2 varsigma) * trapz_x b(z_i - x) arr[:, t]
-    (forward_models.py:20-39)."""
-    x = np.asarray(x, dtype=np.float64).reshape(-1)
-    z = np.asarray(z, dtype=np.float64).reshape(-1)
-    W = b_fwd_1d(z[:, None] - x[None, :], R) * _trapz_weights(x)[None, :]
-    return R / (2 * varsigma) * (W @ np.asarray(arr, dtype=np.float64))
+    (forward_models.py:20-39).  On the device: gpcsd_fwd_operator_1d builds the (nz, nx) weight matrix (b_fwd_1d x
+    trapezoid weights x R/(2 varsigma)) and one gpcsd_dgemm applies it to all time points."""
+    from . import devops
+    return devops.fwd_apply_1d(arr, x, z, R, varsigma)
 
 
 def b_fwd_2d(delta1, delta2, R, eps, w=None):
@@ -42,13 +32,10 @@ def b_fwd_2d(delta1, delta2, R, eps, w=None):
 
 def fwd_model_2d(arr, x1, x2, z, R, eps, varsigma=1):
     """LFP at z (nz, 2) from CSD ``arr`` (nx1, nx2, nt) on the grid x1 x x2: double trapezoid of
-    b_fwd_2d * arr (forward_models.py:57-81; the 1/(4 pi varsigma) factor is omitted there too)."""
-    x1 = np.asarray(x1, dtype=np.float64).reshape(-1)
-    x2 = np.asarray(x2, dtype=np.float64).reshape(-1)
-    z = np.asarray(z, dtype=np.float64)
+    b_fwd_2d * arr (forward_models.py:57-81; the 1/(4 pi varsigma) factor is omitted there too).  On the device:
+    gpcsd_fwd_operator_2d + one gpcsd_dgemm."""
+    from . import devops
     arr = np.asarray(arr, dtype=np.float64)
     if arr.ndim == 4 and arr.shape[3] == 1:       # callers pass (nx1, nx2, nt, 1) (sim_from_gp_2D.py:70); the reference squeezes it
         arr = arr[..., 0]
-    wt = b_fwd_2d(z[:, 0][:, None, None] - x1[None, :, None], z[:, 1][:, None, None] - x2[None, None, :], R, eps)
-    wt = wt * _trapz_weights(x1)[None, :, None] * _trapz_weights(x2)[None, None, :]
-    return np.einsum("zab,abt->zt", wt, arr, optimize=True)
+    return devops.fwd_apply_2d(arr, x1, x2, z, R, eps)

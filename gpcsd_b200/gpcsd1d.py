@@ -108,10 +108,19 @@ class GPCSD1D(GPCSDModelBase):
         evaluation is one fused loglik+gradient pass on the GPU; ``n_workers`` restarts run concurrently (extension)."""
         return self._fit(n_restarts, method, fix_R, verbose, options, n_workers=n_workers)
 
-    def sample_prior(self, ntrials):
-        """CSD draws from the GP prior at the electrode sites (gpcsd1d.py:295-309)."""
+    def sample_prior(self, ntrials, device=False, seed=0):
+        """CSD draws from the GP prior at the electrode sites (gpcsd1d.py:295-309): Cholesky factors of the CSD kernel
+        (+ JITTER) and of Kt on the device (gpcsd_cholesky), then Ls Z_r Lt^T for all trials as two DMMA GEMMs.
+        device=False (reference behaviour): Z is drawn with np.random.normal in the reference's order (one (nx, nt) block per
+        trial from the global numpy RNG) and a host array is returned.  device=True: Z comes from the device's Philox4x32-10
+        generator (`seed`), nothing touches the host, and a CUDA tensor (nx, nt, ntrials) is returned."""
+        from . import devops
         nt, nx = self.t.shape[0], self.x.shape[0]
-        Lt = np.linalg.cholesky(self._kt_total())
-        Ls = np.linalg.cholesky(self.spatial_cov.compute_Ks() + JITTER * np.eye(nx))
+        Lt = devops.cholesky_device(self._kt_total())
+        Ls = devops.cholesky_device(self.spatial_cov.compute_Ks() + JITTER * np.eye(nx))
+        if device:
+            out, n = devops.sample_gp_device(Ls, Lt, ntrials, seed)
+            return out[:, :, :n]
         rand = np.stack([np.random.normal(0, 1, (nx, nt)) for _ in range(ntrials)], axis=2)
-        return self._sample_trials(Ls, Lt, rand)
+        out, n = devops.sample_gp_device(Ls, Lt, ntrials, 0, rand=rand)
+        return np.ascontiguousarray(out[:, :, :n].cpu().numpy())

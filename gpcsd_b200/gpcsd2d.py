@@ -116,21 +116,37 @@ class GPCSD2D(GPCSDModelBase):
             return
         return self._fit(n_restarts, method, fix_R, verbose, options, n_workers=n_workers)
 
-    def sample_prior(self, ntrials, type="csd", seed=1):
+    def sample_prior(self, ntrials, type="csd", seed=1, device=False):
         """CSD and/or LFP draws from the GP prior (gpcsd2d.py:336-360); returns (csd, lfp), NaN-filled when not
-        requested."""
-        np.random.seed(seed)
+        requested.  Cholesky factors on the device (gpcsd_cholesky), Ls Z_r Lt^T as two DMMA GEMMs.  device=False: the
+        reference's np.random.seed(seed) + np.random.normal draw, host arrays.  device=True: Philox4x32-10 normals on the
+        device (`seed`), CUDA tensors (None for the kind not requested)."""
+        from . import devops
         nt, nx = self.t.shape[0], self.x.shape[0]
-        if type == "csd" or type == "both":
-            Ls_csd = np.linalg.cholesky(self.spatial_cov.compute_Ks() + JITTER * np.eye(nx))
-        if type == "lfp" or type == "both":
-            Ls_lfp = np.linalg.cholesky(self.spatial_cov.compKphi_2d(R=self.R['value'], eps=self.eps) + JITTER * np.eye(nx))
-        Lt = np.linalg.cholesky(self._kt_total())
+        want_csd, want_lfp = type in ("csd", "both"), type in ("lfp", "both")
+        Ls_csd = Ls_lfp = None
+        if want_csd:
+            Ls_csd = devops.cholesky_device(self.spatial_cov.compute_Ks() + JITTER * np.eye(nx))
+        if want_lfp:
+            Ls_lfp = devops.cholesky_device(self.spatial_cov.compKphi_2d(R=self.R['value'], eps=self.eps) + JITTER * np.eye(nx))
+        Lt = devops.cholesky_device(self._kt_total())
+        if device:
+            outs = []
+            for Ls in (Ls_csd, Ls_lfp):
+                if Ls is None:
+                    outs.append(None)
+                else:
+                    o, n = devops.sample_gp_device(Ls, Lt, ntrials, seed)      # same Z for both kinds, as in the reference
+                    outs.append(o[:, :, :n])
+            return tuple(outs)
+        np.random.seed(seed)
         csd = np.nan * np.zeros((nx, nt, ntrials))
         lfp = np.nan * np.zeros((nx, nt, ntrials))
         rand_samp = np.random.normal(0, 1, (nx, nt, ntrials))
-        if type == "csd" or type == "both":
-            csd = self._sample_trials(Ls_csd, Lt, rand_samp)
-        if type == "lfp" or type == "both":
-            lfp = self._sample_trials(Ls_lfp, Lt, rand_samp)
+        if want_csd:
+            o, n = devops.sample_gp_device(Ls_csd, Lt, ntrials, 0, rand=rand_samp)
+            csd = np.ascontiguousarray(o[:, :, :n].cpu().numpy())
+        if want_lfp:
+            o, n = devops.sample_gp_device(Ls_lfp, Lt, ntrials, 0, rand=rand_samp)
+            lfp = np.ascontiguousarray(o[:, :, :n].cpu().numpy())
         return csd, lfp

@@ -227,6 +227,48 @@ int gpcsd_dot(int rows, int cols, const double* X, long ldx, const double* Y, lo
 int gpcsd_sum_arrays(long n, int narr, const double* const* h_in, double* out, void* stream);   /* csd += csd_tmp gpcsd1d.py:281 */
 int gpcsd_sum_vec(long n, const double* in, double* out, void* stream);
 
+/* =============================================================================================
+ * Callers either side of the hot path
+ * ============================================================================================= */
+
+/* Forward-model operators (fwd_model_1d forward_models.py:20-39, fwd_model_2d forward_models.py:57-81) as weight matrices:
+ *   1-D: W[i][k]         = scale * b_fwd_1d(z_i - x_k, R) * trapz_w(x)_k          (scale = R / (2 varsigma), :39)
+ *   2-D: W[i][a*nx2 + b] = b_fwd_2d(z_i0 - x1_a, z_i1 - x2_b, R, eps) * trapz_w(x1)_a * trapz_w(x2)_b
+ * so that LFP = W * CSD is ONE gpcsd_dgemm instead of the reference's Python loop over time x location. */
+int gpcsd_fwd_operator_1d(int nz, const double* z, int nx, const double* x, double R, double scale, double* W, long ld,
+                          void* stream);
+int gpcsd_fwd_operator_2d(int nz, const double* z /* [nz][2] */, int nx1, const double* x1, int nx2, const double* x2, double R,
+                          double eps, double* W, long ld, void* stream);
+
+/* Lower Cholesky factor in place (np.linalg.cholesky of sample_prior, gpcsd1d.py:303-304 / gpcsd2d.py:343-350): on return the
+ * lower triangle of L holds the factor and the strict upper triangle is zero.  info (device int): 0 = ok, k+1 = the leading
+ * minor of order k+1 is not positive definite (numpy raises LinAlgError; the Python layer does the same). */
+int gpcsd_cholesky(int n, double* L, long ld, int* info, void* stream);
+
+/* Standard-normal generator for sample_prior (np.random.normal of gpcsd1d.py:308 / gpcsd2d.py:353): Philox4x32-10 counter-based
+ * bits + Box-Muller.  Logical element i = row*ncols + col of out[nrows][ld] is the (i & 1)-th normal of counter i >> 1 for the
+ * given (seed, stream_id), independent of the launch geometry.  accumulate == 0: out = sd * z;  1: out += sd * z (additive
+ * observation noise without materialising it). */
+int gpcsd_randn(long nrows, long ncols, long ld, unsigned long long seed, unsigned int stream_id, double sd, int accumulate,
+                double* out, void* stream);
+/* the generator's raw 4 x 32-bit outputs for counters 0..ncounters-1 (known-answer tests) */
+int gpcsd_philox_raw(long ncounters, unsigned long long seed, unsigned int stream_id, unsigned int* out, void* stream);
+
+/* Per-trial evoked-shift objective (auditory_lfp/fit_mean_function.py:311-321), all trials of a batch at once:
+ *   gpcsd_shift_residual : Rout[i][j][r] = Y[i][j][r] - mu[0][i][j] - sum_s lerp(mu[s+1][i][:], t_j + tau[r][s])
+ *                          (scipy interp1d linear, fill_value="extrapolate"); mu: [nseg+1][nx][nt], tau: [ntrials][nseg]
+ *   gpcsd_quad_per_trial : out[r] = sum_ij B[i][j][r]^2 / rD[i][j]  (= sum alpha_r^2 / Dvec with B = alpha / D from
+ *                          gpcsd_project_quad); ws: gpcsd_per_trial_ws_doubles(nx, nt, ntrials, ldn, 1)
+ *   gpcsd_shift_grad     : out[r][s] = - sum_ij V[i][j][r] * d/dtau lerp(mu[s+1][i][:], t_j + tau[r][s]),  V = K^-1 resid;
+ *                          ws: gpcsd_per_trial_ws_doubles(nx, nt, ntrials, ldn, nseg) */
+int gpcsd_shift_residual(int nx, int nt, int ntrials, long ldn, const double* Y, int nseg, const double* mu, const double* t,
+                         int t_uniform, const double* tau, double* Rout, void* stream);
+long gpcsd_per_trial_ws_doubles(int nx, int nt, int ntrials, long ldn, int ncomp);
+int gpcsd_quad_per_trial(int nx, int nt, int ntrials, long ldn, const double* B, const double* rD, long ldrd, double* ws,
+                         double* out, void* stream);
+int gpcsd_shift_grad(int nx, int nt, int ntrials, long ldn, const double* V, int nseg, const double* mu, const double* t,
+                     int t_uniform, const double* tau, double* ws, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -512,3 +512,49 @@ def predict_kron(model: Model, lfp, z, tstar, kind="csd", eigh=np.linalg.eigh):
         out[name + "_pred"] = sum(parts[1:], parts[0].copy())
         out[name + "_pred_list"] = parts
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# per-trial evoked-shift objective (auditory_lfp/fit_mean_function.py:304-321)
+# --------------------------------------------------------------------------------------------
+def shift_objective(lfp_trial, mu, t, tau, Qs, Qt, Dvec, mutau=0.0, sigtau=10.0):
+    """Literal restatement of ``obj_fun(tau, lfp_trial)`` (fit_mean_function.py:311-321).
+    lfp_trial (nx, nt); mu (nx, nt, nseg+1): background [:, :, 0] plus one evoked component per segment, each shifted in time
+    by tau[i-1] through scipy interp1d(axis=1, fill_value="extrapolate") (:308); returns the scalar nll."""
+    import scipy.interpolate
+    ts = np.asarray(t, dtype=np.float64).squeeze()
+    tau = np.asarray(tau, dtype=np.float64)
+    nseg = mu.shape[2] - 1
+    mu_new = np.copy(mu[:, :, 0])
+    for i in range(1, nseg + 1):
+        f = scipy.interpolate.interp1d(ts, mu[:, :, i], axis=1, fill_value="extrapolate")
+        mu_new += f(ts + tau[i - 1])
+    resid = lfp_trial - mu_new
+    alpha = np.reshape(np.linalg.multi_dot([Qs.T, resid, Qt]), -1)
+    quad = -0.5 * np.sum(alpha ** 2 / Dvec)
+    nll = -1.0 * np.squeeze(quad)
+    nll += -np.sum(-0.5 * np.square((tau - mutau) / sigtau))
+    return float(nll)
+
+
+def shift_objective_grad(lfp_trial, mu, t, tau, Qs, Qt, Dvec, mutau=0.0, sigtau=10.0):
+    """Closed-form d nll / d tau of ``shift_objective`` (the reference lets scipy finite-difference it):
+    d/dtau_s = - sum_ij (K^-1 resid)_ij * slope_s(i, t_j + tau_s) + (tau_s - mutau) / sigtau^2, K^-1 resid = Qs (alpha/D) Qt^T,
+    slope = derivative of the piecewise-linear interpolant (end intervals extrapolate)."""
+    ts = np.asarray(t, dtype=np.float64).squeeze()
+    tau = np.asarray(tau, dtype=np.float64)
+    nx, nt = lfp_trial.shape
+    nseg = mu.shape[2] - 1
+    mu_new = np.copy(mu[:, :, 0])
+    slopes = []
+    for i in range(1, nseg + 1):
+        q = ts + tau[i - 1]
+        k = np.clip(np.searchsorted(ts, q, side="right") - 1, 0, nt - 2)
+        sl = (mu[:, k + 1, i] - mu[:, k, i]) / (ts[k + 1] - ts[k])[None, :]
+        mu_new += mu[:, k, i] + sl * (q - ts[k])[None, :]
+        slopes.append(sl)
+    resid = lfp_trial - mu_new
+    B = (Qs.T @ resid @ Qt) / np.reshape(Dvec, (nx, nt))
+    V = Qs @ B @ Qt.T
+    g = np.array([-np.sum(V * sl) for sl in slopes]) + (tau - mutau) / sigtau ** 2
+    return g

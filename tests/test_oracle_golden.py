@@ -112,8 +112,7 @@ def test_helpers_golden(golden_dir):
     _, _, Dv, _, _ = O.comp_eig_D(g["Ks"], g["Kt"], g["sv"])
     assert relerr(Dv, g["Dvec_vec"]) < 1e-13
     assert relerr(O.fwd_model_1d(g["csd"], g["xd"], g["zz"], 120.0, varsigma=0.4), g["fwd1d"]) < 1e-13
-    assert relerr(fm.fwd_model_1d(g["csd"], g["xd"], g["zz"], 120.0, varsigma=0.4), g["fwd1d"]) < 1e-13
-    assert relerr(fm.fwd_model_2d(g["arr2"], g["x1"], g["x2"], g["z2"], 60.0, 10.0), g["fwd2d"]) < 1e-13
+    # (gpcsd_b200.forward_models.fwd_model_1d/2d run on the device: tests/test_gpu_next_rows.py holds their golden check)
     assert np.array_equal(pc.predictcsd_trad_1d(g["lf"]), g["tcsd1"])
     assert np.array_equal(pc.predictcsd_trad_2d(g["lf4"]), g["tcsd2"], equal_nan=True)
     ig = pr.GPCSDInvGammaPrior()
