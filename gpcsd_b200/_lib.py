@@ -68,6 +68,22 @@ SIGNATURES = {
     "gpcsd_dot": (c_int, [c_int, c_int, _P, c_long, _P, c_long, _P, _P, _P]),
     "gpcsd_sum_arrays": (c_int, [c_long, c_int, POINTER(c_void_p), _P, _P]),
     "gpcsd_sum_vec": (c_int, [c_long, _P, _P, _P]),
+    "gpcsd_plan_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, POINTER(c_double), POINTER(c_double), c_int,
+                                  POINTER(c_double), POINTER(c_double), c_int, POINTER(c_double), POINTER(c_double), c_int,
+                                  POINTER(c_int), c_int, c_double, c_double, c_int, c_int, POINTER(c_int), POINTER(c_int), c_int]),
+    "gpcsd_plan_destroy": (c_int, [_P]),
+    "gpcsd_plan_num_params": (c_int, [_P]),
+    "gpcsd_plan_ws_bytes": (c_long, [_P, c_long, c_int]),
+    "gpcsd_plan_set_lfp": (c_int, [_P, _P, c_long, c_int, c_double, c_double, _P, c_long]),
+    "gpcsd_plan_touch_lfp": (c_int, [_P]),
+    "gpcsd_plan_set_graph": (c_int, [_P, c_int]),
+    "gpcsd_plan_loglik_grad": (c_int, [_P, c_int, POINTER(c_double), c_int, POINTER(c_double), _P]),
+    "gpcsd_plan_enqueue": (c_int, [_P, c_int, POINTER(c_double), c_int, _P]),
+    "gpcsd_plan_finish": (c_int, [_P, c_int, POINTER(c_double), _P]),
+    "gpcsd_plan_device_result": (c_void_p, [_P]),
+    "gpcsd_plan_device_theta": (c_void_p, [_P]),
+    "gpcsd_plan_last_launches": (c_long, [_P]),
+    "gpcsd_plan_loglik_grad_factors": (c_int, [_P, POINTER(c_double), _P, _P, _P, _P, c_int, POINTER(c_double), _P]),
     "gpcsd_fwd_operator_1d": (c_int, [c_int, _P, c_int, _P, c_double, c_double, _P, c_long, _P]),
     "gpcsd_fwd_operator_2d": (c_int, [c_int, _P, c_int, _P, c_int, _P, c_double, c_double, _P, c_long, _P]),
     "gpcsd_cholesky": (c_int, [c_int, _P, c_long, _P, _P]),
@@ -79,7 +95,8 @@ SIGNATURES = {
     "gpcsd_shift_grad": (c_int, [c_int, c_int, c_int, c_long, _P, c_int, _P, _P, c_int, _P, _P, _P, _P]),
 }
 
-_STATUS_CALLS = {n for n, (r, _) in SIGNATURES.items() if r is c_int and n not in ("gpcsd_abi_version", "gpcsd_num_sms")}
+_STATUS_CALLS = {n for n, (r, _) in SIGNATURES.items()
+                 if r is c_int and n not in ("gpcsd_abi_version", "gpcsd_num_sms", "gpcsd_plan_num_params")}
 
 _lib = None
 

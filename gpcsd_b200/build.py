@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgpcsd_b200.so")
-SOURCES = ["gpcsd_gemm.cu", "gpcsd_tma.cu", "gpcsd_kernels.cu", "gpcsd_eig.cu", "gpcsd_aux.cu"]
+SOURCES = ["gpcsd_gemm.cu", "gpcsd_tma.cu", "gpcsd_kernels.cu", "gpcsd_eig.cu", "gpcsd_aux.cu", "gpcsd_plan.cu"]
 HEADERS = ["common.h", "dmma_gemm.cuh", "dc_core.h", os.path.join("..", "..", "include", "gpcsd_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]

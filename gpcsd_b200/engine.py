@@ -143,6 +143,8 @@ class KronEngine:
         is 16-byte aligned; zero weights contribute exactly 0 to every quadrature sum."""
         x = np.asarray(x, dtype=np.float64)
         self.nx = x.shape[0]
+        self.x_host = x.reshape(-1) if self.dim == 1 else x.reshape(self.nx, 2)
+        self._plans = {}
         self.t_host = np.asarray(t, dtype=np.float64).reshape(-1)
         self.nt = self.t_host.shape[0]
         self.t_dev = self._dev(self.t_host)
@@ -155,6 +157,7 @@ class KronEngine:
             if len(gx) % 2:
                 gx, gw = np.append(gx, gx[-1]), np.append(gw, 0.0)
             self.G = len(gx)
+            self.quad_host = dict(gl_x=gx, gl_w=gw)
             self.gl_x, self.gl_w = self._dev(gx), self._dev(gw)
             self.x_dev = self._dev(x.reshape(-1))
         else:
@@ -164,6 +167,7 @@ class KronEngine:
                 g2, w2 = np.append(g2, g2[-1]), np.append(w2, 0.0)
             self.G1, self.G2 = len(g1), len(g2)
             self.G = self.G1 * self.G2
+            self.quad_host = dict(gl_x1=g1, gl_w1=w1, gl_x2=g2, gl_w2=w2)
             self.gl_x1, self.gl_w1, self.gl_x2, self.gl_w2 = self._dev(g1), self._dev(w1), self._dev(g2), self._dev(w2)
             self.x_dev = self._dev(x.reshape(self.nx, 2))
         self.ldx = _even(self.nx)
@@ -176,6 +180,7 @@ class KronEngine:
         the site set is invariant, Ks[pi(i)][pi(j)] == Ks[i][j] and the spatial eigenproblem splits into two
         independent ones of half the order.  Returns (ra, rb) device int32 arrays or None."""
         nx = self.nx
+        self.s_pairs_host = None
         if nx < 4 or nx % 2:
             return None
         if self.dim == 1:
@@ -205,6 +210,7 @@ class KronEngine:
             return None
         ra = np.array([i for i in range(nx) if i < pi[i]], dtype=np.int32)
         rb = pi[ra].astype(np.int32)
+        self.s_pairs_host = (ra, rb)
         return (torch.from_numpy(ra).to(self.device), torch.from_numpy(rb).to(self.device))
 
     def set_lfp(self, lfp, local=False):
@@ -614,9 +620,61 @@ class KronEngine:
         instead of costing a device->host read each."""
         return torch.cat([i.reshape(-1) for i in st["infos"]]).abs().to(F64)
 
+    # ------------------------------------------------------------------ native plan: one ABI call per evaluation
+    use_plan = True             # False: orchestrate the evaluation call by call from Python (the stepwise path below)
+
+    @staticmethod
+    def theta_of(hp):
+        """Natural-unit hyperparameter vector in the plan's (and the gradient's) order."""
+        return np.concatenate([[hp.R], np.asarray(hp.ells, dtype=np.float64),
+                               np.array([[e, s] for _, e, s in hp.temporal], dtype=np.float64).reshape(-1),
+                               np.atleast_1d(np.asarray(hp.sig2n, dtype=np.float64))])
+
+    def _plan_for(self, hp, R=1):
+        from .plan import EvalPlan
+        nsig = self.nx if hp.vector_noise else 1
+        if hp.vector_noise and len(hp.sig2n) != self.nx:
+            raise ValueError("sig2n must be a scalar or have one entry per electrode")
+        key = (tuple(k for k, _, _ in hp.temporal), nsig, float(hp.eps))
+        pl = self._plans.get(key)
+        if pl is None or pl.rmax < R:
+            self._plans[key] = None
+            pl = self._plans[key] = EvalPlan(self, key[0], nsig, eps=key[2], max_restarts=max(R, 1))
+        return pl
+
+    def max_batch(self, hp, want):
+        """Largest restart batch (<= want) whose plan workspace fits in half of the free device memory."""
+        free, _ = torch.cuda.mem_get_info(self.device)
+        slab = 8 * self.nx * self.nt * self.ldn
+        per = (3 if self._t_fold() else 2) * slab + 8 * (7 * self.nx * self.G + 8 * self.nx * self.ldx + 8 * self.nt * self.ldt) + (64 << 20)
+        return int(max(1, min(want, (free // 2) // max(per, 1))))
+
+    def loglik_grad_batch(self, hps, want_grad=True):
+        """Evaluate R hyperparameter sets in ONE native call (restart-batched kernels, CUDA-graph replay).
+        Returns (loglik (R,), gradient (R, P) in natural units, solver flags (R,): non-zero where numpy's eigh would raise)."""
+        hps = list(hps)
+        R = len(hps)
+        chunk = self.max_batch(hps[0], R)
+        outs = []
+        for lo in range(0, R, chunk):
+            part = hps[lo: lo + chunk]
+            pl = self._plan_for(part[0], len(part))
+            outs.append(pl.evaluate(np.stack([self.theta_of(h) for h in part]), want_grad))
+            self.n_launches += max(pl.last_launches(), 0)
+        out = np.concatenate(outs, axis=0)
+        P = out.shape[1] - 4
+        return out[:, 0].copy(), out[:, 1:1 + P].copy(), out[:, 1 + P].copy()
+
     def loglik(self, hp, factors=None):
         """Marginal log-likelihood (gpcsd1d.py:113-128 / gpcsd2d.py:136-151); all-reduced over trial shards.
         factors: optional caller-supplied (Qs, ls, Qt, lt), see _given_factors."""
+        if self.use_plan and self.timers is None:
+            if factors is not None:
+                return float(self._plan_factors(hp, factors, False)[0])
+            ll, _, flag = self.loglik_grad_batch([hp], want_grad=False)
+            if flag[0] != 0:
+                raise np.linalg.LinAlgError("Eigenvalues did not converge")
+            return float(ll[0])
         st = self._factorize(hp, jitter=True, want_grad=False, factors=factors)
         self._project(st)
         # every term is linear in the entries of `flat` (trial sums add up over the shards; the replicated log-det term is
@@ -634,6 +692,13 @@ class KronEngine:
     def loglik_grad(self, hp, factors=None):
         """(loglik, d loglik / d natural parameters) in the order R, ell(s), (ell_t, sigma2_t)..., sig2n[...].
         factors: optional caller-supplied (Qs, ls, Qt, lt) used instead of the eigensolvers (see _given_factors)."""
+        if self.use_plan and self.timers is None:
+            if factors is not None:
+                return self._plan_factors(hp, factors, True)
+            ll, g, flag = self.loglik_grad_batch([hp])
+            if flag[0] != 0:
+                raise np.linalg.LinAlgError("Eigenvalues did not converge")
+            return float(ll[0]), g[0]
         nx, nt, ldn, N = self.nx, self.nt, self.ldn, self.ntrials
         st = self._factorize(hp, jitter=True, want_grad=True, factors=factors)
         Bm = self._project(st)
@@ -744,6 +809,22 @@ class KronEngine:
         else:
             g.append(-0.5 * ntot * f * srD + 0.5 * bsq)
         return float(ll), np.array(g, dtype=np.float64)
+
+    def _plan_factors(self, hp, factors, want_grad):
+        """Caller-supplied factors through the plan's kernel-level ABI entry (gpcsd_plan_loglik_grad_factors)."""
+        Qs, ls, Qt, lt = (np.asarray(a, dtype=np.float64) for a in factors)
+        if Qs.shape != (self.nx, self.nx) or Qt.shape != (self.nt, self.nt) or ls.shape != (self.nx,) or lt.shape != (self.nt,):
+            raise ValueError("factors must be (Qs (nx,nx), ls (nx,), Qt (nt,nt), lt (nt,))")
+        QsT, QtT = self._buf("QT_s_given", self.nx, self.ldx), self._buf("QT_t_given", self.nt, self.ldt)
+        QsT[:, :self.nx].copy_(self._dev(Qs.T))
+        QtT[:, :self.nt].copy_(self._dev(Qt.T))
+        lsd, ltd = self._dev(ls), self._dev(lt)
+        pl = self._plan_for(hp, 1)
+        out = pl.evaluate_with_factors(self.theta_of(hp), QsT, lsd, QtT, ltd, want_grad)
+        if self.shard.enabled and self.shard.world > 1:
+            raise RuntimeError("caller-supplied factors are a single-rank (kernel-level) entry")
+        P = pl.P
+        return float(out[0, 0]), out[0, 1:1 + P].copy()
 
     def _rotate(self, X, QT, n, ld, tag):
         """G = Q X Q^T from QT = Q^T (row-major):  T1 = X QT ;  G = Q T1."""

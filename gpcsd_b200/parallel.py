@@ -116,6 +116,16 @@ class TrialShard:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         return t.cpu().numpy()
 
+    def allreduce_inplace(self, t):
+        """Sum a small float64 DEVICE tensor over the ranks in place, on the caller's current stream (NCCL); the result
+        stays on the device (the native plan reads it back itself).  No-op for a single rank."""
+        if self.enabled and self.world > 1:
+            if dist.get_backend(self.group) != "nccl":
+                raise RuntimeError("device all-reduce needs the NCCL backend")
+            with self._turn():
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
     def allreduce_device(self, t):
         """Sum a small float64 DEVICE vector over the ranks and return it on the host: with NCCL the all-reduce runs in
         place on the caller's stream (no host round trip before the collective), then ONE device->host read; with gloo

@@ -228,6 +228,52 @@ int gpcsd_sum_arrays(long n, int narr, const double* const* h_in, double* out, v
 int gpcsd_sum_vec(long n, const double* in, double* out, void* stream);
 
 /* =============================================================================================
+ * gpcsd_plan: ONE call per loglik + gradient evaluation, batched over R hyperparameter vectors.
+ *
+ * Replaces obj_fun + autograd.grad(obj_fun) inside the restart loop of fit() (gpcsd1d.py:153-211, gpcsd2d.py:177-260): the
+ * covariance build, both eigendecompositions, the Kronecker projection of every trial, the gradient SYRKs and the closed-form
+ * reverse pass for R restarts are enqueued by one native driver; the hyperparameters live in device memory, so the launch
+ * sequence is captured once per (R, mode) into a CUDA graph and replayed.  theta and the gradient are in NATURAL units in the
+ * order R, ell (1-D) or ell1, ell2 (2-D), (ell_t, sigma2_t) per temporal kernel, sig2n (1 or nx entries) -- the order of the
+ * reference's tparams (gpcsd1d.py:160-174) without the log transform, which stays in the host layer with the priors.
+ * ============================================================================================= */
+/* Geometry: x [nx] (1-D) or [nx][2] (2-D), t [nt]; Gauss-Legendre nodes / weights on the integration box (covariances.py:22-27,
+ * 114-124; 1-D: g1/w1 of even length G1, G2 = 0; 2-D: product grid G1 x G2 with G2 even, pad with zero-weight nodes);
+ * temporal kernel kinds (GPCSD_KIND_*); n_sig2n = 1 or nx; jitter (gpcsd1d.py:17 / gpcsd2d.py:16); eps (2-D).
+ * t_uniform != 0 enables the centrosymmetric split of Kt (even nt >= 32) and, from nt >= fold_min_nt, the folded time basis;
+ * h_ra / h_rb (nx/2 ints each, or NULL): site pairing of a reflection-symmetric geometry (used with scalar noise, nx >= 64).
+ * max_restarts bounds R.  All h_* arrays are HOST pointers and are copied. */
+int gpcsd_plan_create(void** plan, int dim, int nx, int nt, const double* h_x, const double* h_t, int G1, const double* h_g1,
+                      const double* h_w1, int G2, const double* h_g2, const double* h_w2, int ntc, const int* h_kinds,
+                      int n_sig2n, double jitter, double eps, int t_uniform, int fold_min_nt, const int* h_ra, const int* h_rb,
+                      int max_restarts);
+int gpcsd_plan_destroy(void* plan);
+int gpcsd_plan_num_params(void* plan);                          /* P */
+/* Bind this rank's trial slab Y[nx][nt][ldn] (device, caller-owned, zero padded; self.lfp of gpcsd1d.py:125) and a caller
+ * allocated workspace of gpcsd_plan_ws_bytes(plan, ldn, ntrials_local) bytes.  ntrials_total: trials of the whole model (all
+ * ranks); det_fraction: share of the trial-independent log-det terms this rank contributes (1 / world). */
+long gpcsd_plan_ws_bytes(void* plan, long ldn, int ntrials_local);
+int gpcsd_plan_set_lfp(void* plan, const double* Y, long ldn, int ntrials_local, double ntrials_total, double det_fraction,
+                       void* ws, long ws_bytes);
+int gpcsd_plan_touch_lfp(void* plan);                           /* the bound Y buffer was overwritten in place */
+int gpcsd_plan_set_graph(void* plan, int enable);               /* CUDA-graph replay on (default) / off */
+/* h_theta [R][P] host -> h_out [R][P+4] host: loglik, d loglik / d theta (P entries; zeros when want_grad == 0), eigensolver
+ * flag (0 = ok; numpy raises LinAlgError otherwise), and a hyperparameter checksum pair (c*f, c^2*f) for rank-consistency
+ * checks after an all-reduce.  gpcsd_plan_loglik_grad = gpcsd_plan_enqueue + gpcsd_plan_finish; trial-sharded callers
+ * all-reduce gpcsd_plan_device_result() ([R][P+4], on `stream`) between the two.  One evaluation in flight per plan. */
+int gpcsd_plan_loglik_grad(void* plan, int R, const double* h_theta, int want_grad, double* h_out, void* stream);
+int gpcsd_plan_enqueue(void* plan, int R, const double* h_theta, int want_grad, void* stream);
+int gpcsd_plan_finish(void* plan, int R, double* h_out, void* stream);
+double* gpcsd_plan_device_result(void* plan);
+double* gpcsd_plan_device_theta(void* plan);
+long gpcsd_plan_last_launches(void* plan);                      /* kernels launched by the last non-replayed evaluation */
+/* Kernel-level entry: one evaluation with CALLER-SUPPLIED eigen-factors instead of the eigensolvers:
+ * device arrays QsT [nx][even(nx)], ls [nx], QtT [nt][even(nt)], lt [nt], rows = eigenvectors (the columns np.linalg.eigh
+ * returns in comp_eig_D, utility_functions.py:58-59). */
+int gpcsd_plan_loglik_grad_factors(void* plan, const double* h_theta, const double* QsT, const double* ls, const double* QtT,
+                                   const double* lt, int want_grad, double* h_out, void* stream);
+
+/* =============================================================================================
  * Callers either side of the hot path
  * ============================================================================================= */
 
