@@ -12,7 +12,10 @@
 //   * the result (loglik, gradient, solver flags) is assembled on the device and read back with one copy.
 // The arithmetic is the one DESIGN.md section 3 derives and engine.py orchestrates call by call; the kernels that do the
 // flops (gpcsd_dgemm, gpcsd_project_quad, gpcsd_wsyrk, gpcsd_eigh_dc) are shared with it.
+#include <stdlib.h>
 #include <string.h>
+
+#include <chrono>
 
 #include <unordered_map>
 #include <vector>
@@ -903,30 +906,26 @@ int enqueue_body(Plan* p, int R, int want_grad, const Factors* fac, cudaStream_t
   }
 
   if (want_grad) {
-    // ---------------- segment-weighted SYRKs over the trial batch
+    // The temporal branch (Mt SYRK -> core -> rotation -> <Gt, dKt>) and the spatial branch (Ms/Ns SYRKs -> core -> rotation
+    // -> <Gs, dKs>) only share the projected data Bm: they run on two streams (two parallel branches of the captured graph).
+    cudaStream_t sG = p->side[1];
+    GP_CUDA(cudaEventRecord(p->ev[2], st));
+    GP_CUDA(cudaStreamWaitEvent(sG, p->ev[2], 0));
     const long nMt = (long)R * nt * ldt, nMs = (long)R * nx * ldx;
     const bool blockT = use_tfold, blockS = use_ssplit;
-    if (blockT || N == 0) {
-      pl::zero_kernel<<<blocks256(nMt) < 1024 ? blocks256(nMt) : 1024, 256, 0, st>>>(p->Mt, nMt);
+    auto zero = [&](double* ptr, long n, cudaStream_t s_) -> int {
+      pl::zero_kernel<<<blocks256(n) < 1024 ? blocks256(n) : 1024, 256, 0, s_>>>(ptr, n);
       PL_LAUNCH(1);
-    }
-    if (blockS || N == 0) {
-      pl::zero_kernel<<<blocks256(nMs) < 1024 ? blocks256(nMs) : 1024, 256, 0, st>>>(p->Ms, nMs);
-      PL_LAUNCH(1);
-    }
-    if (vec && N == 0) {
-      pl::zero_kernel<<<blocks256(nMs) < 1024 ? blocks256(nMs) : 1024, 256, 0, st>>>(p->Ns, nMs);
-      PL_LAUNCH(1);
-    }
+      return 0;
+    };
+    // ================= temporal branch (main stream)
+    if (blockT || N == 0) PL_CHECK(zero(p->Mt, nMt, st));
     if (N > 0) {
       for (int r = 0; r < R; ++r) {
         const double* Br = p->Bm + r * slab;
         const double* lsr = ls + (fac ? 0 : (long)r * nx);
-        const double* ltr = lt + (fac ? 0 : (long)r * nt);
         double* Mt = p->Mt + (long)r * nt * ldt;
-        double* Ms = p->Ms + (long)r * nx * ldx;
         double* wt = p->syrk_ws_t + (long)r * p->syrk_t_doubles;
-        double* wsS = p->syrk_ws_s + (long)r * p->syrk_s_doubles;
         if (blockT) {     // only the two diagonal blocks of Mt enter <dL/dKt, dKt/dtheta>
           const int m = p->tm, ms = p->tms;
           PL_CHECK(gpcsd_wsyrk(ms, nx, N, Br, ldn, row, lsr, Mt, ldt, wt, st));
@@ -936,32 +935,13 @@ int enqueue_body(Plan* p, int R, int want_grad, const Factors* fac, cudaStream_t
           PL_CHECK(gpcsd_wsyrk(nt, nx, N, Br, ldn, row, lsr, Mt, ldt, wt, st));
           p->launches += 2;
         }
-        if (blockS) {
-          const int mh = p->sm;
-          PL_CHECK(gpcsd_wsyrk(mh, nt, N, Br, row, ldn, ltr, Ms, ldx, wsS, st));
-          PL_CHECK(gpcsd_wsyrk(mh, nt, N, Br + (long)mh * row, row, ldn, ltr, Ms + (long)mh * ldx + mh, ldx, wsS, st));
-          p->launches += 4;
-        } else {
-          PL_CHECK(gpcsd_wsyrk(nx, nt, N, Br, row, ldn, ltr, Ms, ldx, wsS, st));
-          p->launches += 2;
-        }
-        if (vec) {
-          PL_CHECK(gpcsd_wsyrk(nx, nt, N, Br, row, ldn, nullptr, p->Ns + (long)r * nx * ldx, ldx, wsS, st));
-          p->launches += 2;
-        }
       }
     }
-    // ---------------- eigen-basis cores and rotation back  G = Q X Q^T
-    pl::grad_core_kernel<<<dim3(blocks256((long)nx * nx), R), 256, 0, st>>>(nx, p->Ms, ldx, nx * ldx, vec ? p->Ns : nullptr, ls, p->theta,
-                                                                          d.P, sig_idx, p->rowA, p->ntot, p->det_frac, p->Xs, ldx, nx * ldx);
-    PL_LAUNCH(1);
     pl::grad_core_kernel<<<dim3(blocks256((long)nt * nt), R), 256, 0, st>>>(nt, p->Mt, ldt, nt * ldt, nullptr, lt, p->theta, d.P, sig_idx,
                                                                           p->colB, p->ntot, p->det_frac, p->Xt, ldt, nt * ldt);
     PL_LAUNCH(1);
-    PL_CHECK(rotate(p, R, nx, ldx, p->Xs, QsT, p->Qs, p->T1s, p->Gs, st));
     PL_CHECK(rotate(p, R, nt, ldt, p->Xt, QtT, p->Qt, p->T1t, p->Gt, st));
-    // ---------------- temporal hyperparameters  <Gt, dKt_k/d(ell_k, sigma2_k)>
-    {
+    {   // <Gt, dKt_k/d(ell_k, sigma2_k)>
       long nb = ((long)nt * nt + 255) / 256;
       const long cap = 4L * gp_num_sms();
       if (R > 1 && nb > 8) nb = nb < cap / R + 1 ? nb : cap / R + 1;
@@ -972,31 +952,61 @@ int enqueue_body(Plan* p, int R, int want_grad, const Factors* fac, cudaStream_t
       pl::sum_cols_kernel<<<dim3(2 * d.ntc, R), 256, 0, st>>>(p->ktg_ws, p->ktg_ws_doubles, (int)nb, 16, p->res + 8, pl::RESW);
       PL_LAUNCH(1);
     }
-    // ---------------- spatial hyperparameters: dL/dR = 2 <dA, Gs U>,  dL/dell_k = <A, (Gs A) dKg_k>
+    // ================= spatial branch (side stream)
+    if (blockS || N == 0) PL_CHECK(zero(p->Ms, nMs, sG));
+    if (vec && N == 0) PL_CHECK(zero(p->Ns, nMs, sG));
+    if (N > 0) {
+      for (int r = 0; r < R; ++r) {
+        const double* Br = p->Bm + r * slab;
+        const double* ltr = lt + (fac ? 0 : (long)r * nt);
+        double* Ms = p->Ms + (long)r * nx * ldx;
+        double* wsS = p->syrk_ws_s + (long)r * p->syrk_s_doubles;
+        if (blockS) {
+          const int mh = p->sm;
+          PL_CHECK(gpcsd_wsyrk(mh, nt, N, Br, row, ldn, ltr, Ms, ldx, wsS, sG));
+          PL_CHECK(gpcsd_wsyrk(mh, nt, N, Br + (long)mh * row, row, ldn, ltr, Ms + (long)mh * ldx + mh, ldx, wsS, sG));
+          p->launches += 4;
+        } else {
+          PL_CHECK(gpcsd_wsyrk(nx, nt, N, Br, row, ldn, ltr, Ms, ldx, wsS, sG));
+          p->launches += 2;
+        }
+        if (vec) {
+          PL_CHECK(gpcsd_wsyrk(nx, nt, N, Br, row, ldn, nullptr, p->Ns + (long)r * nx * ldx, ldx, wsS, sG));
+          p->launches += 2;
+        }
+      }
+    }
+    pl::grad_core_kernel<<<dim3(blocks256((long)nx * nx), R), 256, 0, sG>>>(nx, p->Ms, ldx, nx * ldx, vec ? p->Ns : nullptr, ls, p->theta,
+                                                                          d.P, sig_idx, p->rowA, p->ntot, p->det_frac, p->Xs, ldx, nx * ldx);
+    PL_LAUNCH(1);
+    PL_CHECK(rotate(p, R, nx, ldx, p->Xs, QsT, p->Qs, p->T1s, p->Gs, sG));
+    // dL/dR = 2 <dA, Gs U>,  dL/dell_k = <A, (Gs A) dKg_k>
     auto dot = [&](const double* X, const double* Yv, int slot) -> int {
       long nb = ((long)nx * G + 255) / 256;
       const long cap = 4L * gp_num_sms();
       if (nb > cap) nb = cap;
-      pl::dot_kernel<<<dim3((unsigned)nb, R), 256, 0, st>>>(nx, G, X, G, (long)nx * G, Yv, G, (long)nx * G, p->dot_ws, p->dot_ws_doubles);
+      pl::dot_kernel<<<dim3((unsigned)nb, R), 256, 0, sG>>>(nx, G, X, G, (long)nx * G, Yv, G, (long)nx * G, p->dot_ws, p->dot_ws_doubles);
       PL_LAUNCH(1);
-      pl::sum_cols_kernel<<<dim3(1, R), 256, 0, st>>>(p->dot_ws, p->dot_ws_doubles, (int)nb, 1, p->res + slot, pl::RESW);
+      pl::sum_cols_kernel<<<dim3(1, R), 256, 0, sG>>>(p->dot_ws, p->dot_ws_doubles, (int)nb, 1, p->res + slot, pl::RESW);
       PL_LAUNCH(1);
       return 0;
     };
-    PL_CHECK(gpcsd_dgemm(0, nx, G, nx, p->Gs, ldx, nx * ldx, p->U, G, (long)nx * G, p->GU, G, (long)nx * G, R, st));
+    PL_CHECK(gpcsd_dgemm(0, nx, G, nx, p->Gs, ldx, nx * ldx, p->U, G, (long)nx * G, p->GU, G, (long)nx * G, R, sG));
     p->launches += 1;
     PL_CHECK(dot(p->dA, p->GU, 4));
-    PL_CHECK(gpcsd_dgemm(0, nx, G, nx, p->Gs, ldx, nx * ldx, p->A, G, (long)nx * G, p->GA, G, (long)nx * G, R, st));
+    PL_CHECK(gpcsd_dgemm(0, nx, G, nx, p->Gs, ldx, nx * ldx, p->A, G, (long)nx * G, p->GA, G, (long)nx * G, R, sG));
     p->launches += 1;
     if (d.dim == 1) {
-      PL_CHECK(apply_quad_kernel(p, R, p->GA, p->dKg, nullptr, nullptr, p->Wq, st));
+      PL_CHECK(apply_quad_kernel(p, R, p->GA, p->dKg, nullptr, nullptr, p->Wq, sG));
       PL_CHECK(dot(p->A, p->Wq, 5));
     } else {
-      PL_CHECK(apply_quad_kernel(p, R, p->GA, nullptr, p->dK1, p->K2, p->Wq, st));
+      PL_CHECK(apply_quad_kernel(p, R, p->GA, nullptr, p->dK1, p->K2, p->Wq, sG));
       PL_CHECK(dot(p->A, p->Wq, 5));
-      PL_CHECK(apply_quad_kernel(p, R, p->GA, nullptr, p->K1, p->dK2, p->Wq, st));
+      PL_CHECK(apply_quad_kernel(p, R, p->GA, nullptr, p->K1, p->dK2, p->Wq, sG));
       PL_CHECK(dot(p->A, p->Wq, 6));
     }
+    GP_CUDA(cudaEventRecord(p->ev[3], sG));
+    GP_CUDA(cudaStreamWaitEvent(st, p->ev[3], 0));
   }
   pl::assemble_kernel<<<R, 64, 0, st>>>(d, p->theta, p->res, p->rowC, p->Ns, ldx, nx * ldx, p->ntot, p->det_frac, want_grad, p->out,
                                         d.P + 4);
@@ -1051,7 +1061,20 @@ static int enqueue_on_own(Plan* p, int R, int want_grad, size_t nb) {
     }
   }
   GP_CUDA(cudaMemcpyAsync(p->theta, p->h_theta, nb, cudaMemcpyHostToDevice, st));
-  PL_CHECK(enqueue_body(p, R, want_grad, nullptr, st));
+  static const bool trace = getenv("GPCSD_PLAN_TRACE") != nullptr;
+  if (trace) {
+    cudaStreamSynchronize(st);
+    auto t0 = std::chrono::steady_clock::now();
+    int e = enqueue_body(p, R, want_grad, nullptr, st);
+    auto t1 = std::chrono::steady_clock::now();
+    cudaStreamSynchronize(st);
+    auto t2 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[plan trace] R=%d launches=%ld host enqueue %.1f us, drain %.1f us\n", R, p->launches,
+            std::chrono::duration<double, std::micro>(t1 - t0).count(), std::chrono::duration<double, std::micro>(t2 - t1).count());
+    if (e) return e;
+  } else {
+    PL_CHECK(enqueue_body(p, R, want_grad, nullptr, st));
+  }
   p->warmed[key] += 1;
   return 0;
 }

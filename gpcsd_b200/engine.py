@@ -654,7 +654,9 @@ class KronEngine:
         Returns (loglik (R,), gradient (R, P) in natural units, solver flags (R,): non-zero where numpy's eigh would raise)."""
         hps = list(hps)
         R = len(hps)
-        chunk = self.max_batch(hps[0], R)
+        # (cudaMemGetInfo costs up to milliseconds: only ask when a bigger plan workspace would have to be allocated)
+        have = self._plans.get((tuple(k for k, _, _ in hps[0].temporal), self.nx if hps[0].vector_noise else 1, float(hps[0].eps)))
+        chunk = R if (R == 1 or (have is not None and have.rmax >= R)) else self.max_batch(hps[0], R)
         outs = []
         for lo in range(0, R, chunk):
             part = hps[lo: lo + chunk]
