@@ -241,7 +241,98 @@ class GPCSDModelBase:
         return fun
 
     # ------------------------------------------------------------------ fit
-    def _fit(self, n_restarts, method, fix_R, verbose, options, n_workers=2):
+    def _batched_objective(self, engine, fix_R):
+        """fun(X (b, n), idx) -> (nll (b,), d nll / d tparams (b, n)) for b restarts in ONE native call (the restart-batched
+        plan); same arithmetic as obj_fun_and_grad, nothing written into the model's dictionaries.  A restart whose
+        eigendecomposition fails (numpy would raise LinAlgError, gpcsd1d.py:219 / gpcsd2d.py:215-219) gets nll = +inf."""
+        slots = self._param_slots()
+        scales = np.array([sc for _, sc in slots], dtype=np.float64)
+        priors = [d['prior'] for d, _ in slots]
+        noise_scalar = self._noise_is_scalar()
+        priors += [self.sig2n['prior']] if noise_scalar else list(self.sig2n['prior'])
+        nslots, nsp = len(slots), len(self.SPATIAL_ELL_KEYS)
+        kinds = [tc.KIND for tc in self.temporal_cov_list]
+        R_fixed = float(self.R['value'])
+        eps = float(getattr(self, "eps", 0.0) or 0.0)
+
+        def fun(X, idx):
+            with np.errstate(all='ignore'):
+                X = np.atleast_2d(np.asarray(X, dtype=np.float64))
+                vals = np.exp(X)
+                vals[:, :nslots] *= scales[None, :]
+                if fix_R:
+                    vals[:, 0] = R_fixed
+                hps, lps, dlps = [], [], []
+                for v in vals:
+                    lp = 0.0
+                    for p, x in zip(priors, v):
+                        lp = lp + p.lpdf(x)
+                    lps.append(lp)
+                    dlps.append([_dlpdf(p, x) if x > 0 else 0.0 for p, x in zip(priors, v)])
+                    temporal = [(kinds[k], float(v[1 + nsp + 2 * k]), float(v[2 + nsp + 2 * k])) for k in range(len(kinds))]
+                    sig = float(v[nslots]) if noise_scalar else np.array(v[nslots:])
+                    hps.append(HyperParams(R=float(v[0]), ells=tuple(float(x) for x in v[1:1 + nsp]), temporal=temporal,
+                                           sig2n=sig, eps=eps))
+                ll, g, flag = engine.loglik_grad_batch(hps)
+                nll = -(ll + np.array(lps))
+                grad = -(g + np.array(dlps)) * vals
+                if fix_R:
+                    grad[:, 0] = 0.0
+                bad = flag != 0
+                nll[bad] = np.inf
+                grad[bad] = 0.0
+                return nll, grad
+        return fun
+
+    def _fit_lockstep(self, n_restarts, fix_R, verbose, options):
+        """Multi-start MAP fit with ALL restarts advancing in lock step: every optimiser step is one
+        restart-batched loglik+gradient call on the GPU.  Same bounds, prior-sampled starts, stopping tests (gtol, ftol,
+        maxiter) and best-finite-restart selection as the reference's sequential loop (gpcsd1d.py:137-246)."""
+        from .batched_opt import batched_lbfgsb
+        bounds = self._bounds()
+        shard = RestartShard(getattr(self, "_restart_group", None))
+        starts = [self._sample_tparams0(fix_R) for _ in range(n_restarts)]
+        starts = self._broadcast_from_rank0(starts, fix_R)
+        mine = [i for i in range(n_restarts) if shard.mine(i)]
+        local = {}
+        if mine:
+            eng = self._get_engine()
+            res = batched_lbfgsb(self._batched_objective(eng, fix_R), np.array([starts[i] for i in mine]), bounds=bounds,
+                                 maxiter=int(options.get('maxiter', self.DEFAULT_MAXITER)), gtol=float(options.get('gtol', 1e-5)),
+                                 ftol=float(options.get('ftol', 1e7 * np.finfo(float).eps)))
+            self._last_fit_info = {"nit": res["nit"], "batched_calls": res["nfev"], "status": list(res["status"])}
+            for k, i in enumerate(mine):
+                if res["status"][k] == "nonfinite-start":      # the reference's restart dies with an exception: no entry
+                    print("restart %d: objective not finite at the starting point" % i)
+                    continue
+                local[i] = (float(res["fun"][k]), np.asarray(res["x"][k], dtype=np.float64), str(res["status"][k]))
+        return self._select_best(shard.gather(local), fix_R, verbose)
+
+    def _select_best(self, merged, fix_R, verbose):
+        nll_values, params, term_msg = [], [], []
+        for i in sorted(merged):
+            nll_values.append(merged[i][0])
+            params.append(merged[i][1])
+            term_msg.append(merged[i][2])
+        nll_values = np.array(nll_values)
+        if len(nll_values) < 1 or not np.any(np.isfinite(nll_values)):
+            print('problem with optimization!')
+            return
+        finite = np.isfinite(nll_values)
+        best_ind = np.argmin(nll_values[finite])
+        params = [p for p, ok in zip(params, finite) if ok]
+        if verbose:
+            print('\nNeg log lik values across different initializations:')
+            print(nll_values)
+            print('Best index termination message')
+            print(term_msg[best_ind])
+        self._set_tparams(params[best_ind], fix_R)
+
+    def _fit(self, n_restarts, method, fix_R, verbose, options, n_workers=2, lockstep=None):
+        if lockstep is None:
+            lockstep = (method == 'L-BFGS-B')
+        if lockstep:
+            return self._fit_lockstep(n_restarts, fix_R, verbose, options)
         bounds = self._bounds()
         options = dict(options)
         if method == 'L-BFGS-B' and not options.get('disp', False):
@@ -305,25 +396,7 @@ class GPCSDModelBase:
                 list(pool.map(run, mine))
         bar.update(n_restarts - len(mine))
         bar.close()
-        merged = shard.gather(local)
-        nll_values, params, term_msg = [], [], []
-        for i in sorted(merged):
-            nll_values.append(merged[i][0])
-            params.append(merged[i][1])
-            term_msg.append(merged[i][2])
-        nll_values = np.array(nll_values)
-        if len(nll_values) < 1:
-            print('problem with optimization!')
-            return
-        finite = np.isfinite(nll_values)
-        best_ind = np.argmin(nll_values[finite])
-        params = [p for p, ok in zip(params, finite) if ok]
-        if verbose:
-            print('\nNeg log lik values across different initializations:')
-            print(nll_values)
-            print('Best index termination message')
-            print(term_msg[best_ind])
-        self._set_tparams(params[best_ind], fix_R)
+        return self._select_best(shard.gather(local), fix_R, verbose)
 
     def _broadcast_from_rank0(self, starts, fix_R):
         import torch.distributed as dist

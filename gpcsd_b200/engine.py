@@ -660,8 +660,13 @@ class KronEngine:
         outs = []
         for lo in range(0, R, chunk):
             part = hps[lo: lo + chunk]
-            pl = self._plan_for(part[0], len(part))
-            outs.append(pl.evaluate(np.stack([self.theta_of(h) for h in part]), want_grad))
+            # batch sizes are rounded up to a power of two (the last vector repeated) so that a lock-step optimiser whose
+            # active set shrinks restart by restart replays a handful of recorded graphs instead of capturing one per size
+            n = len(part)
+            npad = min(1 << (n - 1).bit_length(), max(chunk, n)) if n > 1 else 1
+            pl = self._plan_for(part[0], npad)
+            th = np.stack([self.theta_of(h) for h in part] + [self.theta_of(part[-1])] * (npad - n))
+            outs.append(pl.evaluate(th, want_grad)[:n])
             self.n_launches += max(pl.last_launches(), 0)
         out = np.concatenate(outs, axis=0)
         P = out.shape[1] - 4

@@ -103,10 +103,10 @@ class GPCSD1D(GPCSDModelBase):
         self._invalidate_lfp()
 
     def fit(self, n_restarts=10, method='L-BFGS-B', fix_R=False, verbose=False,
-            options={'maxiter': 1000, 'disp': False, 'gtol': 1e-5, 'ftol': 1e7 * np.finfo(float).eps}, n_workers=2):
+            options={'maxiter': 1000, 'disp': False, 'gtol': 1e-5, 'ftol': 1e7 * np.finfo(float).eps}, n_workers=2, lockstep=None):
         """MAP fit by multi-start bounded L-BFGS-B in log space (gpcsd1d.py:130-246).  Every objective
         evaluation is one fused loglik+gradient pass on the GPU; ``n_workers`` restarts run concurrently (extension)."""
-        return self._fit(n_restarts, method, fix_R, verbose, options, n_workers=n_workers)
+        return self._fit(n_restarts, method, fix_R, verbose, options, n_workers=n_workers, lockstep=lockstep)
 
     def sample_prior(self, ntrials, device=False, seed=0):
         """CSD draws from the GP prior at the electrode sites (gpcsd1d.py:295-309): Cholesky factors of the CSD kernel

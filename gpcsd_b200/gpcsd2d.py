@@ -104,7 +104,7 @@ class GPCSD2D(GPCSDModelBase):
         self._invalidate_lfp()
 
     def fit(self, n_restarts=10, method='L-BFGS-B', fix_R=False, verbose=False, profile=False,
-            options={'maxiter': 500, 'disp': False, 'gtol': 1e-5, 'ftol': 1e7 * np.finfo(float).eps}, n_workers=2):
+            options={'maxiter': 500, 'disp': False, 'gtol': 1e-5, 'ftol': 1e7 * np.finfo(float).eps}, n_workers=2, lockstep=None):
         """MAP fit by multi-start bounded L-BFGS-B in log space (gpcsd2d.py:153-287).  ``profile=True`` keeps
         the reference's hook: profile one objective+gradient evaluation from a prior-sampled start with
         cProfile (files objfunstats / gradobjfunstats) and return."""
@@ -114,7 +114,7 @@ class GPCSD2D(GPCSDModelBase):
             cProfile.runctx('self.obj_fun(tparams0, fix_R)', None, locals(), filename='objfunstats')
             cProfile.runctx('self.obj_fun_and_grad(tparams0, fix_R)', None, locals(), filename='gradobjfunstats')
             return
-        return self._fit(n_restarts, method, fix_R, verbose, options, n_workers=n_workers)
+        return self._fit(n_restarts, method, fix_R, verbose, options, n_workers=n_workers, lockstep=lockstep)
 
     def sample_prior(self, ntrials, type="csd", seed=1, device=False):
         """CSD and/or LFP draws from the GP prior (gpcsd2d.py:336-360); returns (csd, lfp), NaN-filled when not

@@ -115,6 +115,14 @@ class _StubModel:
                     return float(f), g
                 return fun
 
+            def _batched_objective(self, engine, fix_R):
+                one = self._pure_objective(engine, fix_R)
+
+                def fun(X, idx):
+                    vals = [one(x) for x in np.atleast_2d(X)]
+                    return np.array([v[0] for v in vals]), np.array([v[1] for v in vals])
+                return fun
+
         m = M()
         ig = GPCSDInvGammaPrior(); ig.set_params(50.0, 500.0)
 
@@ -135,10 +143,10 @@ class _StubModel:
         return m
 
 
-def _fit_stub(restart_group, seed=11, n_restarts=6):
+def _fit_stub(restart_group, seed=11, n_restarts=6, lockstep=False):
     np.random.seed(seed)
     m = _StubModel(restart_group)
-    m._fit(n_restarts, 'L-BFGS-B', False, False, {'maxiter': 200, 'gtol': 1e-10}, n_workers=1)
+    m._fit(n_restarts, 'L-BFGS-B', False, False, {'maxiter': 200, 'gtol': 1e-10}, n_workers=1, lockstep=lockstep)
     return np.array([m.R['value'], m.spatial_cov.params['ell']['value'], m.sig2n['value']] +
                     [tc.params[k]['value'] for tc in m.temporal_cov_list for k in ('ell', 'sigma2')])
 
@@ -151,13 +159,13 @@ def _restart_worker(rank, world, port, q):
     from gpcsd_b200.parallel import RestartShard
     sh = RestartShard(True)
     assert [i for i in range(6) if sh.mine(i)] == list(range(rank, 6, world))
-    q.put((rank, _fit_stub(True)))
+    q.put((rank, np.concatenate([_fit_stub(True), _fit_stub(True, lockstep=True)])))
     dist.destroy_process_group()
 
 
 def test_restart_sharding_world2_matches_unsharded():
     """fit() with restarts sharded over 2 ranks ends at exactly the parameters of the unsharded fit."""
-    single = _fit_stub(None)
+    single = np.concatenate([_fit_stub(None), _fit_stub(None, lockstep=True)])      # per-restart scipy path, lock-step path
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 31500 + (os.getpid() % 2000)
