@@ -33,6 +33,7 @@ SIGNATURES = {
     "gpcsd_project_quad_strided": (c_int, [c_int, c_int, c_int, _P, c_long, _P, c_long, c_long, _P, c_long, _P, _P, _P, _P]),
     "gpcsd_wsyrk_ws_doubles": (c_long, [c_int, c_int, c_int]),
     "gpcsd_wsyrk": (c_int, [c_int, c_int, c_int, _P, c_long, c_long, _P, _P, c_long, _P, _P]),
+    "gpcsd_wsyrk_pair": (c_int, [c_int, c_int, c_int, _P, c_long, c_long, _P, _P, _P, c_long, _P, _P]),
     "gpcsd_eigh_ws_doubles": (c_long, [c_int, c_long]),
     "gpcsd_eigh": (c_int, [c_int, _P, c_long, _P, c_long, _P, _P, c_long, _P, _P]),
     "gpcsd_eigh_batched_ws_bytes": (c_long, [c_int, c_long, c_int]),

@@ -222,7 +222,9 @@ struct SyrkArgs {
 // loads X[8i+g][k + 2q .. 2q+1] with one LDG.128 per row-tile and feeds two DMMAs (k-slots {0,2,4,6} and
 // {1,3,5,7} -- any k permutation is legal as long as both operands use it).  Nothing is staged in shared
 // memory; the kernel is HBM-bound (6 flop/byte) and keeps 4 chunks x MT LDG.128 in flight per lane.
-template <int MT>
+// PAIR: additionally accumulate the UNWEIGHTED product in the same pass over X (Ms = sum_j lt_j B_j B_j^T and Ns = sum_j B_j B_j^T
+// of the per-electrode-noise gradient read Bm once instead of twice); its partials follow the weighted ones in ws.
+template <int MT, bool PAIR>
 __global__ void __launch_bounds__(NTHREADS, 2) wsyrk_small_kernel(SyrkArgs p) {
   extern __shared__ __align__(16) double red[];  // [8 warps][32*32]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -235,10 +237,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) wsyrk_small_kernel(SyrkArgs p) {
   long seg = c / cps, kc = c - seg * cps;
 
   double acc[MT][MT][2];
+  double accp[PAIR ? MT : 1][PAIR ? MT : 1][2];
 #pragma unroll
   for (int i = 0; i < MT; ++i)
 #pragma unroll
-    for (int j = 0; j < MT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < MT; ++j) {
+      acc[i][j][0] = acc[i][j][1] = 0.0;
+      if (PAIR) accp[PAIR ? i : 0][PAIR ? j : 0][0] = accp[PAIR ? i : 0][PAIR ? j : 0][1] = 0.0;
+    }
 
   const double* rowp[MT];
   bool rowok[MT];
@@ -282,6 +288,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) wsyrk_small_kernel(SyrkArgs p) {
         for (int j = 0; j <= i; ++j) {
           dmma884(acc[i][j][0], acc[i][j][1], a0, v[u][j].x);
           dmma884(acc[i][j][0], acc[i][j][1], a1, v[u][j].y);
+          if (PAIR) {
+            dmma884(accp[PAIR ? i : 0][PAIR ? j : 0][0], accp[PAIR ? i : 0][PAIR ? j : 0][1], v[u][i].x, v[u][j].x);
+            dmma884(accp[PAIR ? i : 0][PAIR ? j : 0][0], accp[PAIR ? i : 0][PAIR ? j : 0][1], v[u][i].y, v[u][j].y);
+          }
         }
       }
     }
@@ -290,40 +300,45 @@ __global__ void __launch_bounds__(NTHREADS, 2) wsyrk_small_kernel(SyrkArgs p) {
   // cross-warp reduction (fixed order) -> one 32x32 partial per CTA; only lower 8x8 tiles are meaningful
   double* mine = red + warp * 1024;
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int set = 0; set < (PAIR ? 2 : 1); ++set) {
+    if (set) __syncthreads();
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      double2 o = make_double2(0.0, 0.0);
-      if (i < MT && j <= i && j < MT) o = make_double2(acc[i < MT ? i : 0][j < MT ? j : 0][0], acc[i < MT ? i : 0][j < MT ? j : 0][1]);
-      *reinterpret_cast<double2*>(mine + (8 * i + g) * 32 + 8 * j + 2 * q) = o;
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        double2 o = make_double2(0.0, 0.0);
+        if (i < MT && j <= i && j < MT) {
+          const int ii = i < MT ? i : 0, jj = j < MT ? j : 0;
+          o = (set == 0) ? make_double2(acc[ii][jj][0], acc[ii][jj][1])
+                         : make_double2(accp[PAIR ? ii : 0][PAIR ? jj : 0][0], accp[PAIR ? ii : 0][PAIR ? jj : 0][1]);
+        }
+        *reinterpret_cast<double2*>(mine + (8 * i + g) * 32 + 8 * j + 2 * q) = o;
+      }
+    __syncthreads();
+    double* out = p.ws + ((long)set * gridDim.x + blockIdx.x) * 1024;
+    for (int e = tid; e < 1024; e += NTHREADS) {
+      double sacc = 0.0;
+#pragma unroll
+      for (int w8 = 0; w8 < NTHREADS / 32; ++w8) sacc += red[w8 * 1024 + e];
+      out[e] = sacc;
     }
-  __syncthreads();
-  double* out = p.ws + (long)blockIdx.x * 1024;
-  for (int e = tid; e < 1024; e += NTHREADS) {
-    double sacc = 0.0;
-#pragma unroll
-    for (int w8 = 0; w8 < NTHREADS / 32; ++w8) sacc += red[w8 * 1024 + e];
-    out[e] = sacc;
   }
 }
 
-__global__ void wsyrk_small_reduce_kernel(const double* __restrict__ ws, int nparts, int M, double* __restrict__ C,
-                                          long ldc) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+// One WARP per output entry (128 CTAs instead of 4): lane l sums partials l, l + 32, ... and a shuffle tree closes the sum --
+// a fixed order, so the result is deterministic.  grid.y selects the weighted / unweighted set of the PAIR variant.
+__global__ void wsyrk_small_reduce_kernel(const double* __restrict__ ws, int nparts, int M, double* __restrict__ C0,
+                                          double* __restrict__ C1, long ldc) {
+  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (e >= 1024) return;
   const int r = e >> 5, cc = e & 31;
   if (r >= M || cc >= M) return;
   const int es = ((r >> 3) >= (cc >> 3)) ? e : (cc * 32 + r);  // upper tiles: mirror of the computed lower tile
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  int pidx = 0;
-  for (; pidx + 4 <= nparts; pidx += 4) {
-    s0 += ws[(long)pidx * 1024 + es];
-    s1 += ws[(long)(pidx + 1) * 1024 + es];
-    s2 += ws[(long)(pidx + 2) * 1024 + es];
-    s3 += ws[(long)(pidx + 3) * 1024 + es];
-  }
-  for (; pidx < nparts; ++pidx) s0 += ws[(long)pidx * 1024 + es];
-  C[(long)r * ldc + cc] = (s0 + s1) + (s2 + s3);
+  const double* src = ws + (long)blockIdx.y * nparts * 1024;
+  double s0 = 0.0;
+  for (int pidx = lane; pidx < nparts; pidx += 32) s0 += src[(long)pidx * 1024 + es];
+  s0 = warp_sum(s0);
+  if (lane == 0) (blockIdx.y ? C1 : C0)[(long)r * ldc + cc] = s0;
 }
 
 static int syrk_small_ctas() { return 2 * gp_num_sms(); }
@@ -343,6 +358,43 @@ static int syrk_plan(int M, int nseg, int seglen, int& bmn, int& tiles_1d, int& 
   if (ns < 1) ns = 1;
   if (ns > 65535) ns = 65535;
   nsplit = (int)ns;
+  return 0;
+}
+
+// launch the small-M SYRK (+ its reduction); pair != nullptr selects the one-pass weighted + unweighted variant
+static int wsyrk_small_launch(SyrkArgs& p, const SyrkArgs* pair, double* C0, double* C1, long ldc, cudaStream_t st) {
+  const int mt = (p.M + 7) / 8, nct = syrk_small_ctas();
+  const size_t bytes = (size_t)(NTHREADS / 32) * 1024 * sizeof(double);
+  static bool attr = false;
+  if (!attr) {
+    GP_CUDA(cudaFuncSetAttribute(wsyrk_small_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    GP_CUDA(cudaFuncSetAttribute(wsyrk_small_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    GP_CUDA(cudaFuncSetAttribute(wsyrk_small_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    GP_CUDA(cudaFuncSetAttribute(wsyrk_small_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    GP_CUDA(cudaFuncSetAttribute(wsyrk_small_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    GP_CUDA(cudaFuncSetAttribute(wsyrk_small_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    GP_CUDA(cudaFuncSetAttribute(wsyrk_small_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    GP_CUDA(cudaFuncSetAttribute(wsyrk_small_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    attr = true;
+  }
+  if (pair) {
+    switch (mt) {
+      case 1: wsyrk_small_kernel<1, true><<<nct, NTHREADS, bytes, st>>>(p); break;
+      case 2: wsyrk_small_kernel<2, true><<<nct, NTHREADS, bytes, st>>>(p); break;
+      case 3: wsyrk_small_kernel<3, true><<<nct, NTHREADS, bytes, st>>>(p); break;
+      default: wsyrk_small_kernel<4, true><<<nct, NTHREADS, bytes, st>>>(p); break;
+    }
+  } else {
+    switch (mt) {
+      case 1: wsyrk_small_kernel<1, false><<<nct, NTHREADS, bytes, st>>>(p); break;
+      case 2: wsyrk_small_kernel<2, false><<<nct, NTHREADS, bytes, st>>>(p); break;
+      case 3: wsyrk_small_kernel<3, false><<<nct, NTHREADS, bytes, st>>>(p); break;
+      default: wsyrk_small_kernel<4, false><<<nct, NTHREADS, bytes, st>>>(p); break;
+    }
+  }
+  GP_CUDA(cudaGetLastError());
+  wsyrk_small_reduce_kernel<<<dim3(1024 * 32 / 256, pair ? 2 : 1), 256, 0, st>>>(p.ws, nct, p.M, C0, C1, ldc);
+  GP_CUDA(cudaGetLastError());
   return 0;
 }
 
@@ -421,30 +473,27 @@ int gpcsd_wsyrk(int M, int nseg, int seglen, const double* X, long row_stride, l
   p.M = M; p.nseg = nseg; p.seglen = seglen; p.ws = ws;
   const long ntiles = (long)p.tiles_1d * (p.tiles_1d + 1) / 2;
   dim3 grid((unsigned)ntiles, (unsigned)p.nsplit);
-  if (bmn == 32) {
-    const int mt = (M + 7) / 8, nct = syrk_small_ctas();
-    const size_t bytes = (size_t)(NTHREADS / 32) * 1024 * sizeof(double);
-    static bool attr = false;
-    if (!attr) {
-      GP_CUDA(cudaFuncSetAttribute(wsyrk_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-      GP_CUDA(cudaFuncSetAttribute(wsyrk_small_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-      GP_CUDA(cudaFuncSetAttribute(wsyrk_small_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-      GP_CUDA(cudaFuncSetAttribute(wsyrk_small_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-      attr = true;
-    }
-    switch (mt) {
-      case 1: wsyrk_small_kernel<1><<<nct, NTHREADS, bytes, st>>>(p); break;
-      case 2: wsyrk_small_kernel<2><<<nct, NTHREADS, bytes, st>>>(p); break;
-      case 3: wsyrk_small_kernel<3><<<nct, NTHREADS, bytes, st>>>(p); break;
-      default: wsyrk_small_kernel<4><<<nct, NTHREADS, bytes, st>>>(p); break;
-    }
-    GP_CUDA(cudaGetLastError());
-    wsyrk_small_reduce_kernel<<<4, 256, 0, st>>>(ws, nct, M, C, ldc);
-  } else {
-    return tma_wsyrk(M, nseg, seglen, X, row_stride, seg_stride, w, C, ldc, ws, p.nsplit, p.tiles_1d, p.kbps, p.total_kb, st);
+  if (bmn == 32) return wsyrk_small_launch(p, nullptr, C, nullptr, ldc, st);
+  return tma_wsyrk(M, nseg, seglen, X, row_stride, seg_stride, w, C, ldc, ws, p.nsplit, p.tiles_1d, p.kbps, p.total_kb, st);
+}
+
+/* Cw = sum_seg w[seg] X_seg X_seg^T and Cp = sum_seg X_seg X_seg^T in ONE pass over X (M <= 32: the Ms / Ns pair of the
+ * per-electrode-noise gradient); larger M: two passes.  ws: 2 * gpcsd_wsyrk_ws_doubles(M, nseg, seglen). */
+int gpcsd_wsyrk_pair(int M, int nseg, int seglen, const double* X, long row_stride, long seg_stride, const double* w,
+                     double* Cw, double* Cp, long ldc, double* ws, void* stream) {
+  if (M <= 0) return 0;
+  if (M > 32) {
+    if (int e = gpcsd_wsyrk(M, nseg, seglen, X, row_stride, seg_stride, w, Cw, ldc, ws, stream)) return e;
+    return gpcsd_wsyrk(M, nseg, seglen, X, row_stride, seg_stride, nullptr, Cp, ldc, ws, stream);
   }
-  GP_CUDA(cudaGetLastError());
-  return 0;
+  if ((row_stride | seg_stride) & 1L) return gp_fail("wsyrk: strides must be even");
+  if (((uintptr_t)X | (uintptr_t)ws) & 15) return gp_fail("wsyrk: pointers must be 16-byte aligned");
+  SyrkArgs p{};
+  int bmn;
+  syrk_plan(M, nseg, seglen, bmn, p.tiles_1d, p.kbps, p.total_kb, p.nsplit);
+  p.X = X; p.row_stride = row_stride; p.seg_stride = seg_stride; p.w = w;
+  p.M = M; p.nseg = nseg; p.seglen = seglen; p.ws = ws;
+  return wsyrk_small_launch(p, &p, Cw, Cp, ldc, (cudaStream_t)stream);
 }
 
 }  // extern "C"

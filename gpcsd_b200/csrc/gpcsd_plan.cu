@@ -12,6 +12,7 @@
 //   * the result (loglik, gradient, solver flags) is assembled on the device and read back with one copy.
 // The arithmetic is the one DESIGN.md section 3 derives and engine.py orchestrates call by call; the kernels that do the
 // flops (gpcsd_dgemm, gpcsd_project_quad, gpcsd_wsyrk, gpcsd_eigh_dc) are shared with it.
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -277,14 +278,18 @@ __global__ void eig_D_cols_kernel(Dims d, const double* __restrict__ ls, const d
     for (int i = 0; i < d.nx; ++i) b += lsr[i] * rD[((long)r * d.nx + i) * ldrd + j];
     colB[(long)r * d.nt + j] = b;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  if (blockIdx.x == 0 && threadIdx.x < 32) {          // warp 0: the two scalars (fixed lane order -> deterministic)
     double sl = 0.0, sc = 0.0;
-    for (int i = 0; i < d.nx; ++i) {
+    for (int i = threadIdx.x; i < d.nx; i += 32) {
       sl += rowL[(long)r * d.nx + i];
       sc += rowC[(long)r * d.nx + i];
     }
-    res[(long)r * RESW + 2] = sl;
-    res[(long)r * RESW + 3] = sc;
+    sl = warp_sum(sl);
+    sc = warp_sum(sc);
+    if (threadIdx.x == 0) {
+      res[(long)r * RESW + 2] = sl;
+      res[(long)r * RESW + 3] = sc;
+    }
   }
 }
 
@@ -355,9 +360,7 @@ __global__ void assemble_kernel(Dims d, const double* __restrict__ theta, const 
     } else if (e == d.P + 1) {
       v = q[26];
     } else if (e >= d.P + 2) {
-      double c = 0.0;
-      for (int k = 0; k < d.P; ++k) c += sin(1.0 + k) * log(fmax(theta[(long)r * d.P + k], 1e-300));
-      v = (e == d.P + 2 ? c : c * c) * det_frac;
+      v = theta[(long)gridDim.x * d.P + 2 * r + (e - d.P - 2)] * det_frac;     // checksum pair, computed by the host with theta
     } else if (want_grad) {
       const int k = e - 1;
       if (k == 0) v = 2.0 * q[4];
@@ -433,7 +436,7 @@ struct Plan {
   double *eigws;  long eigws_doubles;
   int* info;      int ninfo;
   double *rD, *rowA, *rowC, *rowL, *colB;
-  double *Z, *Zf, *Bm, *Yf;                            // [R][nx][nt][ldn] (Yf: [nx][nt][ldn])
+  double *Z, *Bm, *Yf;                                 // Z, Bm: [R][nx][nt][ldn]; Yf: the LFP in the evaluation basis [nx][nt][ldn]
   double *pq_ws;  long pq_ws_doubles;                  // per restart
   double *syrk_ws_t, *syrk_ws_s; long syrk_t_doubles, syrk_s_doubles;
   double *dot_ws; long dot_ws_doubles;                 // per restart
@@ -517,7 +520,7 @@ int gpcsd_plan_create(void** out_plan, int dim, int nx, int nt, const double* h_
                cudaMemcpy(p->rb, h_rb, (nx / 2) * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess)) e = 1;
   }
   const size_t outw = (size_t)p->d.P + 4;
-  if (cudaMallocHost((void**)&p->h_theta, (size_t)max_restarts * p->d.P * sizeof(double)) != cudaSuccess) e = 1;
+  if (cudaMallocHost((void**)&p->h_theta, (size_t)max_restarts * (p->d.P + 2) * sizeof(double)) != cudaSuccess) e = 1;
   if (cudaMallocHost((void**)&p->h_out, (size_t)max_restarts * outw * sizeof(double)) != cudaSuccess) e = 1;
   for (int k = 0; k < 2; ++k)
     if (cudaStreamCreateWithFlags(&p->side[k], cudaStreamNonBlocking) != cudaSuccess) e = 1;
@@ -563,7 +566,7 @@ static size_t layout(Plan* p, char* base, long ldn, int N) {
   const pl::Dims& d = p->d;
   const long R = p->Rmax, nx = d.nx, nt = d.nt, G = d.G, ldx = p->ldx, ldt = p->ldt;
   const int outw = d.P + 4;
-  p->theta = b.take<double>(R * d.P);
+  p->theta = b.take<double>(R * (d.P + 2));
   p->out = b.take<double>(R * outw);
   p->res = b.take<double>(R * pl::RESW);
   p->A = b.take<double>(R * nx * G); p->dA = b.take<double>(R * nx * G); p->U = b.take<double>(R * nx * G);
@@ -607,15 +610,15 @@ static size_t layout(Plan* p, char* base, long ldn, int N) {
   p->rowA = b.take<double>(R * nx); p->rowC = b.take<double>(R * nx); p->rowL = b.take<double>(R * nx);
   p->colB = b.take<double>(R * nt);
   const long slab = nx * nt * ldn;
-  p->Z = b.take<double>(R * slab); p->Zf = p->t_fold ? b.take<double>(R * slab) : nullptr; p->Bm = b.take<double>(R * slab);
-  p->Yf = p->s_split ? b.take<double>(slab) : nullptr;
+  p->Z = b.take<double>(R * slab); p->Bm = b.take<double>(R * slab);
+  p->Yf = (p->s_split || p->t_fold) ? b.take<double>(slab) : nullptr;
   const int Nn = N > 0 ? N : 1;
   long pq = 0;
   for (int o : {d.nt, p->tm, p->tms}) { long w = gpcsd_project_quad_ws_doubles(d.nx, o, Nn); if (w > pq) pq = w; }
   p->pq_ws_doubles = pq; p->pq_ws = b.take<double>(R * pq);
   long st = 2, ss = 2;
   for (int o : {d.nt, p->tm, p->tms}) { long w = gpcsd_wsyrk_ws_doubles(o, d.nx, Nn); if (w > st) st = w; }
-  for (int o : {d.nx, p->sm > 0 ? p->sm : 1}) { long w = gpcsd_wsyrk_ws_doubles(o, d.nt, Nn); if (w > ss) ss = w; }
+  for (int o : {d.nx, p->sm > 0 ? p->sm : 1}) { long w = 2 * gpcsd_wsyrk_ws_doubles(o, d.nt, Nn); if (w > ss) ss = w; }
   p->syrk_t_doubles = st; p->syrk_s_doubles = ss;
   p->syrk_ws_t = b.take<double>(R * st); p->syrk_ws_s = b.take<double>(R * ss);
   p->dot_ws_doubles = 4L * gp_num_sms() + 8; p->dot_ws = b.take<double>(R * p->dot_ws_doubles);
@@ -824,21 +827,30 @@ int enqueue_body(Plan* p, int R, int want_grad, const Factors* fac, cudaStream_t
       ninfo += R;
     }
     if (N > 0) {
+      // The symmetry folds act on the DATA axes and commute with the projections: the LFP is moved to the evaluation basis
+      // (channel fold for reflection-symmetric geometries, centrosymmetric time fold on uniform grids) ONCE per upload, so
+      // Z = Qs^T Y comes out directly in the folded time basis -- no per-evaluation fold pass over the trial data.
+      if ((p->s_split || p->t_fold) && !p->yf_valid) {
+        if (p->s_split && p->t_fold) {
+          PL_CHECK(gpcsd_pairsym_fold(nx, p->ra, p->rb, row, p->Y, p->Z, sS));       // Z (restart 0) is free here: scratch
+          PL_CHECK(gpcsd_centro_fold(nx, nt, ldn, p->Z, p->Yf, sS));
+          p->launches += 2;
+        } else if (p->s_split) {
+          PL_CHECK(gpcsd_pairsym_fold(nx, p->ra, p->rb, row, p->Y, p->Yf, sS));
+          p->launches += 1;
+        } else {
+          PL_CHECK(gpcsd_centro_fold(nx, nt, ldn, p->Y, p->Yf, sS));
+          p->launches += 1;
+        }
+      }
+      const double* Ysrc = (p->s_split || p->t_fold) ? p->Yf : p->Y;
       if (use_ssplit) {
         const int m = p->sm;
         const long ldm = p->sldm, sM = (long)m * ldm;
-        if (!p->yf_valid) {
-          PL_CHECK(gpcsd_pairsym_fold(nx, p->ra, p->rb, row, p->Y, p->Yf, sS));
-          p->launches += 1;
-        }
-        PL_CHECK(gemm_shared_b(p, R, m, (int)row, m, p->uS, ldm, sM, p->Yf, row, p->Z, row, slab, sS));
-        PL_CHECK(gemm_shared_b(p, R, m, (int)row, m, p->uS + R * sM, ldm, sM, p->Yf + (long)m * row, row, p->Z + (long)m * row, row, slab, sS));
+        PL_CHECK(gemm_shared_b(p, R, m, (int)row, m, p->uS, ldm, sM, Ysrc, row, p->Z, row, slab, sS));
+        PL_CHECK(gemm_shared_b(p, R, m, (int)row, m, p->uS + R * sM, ldm, sM, Ysrc + (long)m * row, row, p->Z + (long)m * row, row, slab, sS));
       } else {
-        PL_CHECK(gemm_shared_b(p, R, nx, (int)row, nx, p->QsT, ldx, nx * ldx, p->Y, row, p->Z, row, slab, sS));
-      }
-      if (use_tfold) {
-        PL_CHECK(gpcsd_centro_fold(R * nx, nt, ldn, p->Z, p->Zf, sS));
-        p->launches += 1;
+        PL_CHECK(gemm_shared_b(p, R, nx, (int)row, nx, p->QsT, ldx, nx * ldx, Ysrc, row, p->Z, row, slab, sS));
       }
     }
     GP_CUDA(cudaEventRecord(p->ev[1], sS));
@@ -881,7 +893,7 @@ int enqueue_body(Plan* p, int R, int want_grad, const Factors* fac, cudaStream_t
   PL_LAUNCH(1);
 
   // ---------------- projection A_i = Qt^T Z_i with the fused /D + quadratic form (hot loop gpcsd1d.py:124-126)
-  const double* Zuse = use_tfold ? p->Zf : p->Z;
+  const double* Zuse = p->Z;
   if (N > 0) {
     for (int r = 0; r < R; ++r) {
       double* res = p->res + (long)r * pl::RESW;
@@ -966,11 +978,14 @@ int enqueue_body(Plan* p, int R, int want_grad, const Factors* fac, cudaStream_t
           PL_CHECK(gpcsd_wsyrk(mh, nt, N, Br, row, ldn, ltr, Ms, ldx, wsS, sG));
           PL_CHECK(gpcsd_wsyrk(mh, nt, N, Br + (long)mh * row, row, ldn, ltr, Ms + (long)mh * ldx + mh, ldx, wsS, sG));
           p->launches += 4;
+        } else if (vec) {  // per-electrode noise: Ms and Ns from one pass over Bm
+          PL_CHECK(gpcsd_wsyrk_pair(nx, nt, N, Br, row, ldn, ltr, Ms, p->Ns + (long)r * nx * ldx, ldx, wsS, sG));
+          p->launches += (nx <= 32) ? 2 : 4;
         } else {
           PL_CHECK(gpcsd_wsyrk(nx, nt, N, Br, row, ldn, ltr, Ms, ldx, wsS, sG));
           p->launches += 2;
         }
-        if (vec) {
+        if (vec && blockS) {
           PL_CHECK(gpcsd_wsyrk(nx, nt, N, Br, row, ldn, nullptr, p->Ns + (long)r * nx * ldx, ldx, wsS, sG));
           p->launches += 2;
         }
@@ -1011,7 +1026,7 @@ int enqueue_body(Plan* p, int R, int want_grad, const Factors* fac, cudaStream_t
   pl::assemble_kernel<<<R, 64, 0, st>>>(d, p->theta, p->res, p->rowC, p->Ns, ldx, nx * ldx, p->ntot, p->det_frac, want_grad, p->out,
                                         d.P + 4);
   PL_LAUNCH(1);
-  if (use_ssplit && N > 0) p->yf_valid = 1;
+  if ((p->s_split || p->t_fold) && !fac && N > 0) p->yf_valid = 1;
   return 0;
 }
 
@@ -1022,11 +1037,26 @@ extern "C" {
 // Upload R hyperparameter vectors (host, natural units, [R][P] in the gradient's order R, ell(s), (ell_t, sigma2_t)..., sig2n[...])
 // and enqueue the whole evaluation on `stream`; the partial result of this rank is left in gpcsd_plan_device_result()
 // ([R][P+4]: loglik, gradient, solver flag, hyperparameter checksum pair) for an optional all-reduce by the caller before gpcsd_plan_finish.
+// theta[R][P] followed by the checksum pairs (c, c^2)[R], c = sum_k sin(1 + k) log theta_k, into the pinned staging buffer
+static void stage_theta(Plan* p, int R, const double* h_theta) {
+  const int P = p->d.P;
+  memcpy(p->h_theta, h_theta, (size_t)R * P * sizeof(double));
+  for (int r = 0; r < R; ++r) {
+    double c = 0.0;
+    for (int k = 0; k < P; ++k) {
+      const double v = h_theta[(size_t)r * P + k];
+      c += sin(1.0 + k) * log(v > 1e-300 ? v : 1e-300);
+    }
+    p->h_theta[(size_t)R * P + 2 * r] = c;
+    p->h_theta[(size_t)R * P + 2 * r + 1] = c * c;
+  }
+}
+
 static int enqueue_on_own(Plan* p, int R, int want_grad, size_t nb) {
   cudaStream_t st = p->own;
   const long key = (long)R * 2 + (want_grad ? 1 : 0);
   // (the channel-folded copy Yf is rebuilt eagerly after every new upload; graphs are recorded without that step)
-  const bool graphable = p->use_graph && !needs_cusolver(p) && (!p->s_split || p->yf_valid || p->N == 0);
+  const bool graphable = p->use_graph && !needs_cusolver(p) && (!(p->s_split || p->t_fold) || p->yf_valid || p->N == 0);
   if (graphable) {
     auto it = p->graphs.find(key);
     if (it != p->graphs.end()) {
@@ -1085,8 +1115,8 @@ int gpcsd_plan_enqueue(void* plan, int R, const double* h_theta, int want_grad, 
   if (!p->ws) return fail_plan("plan: no LFP / workspace bound (gpcsd_plan_set_lfp)");
   if (R < 1 || R > p->Rmax) return fail_plan("plan: restart count out of range");
   cudaStream_t caller = (cudaStream_t)stream;
-  const size_t nb = (size_t)R * p->d.P * sizeof(double);
-  memcpy(p->h_theta, h_theta, nb);
+  const size_t nb = (size_t)R * (p->d.P + 2) * sizeof(double);
+  stage_theta(p, R, h_theta);
   // the evaluation runs on the plan's own stream (the caller's may be the legacy default stream, which cannot be captured),
   // ordered after everything already enqueued on the caller's stream and before everything enqueued there afterwards
   GP_CUDA(cudaEventRecord(p->ev[6], caller));
@@ -1124,8 +1154,8 @@ int gpcsd_plan_loglik_grad_factors(void* plan, const double* h_theta, const doub
   Plan* p = (Plan*)plan;
   if (!p->ws) return fail_plan("plan: no LFP / workspace bound (gpcsd_plan_set_lfp)");
   cudaStream_t caller = (cudaStream_t)stream, st = p->own;
-  const size_t nb = (size_t)p->d.P * sizeof(double);
-  memcpy(p->h_theta, h_theta, nb);
+  const size_t nb = (size_t)(p->d.P + 2) * sizeof(double);
+  stage_theta(p, 1, h_theta);
   GP_CUDA(cudaEventRecord(p->ev[6], caller));
   GP_CUDA(cudaStreamWaitEvent(st, p->ev[6], 0));
   GP_CUDA(cudaMemcpyAsync(p->theta, p->h_theta, nb, cudaMemcpyHostToDevice, st));

@@ -385,29 +385,36 @@ __global__ void __launch_bounds__(T_THREADS, 1)
       *reinterpret_cast<double2*>(out + ((((warp * T_MT + i) * 4 + j) * 32 + lane) << 1)) = make_double2(acc[i][j][0], acc[i][j][1]);
 }
 
-// sum the split-K partials in fixed order, un-permute the fragment layout, mirror the upper triangle
-__global__ void tma_wsyrk_reduce_kernel(const double* __restrict__ ws, int nsplit, int tiles_1d, int M,
-                                        double* __restrict__ C, long ldc) {
+// sum the split-K partials in fixed order, un-permute the fragment layout, mirror the upper triangle.
+// Block = 64 consecutive fragment-order elements x 4 split groups (group s sums splits s, s + 4, ...; the four group sums
+// are added in order through shared memory): four times the loads in flight of a one-thread-per-element sum, which was
+// latency-bound at 14 % of HBM bandwidth.
+__global__ void __launch_bounds__(256) tma_wsyrk_reduce_kernel(const double* __restrict__ ws, int nsplit, int tiles_1d, int M,
+                                                               double* __restrict__ C, long ldc) {
+  __shared__ double part[4][64];
   const long ntiles = (long)tiles_1d * (tiles_1d + 1) / 2;
   const int t = blockIdx.y;
   int tm = 0;
   while ((tm + 1) * (tm + 2) / 2 <= t) ++tm;
   const int tn = t - tm * (tm + 1) / 2;
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;  // fragment-order element index
-  if (e >= T_BM * T_BN) return;
+  const int el = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  const int e = blockIdx.x * 64 + el;                   // fragment-order element index
+  double s0 = 0.0, s1 = 0.0;
+  int sp = grp;
+  for (; sp + 4 < nsplit; sp += 8) {
+    s0 += ws[((long)sp * ntiles + t) * (T_BM * T_BN) + e];
+    s1 += ws[((long)(sp + 4) * ntiles + t) * (T_BM * T_BN) + e];
+  }
+  if (sp < nsplit) s0 += ws[((long)sp * ntiles + t) * (T_BM * T_BN) + e];
+  part[grp][el] = s0 + s1;
+  __syncthreads();
+  if (grp != 0) return;
+  const double s = (part[0][el] + part[1][el]) + (part[2][el] + part[3][el]);
   const int v = e & 1, lane = (e >> 1) & 31, j = (e >> 6) & 3, i = (e >> 8) % T_MT, warp = (e >> 8) / T_MT;
   const int g = lane >> 2, q = lane & 3, wm = warp % T_WARPS_M, wn = warp / T_WARPS_M;
   const int r = wm * T_WM + 8 * i + perm8(g), c = wn * T_WN + 8 * j + q + 4 * v;
   const int m = tm * T_BM + r, n = tn * T_BN + c;
   if (m >= M || n >= M) return;
-  double s0 = 0.0, s1 = 0.0;
-  int sp = 0;
-  for (; sp + 2 <= nsplit; sp += 2) {
-    s0 += ws[((long)sp * ntiles + t) * (T_BM * T_BN) + e];
-    s1 += ws[((long)(sp + 1) * ntiles + t) * (T_BM * T_BN) + e];
-  }
-  if (sp < nsplit) s0 += ws[((long)sp * ntiles + t) * (T_BM * T_BN) + e];
-  const double s = s0 + s1;
   C[(long)m * ldc + n] = s;
   if (tm != tn) C[(long)n * ldc + m] = s;
 }
@@ -556,7 +563,7 @@ int tma_wsyrk(int M, int nseg, int seglen, const double* X, long row_stride, lon
   const long ntiles = (long)tiles_1d * (tiles_1d + 1) / 2;
   tma_wsyrk_kernel<<<dim3((unsigned)ntiles, (unsigned)nsplit), T_THREADS, T_SMEM_BYTES, st>>>(tX, p);
   GP_CUDA(cudaGetLastError());
-  tma_wsyrk_reduce_kernel<<<dim3(T_BM * T_BN / 256, (unsigned)ntiles), 256, 0, st>>>(ws, nsplit, tiles_1d, M, C, ldc);
+  tma_wsyrk_reduce_kernel<<<dim3(T_BM * T_BN / 64, (unsigned)ntiles), 256, 0, st>>>(ws, nsplit, tiles_1d, M, C, ldc);
   GP_CUDA(cudaGetLastError());
   return 0;
 }

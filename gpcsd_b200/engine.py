@@ -646,7 +646,7 @@ class KronEngine:
         """Largest restart batch (<= want) whose plan workspace fits in half of the free device memory."""
         free, _ = torch.cuda.mem_get_info(self.device)
         slab = 8 * self.nx * self.nt * self.ldn
-        per = (3 if self._t_fold() else 2) * slab + 8 * (7 * self.nx * self.G + 8 * self.nx * self.ldx + 8 * self.nt * self.ldt) + (64 << 20)
+        per = 2 * slab + 8 * (7 * self.nx * self.G + 8 * self.nx * self.ldx + 8 * self.nt * self.ldt) + (64 << 20)
         return int(max(1, min(want, (free // 2) // max(per, 1))))
 
     def loglik_grad_batch(self, hps, want_grad=True):

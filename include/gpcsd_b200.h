@@ -88,6 +88,11 @@ int gpcsd_wsyrk(int M, int nseg, int seglen,
                 const double* X, long row_stride, long seg_stride,
                 const double* w, double* C, long ldc, double* ws, void* stream);
 
+/* Cw = sum_seg w[seg] X_seg X_seg^T and Cp = sum_seg X_seg X_seg^T in ONE pass over X when M <= 32 (the Ms / Ns pair of the
+ * per-electrode-noise gradient: both read Bm); two passes above.  ws: 2 * gpcsd_wsyrk_ws_doubles(M, nseg, seglen) doubles. */
+int gpcsd_wsyrk_pair(int M, int nseg, int seglen, const double* X, long row_stride, long seg_stride, const double* w,
+                     double* Cw, double* Cp, long ldc, double* ws, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Eigendecomposition of the small factors (np.linalg.eigh in comp_eig_D, utility_functions.py:58-59).
  * cuSOLVER syevd on a copy; returns eigenvalues ascending in W and Q^T row-major (== column-major Q)

@@ -121,6 +121,28 @@ def test_wsyrk_both_orientations(cuda_lib, nx, nt, N, weighted):
     assert relerr(Ms[:, :nx].cpu().numpy(), ref) < 1e-12
 
 
+@pytest.mark.parametrize("nx,nt,N", [(24, 50, 50), (24, 500, 333), (5, 140, 300), (130, 9, 33), (3, 3, 1)])
+def test_wsyrk_pair_one_pass(cuda_lib, nx, nt, N):
+    """Ms = sum_j lt_j B_j B_j^T and Ns = sum_j B_j B_j^T from one pass over Bm (nx <= 32) or two (nx > 32)."""
+    from gpcsd_b200 import _lib as L
+    rng = np.random.default_rng(nx + 7 * nt + N)
+    ldn = (N + 7) // 8 * 8
+    Bm = np.zeros((nx, nt, ldn))
+    Bm[:, :, :N] = rng.standard_normal((nx, nt, N))
+    Bm[:, :, N:] = 99.0
+    lt = rng.standard_normal(nt)
+    Bd, ltd = torch.from_numpy(Bm).cuda(), torch.from_numpy(lt).cuda()
+    B = Bm[:, :, :N]
+    ldx = _ld(nx)
+    Ms = torch.zeros((nx, ldx), dtype=F64, device="cuda")
+    Ns = torch.zeros((nx, ldx), dtype=F64, device="cuda")
+    ws = torch.zeros(2 * L.query("gpcsd_wsyrk_ws_doubles", nx, nt, N), dtype=F64, device="cuda")
+    L.call("gpcsd_wsyrk_pair", nx, nt, N, Bd.data_ptr(), nt * ldn, ldn, ltd.data_ptr(), Ms.data_ptr(), Ns.data_ptr(), ldx,
+           ws.data_ptr(), _stream())
+    assert relerr(Ms[:, :nx].cpu().numpy(), np.einsum("ajr,j,bjr->ab", B, lt, B)) < 1e-12
+    assert relerr(Ns[:, :nx].cpu().numpy(), np.einsum("ajr,bjr->ab", B, B)) < 1e-12
+
+
 @pytest.mark.parametrize("n", [5, 24, 100, 251])
 def test_eigh(cuda_lib, n):
     from gpcsd_b200 import _lib as L
