@@ -84,6 +84,8 @@ SIGNATURES = {
     "gpcsd_plan_device_result": (c_void_p, [_P]),
     "gpcsd_plan_device_theta": (c_void_p, [_P]),
     "gpcsd_plan_last_launches": (c_long, [_P]),
+    "gpcsd_plan_mailbox_bytes": (c_long, [_P, c_int]),
+    "gpcsd_plan_set_mailbox": (c_int, [_P, _P, c_long, c_int, c_int]),
     "gpcsd_plan_loglik_grad_factors": (c_int, [_P, POINTER(c_double), _P, _P, _P, _P, c_int, POINTER(c_double), _P]),
     "gpcsd_fwd_operator_1d": (c_int, [c_int, _P, c_int, _P, c_double, c_double, _P, c_long, _P]),
     "gpcsd_fwd_operator_2d": (c_int, [c_int, _P, c_int, _P, c_int, _P, c_double, c_double, _P, c_long, _P]),

@@ -16,6 +16,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <chrono>
 
 #include <unordered_map>
@@ -376,6 +377,25 @@ __global__ void assemble_kernel(Dims d, const double* __restrict__ theta, const 
   }
 }
 
+// ---- result mailbox: this rank's [n] result vector -> its slot of a host-mapped shared segment, then the sequence flag.
+// The ranks of a trial-sharded model read each other's slots on the host (gpcsd_plan_finish): the all-reduce of ~70 doubles
+// costs one posted PCIe write per rank, no device-side waiting, no collective kernel and no device->host copy.
+__global__ void publish_kernel(const double* __restrict__ out, int n, unsigned char* __restrict__ slot, long parity_bytes,
+                               unsigned long long* __restrict__ seq_dev) {
+  __shared__ unsigned long long seq;
+  if (threadIdx.x == 0) seq = seq_dev[0] + 1ull;
+  __syncthreads();
+  unsigned char* base = slot + (seq & 1ull) * parity_bytes;
+  volatile double* dst = reinterpret_cast<volatile double*>(base + 64);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = out[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *reinterpret_cast<volatile unsigned long long*>(base) = seq;     // data first, flag second (fence above)
+    seq_dev[0] = seq;
+  }
+}
+
 }  // namespace plan
 }  // namespace gpcsd
 
@@ -452,6 +472,12 @@ struct Plan {
   std::unordered_map<long, int> warmed;
   int use_graph;
   long launches;                                      // kernels launched by the last enqueue
+  // result mailbox shared by the ranks of a trial-sharded model (host-mapped POSIX shared memory)
+  unsigned char *mb_host, *mb_dev;
+  long mb_slot_bytes, mb_parity_bytes;
+  int world, rank;
+  unsigned long long* seq_dev;
+  unsigned long long seq_host;
 };
 
 int fail_plan(const char* m) { return gp_fail(m); }
@@ -499,6 +525,8 @@ int gpcsd_plan_create(void** out_plan, int dim, int nx, int nt, const double* h_
   p->ws = nullptr; p->ws_bytes = 0;
   p->use_graph = 1;
   p->launches = 0;
+  p->mb_host = p->mb_dev = nullptr; p->mb_slot_bytes = p->mb_parity_bytes = 0; p->world = 1; p->rank = 0;
+  p->seq_dev = nullptr; p->seq_host = 0;
   // geometry
   auto upload = [&](double** dst, const double* src, size_t n) -> int {
     GP_CUDA(cudaMalloc((void**)dst, (n ? n : 1) * sizeof(double)));
@@ -553,6 +581,8 @@ int gpcsd_plan_destroy(void* plan) {
   cudaFree(p->x); cudaFree(p->t); cudaFree(p->g1); cudaFree(p->w1); cudaFree(p->g2); cudaFree(p->w2);
   cudaFree(p->ra); cudaFree(p->rb);
   cudaFreeHost(p->h_theta); cudaFreeHost(p->h_out);
+  if (p->mb_host) cudaHostUnregister(p->mb_host);
+  cudaFree(p->seq_dev);
   for (int k = 0; k < 2; ++k) cudaStreamDestroy(p->side[k]);
   cudaStreamDestroy(p->own);
   for (int k = 0; k < 8; ++k) cudaEventDestroy(p->ev[k]);
@@ -1026,6 +1056,11 @@ int enqueue_body(Plan* p, int R, int want_grad, const Factors* fac, cudaStream_t
   pl::assemble_kernel<<<R, 64, 0, st>>>(d, p->theta, p->res, p->rowC, p->Ns, ldx, nx * ldx, p->ntot, p->det_frac, want_grad, p->out,
                                         d.P + 4);
   PL_LAUNCH(1);
+  if (p->mb_dev && !fac) {
+    pl::publish_kernel<<<1, 256, 0, st>>>(p->out, R * (d.P + 4), p->mb_dev + (long)p->rank * p->mb_slot_bytes, p->mb_parity_bytes,
+                                          p->seq_dev);
+    PL_LAUNCH(1);
+  }
   if ((p->s_split || p->t_fold) && !fac && N > 0) p->yf_valid = 1;
   return 0;
 }
@@ -1133,9 +1168,68 @@ int gpcsd_plan_finish(void* plan, int R, double* h_out, void* stream) {
   Plan* p = (Plan*)plan;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t nb = (size_t)R * (p->d.P + 4) * sizeof(double);
+  if (p->mb_host) {
+    // all-reduce through the mailbox: wait for every rank's slot to carry this evaluation's sequence number, then sum the
+    // vectors in RANK ORDER (deterministic, bit-identical on every rank).  Two parity buffers per slot: a rank can be at most
+    // one evaluation ahead of the slowest one, because finishing evaluation k needs every rank's slot of evaluation k.
+    const unsigned long long want = ++p->seq_host;
+    const long n = (long)R * (p->d.P + 4);
+    for (long i = 0; i < n; ++i) h_out[i] = 0.0;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int q = 0; q < p->world; ++q) {
+      const unsigned char* base = p->mb_host + (long)q * p->mb_slot_bytes + (long)(want & 1ull) * p->mb_parity_bytes;
+      const volatile unsigned long long* flag = reinterpret_cast<const volatile unsigned long long*>(base);
+      unsigned long spins = 0;
+      while (*flag != want) {
+        if ((++spins & 0xFFFF) == 0) {
+          const cudaError_t qe = cudaStreamQuery(st);
+          if (qe != cudaSuccess && qe != cudaErrorNotReady) return gp_fail_cuda(qe, "waiting for the result mailbox", __LINE__);
+          if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 120.0)
+            return fail_plan("plan: timed out waiting for a rank's result (ranks must issue the same evaluations)");
+        }
+      }
+      std::atomic_thread_fence(std::memory_order_acquire);
+      const volatile double* src = reinterpret_cast<const volatile double*>(base + 64);
+      for (long i = 0; i < n; ++i) h_out[i] += src[i];
+    }
+    return 0;
+  }
   GP_CUDA(cudaMemcpyAsync(p->h_out, p->out, nb, cudaMemcpyDeviceToHost, st));
   GP_CUDA(cudaStreamSynchronize(st));
   memcpy(h_out, p->h_out, nb);
+  return 0;
+}
+
+// Result mailbox of a trial-sharded model: ONE host shared-memory segment (POSIX shm, zero-initialised) mapped by every rank
+// of the node.  gpcsd_plan_mailbox_bytes gives its size; gpcsd_plan_set_mailbox registers this rank's mapping with CUDA
+// (host-mapped, so the evaluation's last kernel writes the result straight into it) and switches gpcsd_plan_finish to the
+// mailbox all-reduce.  Every rank must then issue the same sequence of evaluations (as with any collective).
+long gpcsd_plan_mailbox_bytes(void* plan, int world) {
+  if (!plan || world < 1) return -1;
+  Plan* p = (Plan*)plan;
+  const long data = ((long)p->Rmax * (p->d.P + 4) * 8 + 63) / 64 * 64;
+  const long slot = 2 * (64 + data);
+  return ((long)world * slot + 4095) / 4096 * 4096;
+}
+
+int gpcsd_plan_set_mailbox(void* plan, void* h_shared, long bytes, int world, int rank) {
+  if (!plan) return fail_plan("null plan");
+  Plan* p = (Plan*)plan;
+  if (world < 2 || rank < 0 || rank >= world) return fail_plan("plan_set_mailbox: bad world / rank");
+  if (bytes < gpcsd_plan_mailbox_bytes(plan, world)) return fail_plan("plan_set_mailbox: segment too small");
+  if (p->mb_host) return fail_plan("plan_set_mailbox: mailbox already set");
+  GP_CUDA(cudaHostRegister(h_shared, (size_t)bytes, cudaHostRegisterMapped | cudaHostRegisterPortable));
+  void* dptr = nullptr;
+  GP_CUDA(cudaHostGetDevicePointer(&dptr, h_shared, 0));
+  GP_CUDA(cudaMalloc((void**)&p->seq_dev, sizeof(unsigned long long)));
+  GP_CUDA(cudaMemset(p->seq_dev, 0, sizeof(unsigned long long)));
+  const long data = ((long)p->Rmax * (p->d.P + 4) * 8 + 63) / 64 * 64;
+  p->mb_parity_bytes = 64 + data;
+  p->mb_slot_bytes = 2 * p->mb_parity_bytes;
+  p->mb_host = (unsigned char*)h_shared;
+  p->mb_dev = (unsigned char*)dptr;
+  p->world = world; p->rank = rank; p->seq_host = 0;
+  drop_graphs(p);
   return 0;
 }
 

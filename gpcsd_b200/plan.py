@@ -58,6 +58,8 @@ class EvalPlan:
         self.outw = self.P + 4
         self.ws = None
         self._bound = None
+        self._mailbox = None
+        self._mailbox_tried = False
         self.n_replays = 0
 
     def __del__(self):
@@ -91,6 +93,45 @@ class EvalPlan:
                float(eng.shard.det_fraction()), self.ws.data_ptr(), self.ws.numel() * 8)
         self._bound = (key, eng._lfp_version)
 
+    def setup_mailbox(self):
+        """Trial-sharded model with all ranks on one node: create / attach the shared host segment of the result mailbox
+        (gpcsd_plan_set_mailbox) so that the per-evaluation all-reduce needs neither NCCL nor a device->host copy.  Collective
+        over the shard's process group (every rank must call it).  Returns True when the mailbox is active."""
+        import mmap
+        import os
+        import socket
+        import uuid
+        import torch.distributed as dist
+        sh = self.eng.shard
+        if self._mailbox is not None or not (sh.enabled and sh.world > 1) or os.environ.get("GPCSD_MAILBOX", "1") == "0":
+            return self._mailbox is not None
+        hosts = [None] * sh.world
+        dist.all_gather_object(hosts, socket.gethostname(), group=sh.group)
+        if len(set(hosts)) != 1:
+            return False                                   # multi-node: stay on the NCCL path
+        nbytes = int(L.query("gpcsd_plan_mailbox_bytes", self.handle, sh.world))
+        box = [None]
+        path = None
+        if sh.rank == 0:
+            path = "/dev/shm/gpcsd_b200_%s" % uuid.uuid4().hex
+            fd = os.open(path, os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
+            os.ftruncate(fd, nbytes)                       # zero-filled
+            box[0] = path
+        src = dist.get_global_rank(sh.group, 0) if sh.group is not None else 0
+        dist.broadcast_object_list(box, src=src, group=sh.group)
+        if sh.rank != 0:
+            fd = os.open(box[0], os.O_RDWR)
+        mm = mmap.mmap(fd, nbytes, mmap.MAP_SHARED, mmap.PROT_READ | mmap.PROT_WRITE)
+        os.close(fd)
+        addr = ctypes.addressof(ctypes.c_char.from_buffer(mm))
+        with torch.cuda.device(self.eng.device):
+            L.call("gpcsd_plan_set_mailbox", self.handle, addr, nbytes, sh.world, sh.rank)
+        dist.barrier(group=sh.group)                       # every rank has mapped the segment: the name can go
+        if sh.rank == 0:
+            os.unlink(path)
+        self._mailbox = mm
+        return True
+
     def device_result(self, R):
         """The plan's device result [R][P+4] as a torch view into the workspace (for the trial-shard all-reduce)."""
         ptr = L.load().gpcsd_plan_device_result(self.handle)
@@ -111,12 +152,17 @@ class EvalPlan:
             stream.wait_event(eng._y_ready)
         out = np.empty((R, self.outw), dtype=np.float64)
         sharded = eng.shard.enabled and eng.shard.world > 1
-        if not sharded:
+        if sharded and self._mailbox is None and not self._mailbox_tried:
+            self._mailbox_tried = True
+            self.setup_mailbox()
+        if not sharded or self._mailbox is not None:
+            # single rank, or the ranks' results meet in the host-mapped mailbox inside gpcsd_plan_finish
             L.call("gpcsd_plan_loglik_grad", self.handle, R, _pd(thetas), 1 if want_grad else 0, _pd(out), stream.cuda_stream)
         else:
             L.call("gpcsd_plan_enqueue", self.handle, R, _pd(thetas), 1 if want_grad else 0, stream.cuda_stream)
             eng.shard.allreduce_inplace(self.device_result(R))
             L.call("gpcsd_plan_finish", self.handle, R, _pd(out), stream.cuda_stream)
+        if sharded:
             mean, meansq = out[:, self.P + 2], out[:, self.P + 3]
             if np.any(np.abs(meansq - mean * mean) > 1e-9 * np.maximum(np.abs(meansq), 1e-300)):
                 raise RuntimeError("trial-sharded evaluation: the ranks hold different hyperparameters; seed numpy identically "

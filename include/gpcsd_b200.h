@@ -272,6 +272,14 @@ int gpcsd_plan_finish(void* plan, int R, double* h_out, void* stream);
 double* gpcsd_plan_device_result(void* plan);
 double* gpcsd_plan_device_theta(void* plan);
 long gpcsd_plan_last_launches(void* plan);                      /* kernels launched by the last non-replayed evaluation */
+/* Trial-sharded models on one node: the per-evaluation all-reduce of the [R][P+4] result (the sum over `trial` of
+ * gpcsd1d.py:124-126 split over ranks) through a host-mapped mailbox.  h_shared: ONE zero-initialised POSIX shared-memory
+ * segment of gpcsd_plan_mailbox_bytes(plan, world) bytes mapped by every rank.  After gpcsd_plan_set_mailbox the last kernel of
+ * every evaluation writes this rank's result and a sequence flag into its slot, and gpcsd_plan_finish sums all slots in rank
+ * order on the host: no collective kernel, no device-side waiting, no device->host copy.  Every rank must issue the same
+ * sequence of evaluations. */
+long gpcsd_plan_mailbox_bytes(void* plan, int world);
+int gpcsd_plan_set_mailbox(void* plan, void* h_shared, long bytes, int world, int rank);
 /* Kernel-level entry: one evaluation with CALLER-SUPPLIED eigen-factors instead of the eigensolvers:
  * device arrays QsT [nx][even(nx)], ls [nx], QtT [nt][even(nt)], lt [nt], rows = eigenvectors (the columns np.linalg.eigh
  * returns in comp_eig_D, utility_functions.py:58-59). */
