@@ -56,11 +56,30 @@ class GPCSDModelBase:
                              jitter=self.JITTER)
             if getattr(self, "_collective_order", None) is not None:
                 eng.shard.set_order(*self._collective_order)      # models evaluated from several host threads (parallel.py)
-            self._engine, self._engine_geom, self._engine_lfp = eng, geom_key, None
-        if self._engine_lfp is not self.lfp:
+            self._engine, self._engine_geom, self._engine_lfp, self._engine_fp = eng, geom_key, None, None
+        fp = self._lfp_fingerprint()
+        if self._engine_lfp is not self.lfp or self._engine_fp != fp:
             eng.set_lfp(self.lfp, local=getattr(self, "lfp_is_local", False))
-            self._engine_lfp = self.lfp
+            self._engine_lfp, self._engine_fp = self.lfp, fp
         return eng
+
+    def _lfp_fingerprint(self):
+        """Cheap content fingerprint of ``self.lfp`` (address, shape and 64 strided samples): the reference re-reads the array
+        on every call, so an in-place edit such as ``model.lfp -= model.lfp.mean(...)`` must trigger a new upload even though
+        the object is the same.  Edits that miss all the samples need ``invalidate()``."""
+        a = self.lfp
+        try:
+            flat = a.reshape(-1)
+            n = flat.shape[0]
+            step = max(1, n // 64)
+            return (a.__array_interface__['data'][0], a.shape, float(np.sum(flat[::step][:64])), float(flat[n - 1]) if n else 0.0)
+        except Exception:
+            return None
+
+    def invalidate(self):
+        """Public: the data (or geometry arrays) were modified in place -- re-upload / rebuild at the next evaluation."""
+        self._engine_lfp = None
+        self._engine_geom = None
 
     def _invalidate_lfp(self):
         """Force a fresh host->device upload at the next evaluation (called by update_lfp)."""

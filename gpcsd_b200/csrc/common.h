@@ -15,3 +15,14 @@ int gp_num_sms();
     cudaError_t _e = (expr);                                           \
     if (_e != cudaSuccess) return gp_fail_cuda(_e, #expr, __LINE__);   \
   } while (0)
+
+// Per-DEVICE one-shot guard for cudaFuncSetAttribute calls (function attributes are per device; a process may drive more
+// than one): flags is a zero-initialised static array of GP_MAX_DEVICES ints owned by the call site.
+#define GP_MAX_DEVICES 64
+static inline bool gp_first_use_on_device(int* flags) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= GP_MAX_DEVICES) return true;
+  if (flags[dev]) return false;
+  flags[dev] = 1;
+  return true;
+}

@@ -947,10 +947,9 @@ long gpcsd_tridiag_eig_ws_doubles(int n, long ldx, int nmat) { return 2L * nmat 
 
 static int dc_launch(int n, int nmat, const double* d, const double* e, double* Qa, double* Qb, long ldq, double* W, double* XT,
                      long ldx, double* Cmat, long ldc, int* info, cudaStream_t stream) {
-  static bool attr = false;
-  if (!attr) {
+  static int attr[GP_MAX_DEVICES];
+  if (gp_first_use_on_device(attr)) {
     GP_CUDA(cudaFuncSetAttribute(dc_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DcSmem)));
-    attr = true;
   }
   dc_cluster_kernel<<<DC_CLUSTER * nmat, DC_THREADS, sizeof(DcSmem), stream>>>(n, d, e, Qa, Qb, ldq, W, XT, ldx, Cmat, ldc, info);
   GP_CUDA(cudaGetLastError());
@@ -1002,11 +1001,13 @@ int gpcsd_eigh_dc(int n, int nmat, const double* M, long ldm, double* QT, long l
   }
   // one side stream + event pair per CALLER stream (created on first use, kept for the life of the process)
   static std::mutex side_mutex;
-  static std::unordered_map<cudaStream_t, EighSide> sides;
+  static std::unordered_map<unsigned long long, EighSide> sides;      // key: (device, caller stream)
   EighSide side;
   {
     std::lock_guard<std::mutex> lock(side_mutex);
-    EighSide& slot = sides[st];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    EighSide& slot = sides[((unsigned long long)(uintptr_t)st) ^ ((unsigned long long)(dev + 1) << 56)];
     if (!slot.stream) {
       GP_CUDA(cudaStreamCreateWithFlags(&slot.stream, cudaStreamNonBlocking));
       GP_CUDA(cudaEventCreateWithFlags(&slot.fork, cudaEventDisableTiming));

@@ -168,10 +168,9 @@ template <int BM, int BN, int WM, int WN, int STAGES, bool BT, int EPI, int MINB
 static int launch_gemm(GemmArgs& p, int batch, cudaStream_t st) {
   using L = SmemLayout<BM, BN, BT, STAGES>;
   auto kern = dmma_gemm_kernel<BM, BN, WM, WN, STAGES, BT, EPI, MINB>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static int attr_set[GP_MAX_DEVICES];
+  if (gp_first_use_on_device(attr_set)) {
     GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
-    attr_set = true;
   }
   p.m_tiles = (p.M + BM - 1) / BM;
   const long n_tiles = ((long)p.N + BN - 1) / BN;
@@ -365,8 +364,8 @@ static int syrk_plan(int M, int nseg, int seglen, int& bmn, int& tiles_1d, int& 
 static int wsyrk_small_launch(SyrkArgs& p, const SyrkArgs* pair, double* C0, double* C1, long ldc, cudaStream_t st) {
   const int mt = (p.M + 7) / 8, nct = syrk_small_ctas();
   const size_t bytes = (size_t)(NTHREADS / 32) * 1024 * sizeof(double);
-  static bool attr = false;
-  if (!attr) {
+  static int attr[GP_MAX_DEVICES];
+  if (gp_first_use_on_device(attr)) {
     GP_CUDA(cudaFuncSetAttribute(wsyrk_small_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     GP_CUDA(cudaFuncSetAttribute(wsyrk_small_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     GP_CUDA(cudaFuncSetAttribute(wsyrk_small_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -375,7 +374,6 @@ static int wsyrk_small_launch(SyrkArgs& p, const SyrkArgs* pair, double* C0, dou
     GP_CUDA(cudaFuncSetAttribute(wsyrk_small_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     GP_CUDA(cudaFuncSetAttribute(wsyrk_small_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     GP_CUDA(cudaFuncSetAttribute(wsyrk_small_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    attr = true;
   }
   if (pair) {
     switch (mt) {

@@ -22,13 +22,15 @@ int gp_fail_cuda(cudaError_t e, const char* what, int line) {
   return 2;
 }
 int gp_num_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  static int sms[GP_MAX_DEVICES];                  // per device (a process may drive more than one)
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= GP_MAX_DEVICES) return 148;
+  if (sms[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    sms[dev] = v;
   }
-  return sms;
+  return sms[dev];
 }
 
 namespace gpcsd {
@@ -289,6 +291,7 @@ static int dot_blocks(long n) {
 // (with the cuBLAS workspace inside it) must not be shared by work in flight on two streams.  Creating a handle
 // costs ~100 ms, so they are cached for the life of the process.
 struct SolverSlot {
+  int device;
   cudaStream_t stream;
   cusolverDnHandle_t handle;
 };
@@ -297,19 +300,19 @@ static int g_nslots = 0;
 static std::mutex g_slot_mutex;
 static int solver_handle(cusolverDnHandle_t* h, cudaStream_t st = nullptr) {
   std::lock_guard<std::mutex> lock(g_slot_mutex);
+  int dev = 0;
+  cudaGetDevice(&dev);
   for (int i = 0; i < g_nslots; ++i)
-    if (g_slots[i].stream == st) {
+    if (g_slots[i].stream == st && g_slots[i].device == dev) {
       *h = g_slots[i].handle;
       return 0;
     }
-  if (g_nslots == 64) {  // recycle the oldest slot
-    cusolverDnDestroy(g_slots[0].handle);
-    for (int i = 1; i < 64; ++i) g_slots[i - 1] = g_slots[i];
-    g_nslots = 63;
-  }
+  // a full table is an error rather than a reason to destroy a handle another thread may still be using
+  if (g_nslots == 64) return gp_fail("cuSOLVER handle table full (64 (device, stream) pairs)");
   cusolverDnHandle_t nh = nullptr;
   if (cusolverDnCreate(&nh) != CUSOLVER_STATUS_SUCCESS) return gp_fail("cusolverDnCreate failed");
   if (cusolverDnSetStream(nh, st) != CUSOLVER_STATUS_SUCCESS) return gp_fail("cusolverDnSetStream failed");
+  g_slots[g_nslots].device = dev;
   g_slots[g_nslots].stream = st;
   g_slots[g_nslots].handle = nh;
   ++g_nslots;

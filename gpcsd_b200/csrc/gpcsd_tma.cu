@@ -468,10 +468,9 @@ static int make_map3(CUtensorMap* m, const double* base, uint64_t d0, uint64_t d
 template <bool BT, int EPI, int NTW>
 static int launch_tma_gemm(const CUtensorMap& tA, const CUtensorMap& tB, TmaGemmArgs& p, cudaStream_t st) {
   auto kern = tma_gemm_kernel<BT, EPI, NTW>;
-  static bool attr = false;
-  if (!attr) {
+  static int attr[GP_MAX_DEVICES];
+  if (gp_first_use_on_device(attr)) {
     GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_SMEM_BYTES));
-    attr = true;
   }
   const long ntiles = (long)p.m_tiles * p.n_tiles * p.batch;
   const long grid = ntiles < gp_num_sms() ? ntiles : gp_num_sms();
@@ -555,10 +554,9 @@ int tma_wsyrk(int M, int nseg, int seglen, const double* X, long row_stride, lon
   p.w = w; p.M = M; p.nseg = nseg; p.seglen = seglen;
   p.kbps = kbps; p.total_kb = total_kb; p.nsplit = nsplit; p.tiles_1d = tiles_1d; p.ws = ws;
   p.seg_middle = seg_middle ? 1 : 0;
-  static bool attr = false;
-  if (!attr) {
+  static int attr[GP_MAX_DEVICES];
+  if (gp_first_use_on_device(attr)) {
     GP_CUDA(cudaFuncSetAttribute(tma_wsyrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_SMEM_BYTES));
-    attr = true;
   }
   const long ntiles = (long)tiles_1d * (tiles_1d + 1) / 2;
   tma_wsyrk_kernel<<<dim3((unsigned)ntiles, (unsigned)nsplit), T_THREADS, T_SMEM_BYTES, st>>>(tX, p);

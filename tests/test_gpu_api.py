@@ -158,6 +158,20 @@ def test_update_lfp_reuploads(cuda_lib, golden_dir):
     assert abs(float(m.loglik()) - ll1) < 1e-12 * abs(ll1)
 
 
+def test_in_place_edit_of_lfp_is_seen(cuda_lib, golden_dir):
+    """The reference re-reads self.lfp on every call; an in-place edit of the same array object must not leave a stale device
+    copy (content fingerprint in GPCSDModelBase._get_engine), and invalidate() forces a re-upload unconditionally."""
+    g = np.load(os.path.join(golden_dir, "gpcsd1d_lownoise.npz"))
+    m = _api_model_1d(g)
+    ll1 = float(m.loglik())
+    m.lfp *= 2.0                                       # same object, new contents
+    ll2 = float(m.loglik())
+    assert ll2 != ll1
+    m.lfp *= 0.5
+    m.invalidate()
+    assert abs(float(m.loglik()) - ll1) < 1e-12 * abs(ll1)
+
+
 def test_fit_concurrent_workers_match_sequential(cuda_lib):
     """fit(n_workers=2) -- restarts on two threads/streams/engines sharing the uploaded LFP -- must end at exactly the
     parameters of the sequential fit (same starts, deterministic kernels)."""
