@@ -101,6 +101,8 @@ def main():
                 print(json.dumps(rows[-1]), flush=True)
             eng.Y = None
             eng._ws = {k: v for k, v in eng._ws.items() if k[0] not in ("Z", "Bm")}
+            for pl in eng._plans.values():            # the native plan's workspace is sized by the trial count: release it
+                pl.ws, pl._bound = None, None
             torch.cuda.empty_cache()
         del eng
         torch.cuda.empty_cache()
