@@ -148,6 +148,116 @@ __global__ void __launch_bounds__(NTHREADS, MINB) dmma_gemm_kernel(GemmArgs p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// C_b = A_b (M x K) * B_b (K x N) for M <= 32 AND K <= 32 (Z = Qs^T Y of the 1-D model: 24 x 24 times 24 x (nt * trials),
+// 3 flop per byte -> HBM-bound).  No shared memory: the whole A operand lives in DMMA fragments for the life of the warp
+// (MT x KT doubles per lane); B fragments come straight from global memory with 16-byte loads and C leaves with 16-byte
+// stores.  One warp step covers 16 columns: MMA column g of tile 0 / 1 is memory column 2g / 2g+1 (any column permutation is
+// legal as long as loads and stores agree), so lane (g, q) loads B[4kk + q][n0 + 2g .. 2g+1] -- 8 lanes x 16 B = 128
+// contiguous bytes per row -- and ends up holding C[8it + g][n0 + 4q .. 4q+3], 32 contiguous bytes.
+// grid.x = CTAs striding over the 16-column steps, grid.y = batch.
+// ------------------------------------------------------------------------------------------------
+template <int MT, int KT>
+__global__ void __launch_bounds__(NTHREADS) smallmk_gemm_kernel(GemmArgs p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, q = lane & 3;
+  const int b = blockIdx.y;
+  const double* A = p.A + (long)b * p.sA;
+  const double* B = p.B + (long)b * p.sB;
+  double* C = p.C + (long)b * p.sC;
+  double a[MT][KT];
+#pragma unroll
+  for (int it = 0; it < MT; ++it)
+#pragma unroll
+    for (int kk = 0; kk < KT; ++kk) {
+      const int r = 8 * it + g, k = 4 * kk + q;
+      a[it][kk] = (r < p.M && k < p.K) ? __ldg(A + (long)r * p.lda + k) : 0.0;
+    }
+  const long nsteps = ((long)p.N + 15) / 16;
+  const long nwarps = (long)gridDim.x * (NTHREADS / 32), w0 = (long)blockIdx.x * (NTHREADS / 32) + warp;
+  constexpr int U = (MT * KT > 18) ? 2 : 4;       // 16-column steps in flight per warp (register budget: 255)
+  for (long s0 = w0 * U; s0 < nsteps; s0 += nwarps * U) {
+    double2 bv[U][KT];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long n = (s0 + u) * 16 + 2 * g;
+#pragma unroll
+      for (int kk = 0; kk < KT; ++kk) {
+        const int k = 4 * kk + q;
+        double2 t = make_double2(0.0, 0.0);
+        if (s0 + u < nsteps && k < p.K) {
+          if (n + 1 < p.N) t = __ldg(reinterpret_cast<const double2*>(B + (long)k * p.ldb + n));
+          else if (n < p.N) t.x = __ldg(B + (long)k * p.ldb + n);
+        }
+        bv[u][kk] = t;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (s0 + u >= nsteps) break;
+      double acc[MT][2][2];
+#pragma unroll
+      for (int it = 0; it < MT; ++it) acc[it][0][0] = acc[it][0][1] = acc[it][1][0] = acc[it][1][1] = 0.0;
+#pragma unroll
+      for (int kk = 0; kk < KT; ++kk)
+#pragma unroll
+        for (int it = 0; it < MT; ++it) {
+          dmma884(acc[it][0][0], acc[it][0][1], a[it][kk], bv[u][kk].x);     // memory columns n0 + 2g   -> MMA column g
+          dmma884(acc[it][1][0], acc[it][1][1], a[it][kk], bv[u][kk].y);     // memory columns n0 + 2g+1
+        }
+      // lane (g, q): tile 0 holds MMA columns 2q, 2q+1 = memory 4q, 4q+2; tile 1 holds memory 4q+1, 4q+3
+      const long n = (s0 + u) * 16 + 4 * q;
+#pragma unroll
+      for (int it = 0; it < MT; ++it) {
+        const int r = 8 * it + g;
+        if (r >= p.M) continue;
+        double* dst = C + (long)r * p.ldc + n;
+        if (n + 3 < p.N) {
+          *reinterpret_cast<double2*>(dst) = make_double2(acc[it][0][0], acc[it][1][0]);
+          *reinterpret_cast<double2*>(dst + 2) = make_double2(acc[it][0][1], acc[it][1][1]);
+        } else {
+          if (n < p.N) dst[0] = acc[it][0][0];
+          if (n + 1 < p.N) dst[1] = acc[it][1][0];
+          if (n + 2 < p.N) dst[2] = acc[it][0][1];
+        }
+      }
+    }
+  }
+}
+
+template <int MT>
+static int launch_smallmk_kt(GemmArgs& p, int batch, cudaStream_t st) {
+  const long nsteps = ((long)p.N + 15) / 16;
+  long ctas = (nsteps + 4 * (NTHREADS / 32) - 1) / (4 * (NTHREADS / 32));
+  const long cap = 4L * gp_num_sms();
+  if (ctas > cap) ctas = cap;
+  if (ctas < 1) ctas = 1;
+  dim3 grid((unsigned)ctas, (unsigned)batch);
+  const int kt = (p.K + 3) / 4;
+  switch (kt) {
+    case 1: smallmk_gemm_kernel<MT, 1><<<grid, NTHREADS, 0, st>>>(p); break;
+    case 2: smallmk_gemm_kernel<MT, 2><<<grid, NTHREADS, 0, st>>>(p); break;
+    case 3: smallmk_gemm_kernel<MT, 3><<<grid, NTHREADS, 0, st>>>(p); break;
+    case 4: smallmk_gemm_kernel<MT, 4><<<grid, NTHREADS, 0, st>>>(p); break;
+    case 5: smallmk_gemm_kernel<MT, 5><<<grid, NTHREADS, 0, st>>>(p); break;
+    case 6: smallmk_gemm_kernel<MT, 6><<<grid, NTHREADS, 0, st>>>(p); break;
+    case 7: smallmk_gemm_kernel<MT, 7><<<grid, NTHREADS, 0, st>>>(p); break;
+    default: smallmk_gemm_kernel<MT, 8><<<grid, NTHREADS, 0, st>>>(p); break;
+  }
+  GP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int launch_smallmk(GemmArgs& p, int batch, cudaStream_t st) {
+  if (batch > 65535) return gp_fail("gemm batch too large");
+  switch ((p.M + 7) / 8) {
+    case 1: return launch_smallmk_kt<1>(p, batch, st);
+    case 2: return launch_smallmk_kt<2>(p, batch, st);
+    case 3: return launch_smallmk_kt<3>(p, batch, st);
+    default: return launch_smallmk_kt<4>(p, batch, st);
+  }
+}
+
 // fixed-order reduction of [n][2] partials -> out[2]
 __global__ void reduce_pairs_kernel(const double* __restrict__ part, long n, double* __restrict__ out) {
   __shared__ double red[16];
@@ -192,6 +302,7 @@ template <int EPI>
 static int dispatch_gemm(GemmArgs& p, int transB, int batch, cudaStream_t st) {
   if (p.M <= 0 || p.N <= 0 || batch <= 0) return 0;
   if (int e = check_gemm_alignment(p)) return e;
+  if (EPI == EPI_STORE && !transB && p.M <= 32 && p.K <= 32 && p.K > 0) return launch_smallmk(p, batch, st);
   if (p.M <= 32) {
     if (transB) return launch_gemm<32, 128, 32, 16, 3, true, EPI, 2>(p, batch, st);
     return launch_gemm<32, 128, 32, 16, 3, false, EPI, 2>(p, batch, st);

@@ -27,7 +27,8 @@ def _stream():
 
 
 @pytest.mark.parametrize("M,N,K,batch", [(128, 128, 16, 1), (500, 2000, 500, 3), (24, 1003, 24, 1), (7, 50, 5, 2),
-                                          (33, 65, 17, 2), (384, 777, 384, 1), (130, 258, 131, 1), (1, 9, 300, 1)])
+                                          (33, 65, 17, 2), (384, 777, 384, 1), (130, 258, 131, 1), (1, 9, 300, 1),
+                                          (24, 100008, 24, 1), (32, 4101, 32, 2), (9, 17, 31, 3), (24, 24, 24, 1), (30, 8, 3, 1)])
 @pytest.mark.parametrize("transB", [0, 1])
 def test_dgemm(cuda_lib, M, N, K, batch, transB):
     from gpcsd_b200 import _lib as L
