@@ -31,8 +31,13 @@ SIGNATURES = {
     "gpcsd_project_quad_ws_doubles": (c_long, [c_int, c_int, c_int]),
     "gpcsd_project_quad": (c_int, [c_int, c_int, c_int, _P, c_long, _P, c_long, _P, c_long, _P, _P, _P, _P]),
     "gpcsd_project_quad_strided": (c_int, [c_int, c_int, c_int, _P, c_long, _P, c_long, c_long, _P, c_long, _P, _P, _P, _P]),
+    "gpcsd_project_quad_batched_ws_doubles": (c_long, [c_int, c_int, c_int, c_int]),
+    "gpcsd_project_quad_batched": (c_int, [c_int, c_int, c_int, c_int, _P, c_long, c_long, _P, c_long, c_long, _P, c_long, _P, _P, _P,
+                                           c_long, _P]),
     "gpcsd_wsyrk_ws_doubles": (c_long, [c_int, c_int, c_int]),
     "gpcsd_wsyrk": (c_int, [c_int, c_int, c_int, _P, c_long, c_long, _P, _P, c_long, _P, _P]),
+    "gpcsd_wsyrk_batched_ws_doubles": (c_long, [c_int, c_int, c_int, c_int, c_int]),
+    "gpcsd_wsyrk_batched": (c_int, [c_int, c_int, c_int, c_int, _P, c_long, c_long, c_long, _P, c_long, _P, _P, c_long, c_long, _P, _P]),
     "gpcsd_wsyrk_pair": (c_int, [c_int, c_int, c_int, _P, c_long, c_long, _P, _P, _P, c_long, _P, _P]),
     "gpcsd_eigh_ws_doubles": (c_long, [c_int, c_long]),
     "gpcsd_eigh": (c_int, [c_int, _P, c_long, _P, c_long, _P, _P, c_long, _P, _P]),

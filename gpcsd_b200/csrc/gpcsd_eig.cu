@@ -903,6 +903,152 @@ __global__ void identity_rows_kernel(int n, long ld, long total, double* __restr
   R[idx] = (c == r) ? 1.0 : 0.0;
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// Orders 1..32: two-sided parallel Jacobi, ONE CTA per matrix (matrix and eigenvector matrix in shared memory).
+// The cluster solver above spends ~155 us on a 24-order matrix (5 merge levels and 24 exchange round trips of fixed latency)
+// and occupies 8 SMs per matrix, so the 64 + 128 factors of a 64-restart batch at 24 x 50 run in ~10 waves; here every matrix
+// gets its own CTA and all of them run at once.  Round-robin ordering (circle method): each round applies ceil(n/2) rotations on
+// disjoint index pairs -- rows first, then columns (and the columns of V) -- with thread (k, j) handling pair k, column / row
+// j.  A rotation is skipped when |a_pq| <= max(8 eps sqrt(|a_pp a_qq|), eps/8 max|a_ij|): the absolute floor is the accuracy
+// LAPACK and the cluster solver deliver (eps |K|); chasing the purely relative criterion inside the numerically degenerate
+// jitter-level cluster of a GP factor costs 22 sweeps instead of ~8 for digits nothing downstream can use.  A sweep without
+// rotations ends the iteration.
+// Eigenvalues ascending, eigenvectors as ROWS of QT like the other solvers; info = 1 (NaN outputs) on non-finite input.
+// ------------------------------------------------------------------------------------------------------------------------
+constexpr int JAC_MAXN = 32;
+
+__global__ void __launch_bounds__(JAC_MAXN* JAC_MAXN / 2) jacobi_small_kernel(int n, const double* __restrict__ M, long ldm,
+                                                                              double* __restrict__ QT, long ldq,
+                                                                              double* __restrict__ W, int* __restrict__ info) {
+  __shared__ double A[JAC_MAXN][JAC_MAXN + 1], V[JAC_MAXN][JAC_MAXN + 1];
+  __shared__ double cs[JAC_MAXN / 2], sn[JAC_MAXN / 2];
+  __shared__ int pp[JAC_MAXN / 2], qq[JAC_MAXN / 2];
+  __shared__ int rotated, bad;
+  __shared__ double fro;
+  const int mat = blockIdx.x;
+  M += (long)mat * n * ldm;
+  QT += (long)mat * n * ldq;
+  W += (long)mat * n;
+  const int m = (n + 1) / 2, np = 2 * m;            // pairs per round, padded order (index n is a dummy when n is odd)
+  const int tid = threadIdx.x, k = tid / np, j = tid - k * np;   // launched with m * np threads
+  if (tid == 0) {
+    rotated = 0;
+    bad = 0;
+    fro = 0.0;
+  }
+  __syncthreads();
+  for (int e = tid; e < np * np; e += blockDim.x) {
+    const int r = e / np, c = e - r * np;
+    double v = 0.0;
+    if (r < n && c < n) {
+      v = 0.5 * (M[(long)r * ldm + c] + M[(long)c * ldm + r]);
+      if (!isfinite(v)) bad = 1;
+    }
+    A[r][c] = v;
+    V[r][c] = (r == c) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  if (tid == 0) {                                    // scale of the matrix (fixed order: results are bit-reproducible)
+    double mx = 0.0;
+    for (int i = 0; i < n; ++i)
+      for (int c = 0; c <= i; ++c) mx = fmax(mx, fabs(A[i][c]));
+    fro = mx;
+  }
+  __syncthreads();
+  if (bad) {
+    for (int e = tid; e < n * n; e += blockDim.x) QT[(long)(e / n) * ldq + e % n] = nan("");
+    if (tid < n) W[tid] = nan("");
+    if (tid == 0 && info) info[mat] = 1;
+    return;
+  }
+  const double tiny = 2.7755575615628914e-17 * fro;     // eps/8 max|a_ij|: LAPACK-grade absolute accuracy, see the header comment
+  // Round-robin pairing in closed form (circle method on np players, np even): in round r player np-1 meets player r, and for
+  // k = 1..m-1 player (r + k) mod (np-1) meets player (r - k) mod (np-1) -- m disjoint pairs, every pair once per sweep.
+  // Three barriers per round: rotation parameters | row update | column update.
+  const int nm1 = np - 1;
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    for (int round = 0; round < nm1; ++round) {
+      if (tid < m) {
+        int a, b;
+        if (tid == 0) {
+          a = round;
+          b = nm1;
+        } else {
+          a = round + tid;
+          if (a >= nm1) a -= nm1;
+          b = round - tid;
+          if (b < 0) b += nm1;
+        }
+        const int p = a < b ? a : b, q = a < b ? b : a;
+        pp[tid] = p;
+        qq[tid] = q;
+        double c = 1.0, sv = 0.0;
+        if (q < n) {
+          const double apq = 0.5 * (A[p][q] + A[q][p]), app = A[p][p], aqq = A[q][q];
+          const double thr = fmax(1.7763568394002505e-15 * sqrt(fabs(app * aqq)), tiny);     // 8 eps sqrt(|a_pp a_qq|)
+          if (fabs(apq) > thr) {
+            // symmetric Schur rotation: tau = (aqq - app) / (2 apq), t = sign(tau) / (|tau| + sqrt(1 + tau^2)),
+            // c = 1 / sqrt(1 + t^2), s = t c; reciprocal / rsqrt from single-precision seeds + Newton when in range
+            const double den = 2.0 * apq, ad = fabs(den);
+            const double rden = (ad > 1e-30 && ad < 1e30) ? copysign(refine_recip(ad, (double)__frcp_rn((float)ad)), den) : 1.0 / den;
+            const double tau = (aqq - app) * rden, at = fabs(tau);
+            const double u = 1.0 + tau * tau;
+            const double root = (u < 1e30) ? u * fast_rsqrt(u) : sqrt(u);
+            const double dd = at + root;                                   // >= 1
+            const double t = copysign((dd < 1e30) ? refine_recip(dd, (double)__frcp_rn((float)dd)) : 1.0 / dd, tau);
+            c = fast_rsqrt(1.0 + t * t);
+            sv = t * c;
+            rotated = 1;
+          }
+        }
+        cs[tid] = c;
+        sn[tid] = sv;
+      }
+      __syncthreads();
+      const int p = pp[k], q = qq[k];
+      const double c = cs[k], sv = sn[k];
+      const bool act = (sv != 0.0);
+      if (act) {               // rows p, q:  a_pj <- c a_pj - s a_qj,  a_qj <- s a_pj + c a_qj
+        const double x = A[p][j], y = A[q][j];
+        A[p][j] = c * x - sv * y;
+        A[q][j] = sv * x + c * y;
+      }
+      __syncthreads();
+      if (act) {               // columns p, q of A (the annihilated pair is set to exactly zero) and of V
+        const double x = A[j][p], y = A[j][q];
+        A[j][p] = (j == q) ? 0.0 : c * x - sv * y;
+        A[j][q] = (j == p) ? 0.0 : sv * x + c * y;
+        const double u = V[j][p], w = V[j][q];
+        V[j][p] = c * u - sv * w;
+        V[j][q] = sv * u + c * w;
+      }
+      __syncthreads();
+    }
+    const int any = rotated;
+    __syncthreads();
+    if (tid == 0) rotated = 0;
+    __syncthreads();
+    if (!any) break;
+  }
+  // ascending order by counting ranks (ties by index), eigenvectors (columns of V) as rows of QT
+  if (tid < n) {
+    const double l = A[tid][tid];
+    int rank = 0;
+    for (int i = 0; i < n; ++i) {
+      const double li = A[i][i];
+      rank += (li < l || (li == l && i < tid)) ? 1 : 0;
+    }
+    W[rank] = l;
+    V[tid][JAC_MAXN] = (double)rank;                  // the padding column of V carries the destination row
+  }
+  __syncthreads();
+  for (int e = tid; e < n * n; e += blockDim.x) {
+    const int i = e / n, c = e - i * n;               // eigenvector i, component c
+    QT[(long)((int)V[i][JAC_MAXN]) * ldq + c] = V[c][i];
+  }
+  if (tid == 0 && info) info[mat] = 0;
+}
+
 }  // namespace gpcsd
 
 using namespace gpcsd;
@@ -981,9 +1127,19 @@ struct EighSide {
 
 int gpcsd_eigh_dc(int n, int nmat, const double* M, long ldm, double* QT, long ldq, double* W, double* ws, long ws_doubles,
                   int* info, void* stream) {
-  if (n < 3 || n > DC_MAXN) return gp_fail("gpcsd_eigh_dc: order must be in 3..256");
-  if (ws_doubles < gpcsd_eigh_dc_ws_doubles(n, ldq, nmat)) return gp_fail("gpcsd_eigh_dc: workspace too small");
+  if (n < 1 || n > DC_MAXN) return gp_fail("gpcsd_eigh_dc: order must be in 1..256");
   cudaStream_t st = (cudaStream_t)stream;
+  // Orders <= 32: the Jacobi kernel (one CTA per matrix, ~240 us whatever the batch) when the cluster solver (8 SMs per
+  // matrix, ~155 us per wave of 18 matrices) would need more than one wave -- i.e. for restart batches; single models keep
+  // the lower latency of the cluster solver.  Orders 1 and 2 always go to Jacobi.
+  if (n <= JAC_MAXN && (n < 3 || (long)nmat * TRD_CLUSTER > gp_num_sms())) {
+    if (nmat <= 0) return 0;
+    const int m = (n + 1) / 2;
+    jacobi_small_kernel<<<nmat, m * 2 * m, 0, st>>>(n, M, ldm, QT, ldq, W, info);
+    GP_CUDA(cudaGetLastError());
+    return 0;
+  }
+  if (ws_doubles < gpcsd_eigh_dc_ws_doubles(n, ldq, nmat)) return gp_fail("gpcsd_eigh_dc: workspace too small");
   const long slab = (long)nmat * n * ldq, mstride = (long)n * ldq;
   double* V = ws;                     // reflectors
   double* Qa = V + slab;              // D&C ping-pong

@@ -9,10 +9,11 @@ namespace gpcsd {
 // gpcsd_tma.cu: persistent TMA + mbarrier warp-specialised kernels (M > 32)
 int tma_gemm(int transB, int M, int N, int K, const double* A, long lda, long sA, const double* B, long ldb, long sB,
              double* C, long ldc, long sC, int batch, const double* rD, long ldrd, double* partials, int epi_quad,
-             cudaStream_t st);
+             cudaStream_t st, int a_div = 1, int grp = 0);
 int tma_gemm_ctas(int M, int N, int batch);
 int tma_wsyrk(int M, int nseg, int seglen, const double* X, long row_stride, long seg_stride, const double* w, double* C,
-              long ldc, double* ws, int nsplit, int tiles_1d, int kbps, long total_kb, cudaStream_t st);
+              long ldc, double* ws, int nsplit, int tiles_1d, int kbps, long total_kb, cudaStream_t st, int R = 1, long x_stride = 0,
+              long w_stride = 0, long c_stride = 0);
 
 struct GemmArgs {
   const double* A;
@@ -22,6 +23,8 @@ struct GemmArgs {
   long sA, sB, sC;  // batch strides
   int M, N, K;
   int m_tiles;
+  int a_div = 1;     // A operand of batch b: A + (b / a_div) * sA   (restart-batched projection: a_div = nx)
+  int grp = 0;       // quad epilogue: batches per reduction group (0: one group)
   // quad epilogue
   const double* rD;  // rD[batch*ldrd + m]
   long ldrd;
@@ -56,7 +59,7 @@ __global__ void __launch_bounds__(NTHREADS, MINB) dmma_gemm_kernel(GemmArgs p) {
   const int mt = blockIdx.x % p.m_tiles, nt_ = blockIdx.x / p.m_tiles;
   const int m0 = mt * BM, n0 = nt_ * BN;
   const int b = blockIdx.y;
-  const double* A = p.A + (long)b * p.sA + (long)m0 * p.lda;
+  const double* A = p.A + (long)(b / p.a_div) * p.sA + (long)m0 * p.lda;
   const double* B = p.B + (long)b * p.sB + (BT ? (long)n0 * p.ldb : (long)n0);
   const int rowsA = p.M - m0;
   const long colsB = (long)p.N - n0;
@@ -274,6 +277,23 @@ __global__ void reduce_pairs_kernel(const double* __restrict__ part, long n, dou
   }
 }
 
+// grouped variant: out[g * out_stride + {0,1}] = sum of partial pairs [g * n, (g+1) * n)   (one CTA per group / restart)
+__global__ void reduce_pairs_grouped_kernel(const double* __restrict__ part, long n, double* __restrict__ out, long out_stride) {
+  __shared__ double red[16];
+  const double* pg = part + 2 * n * blockIdx.x;
+  double a = 0.0, b = 0.0;
+  for (long i = threadIdx.x; i < n; i += blockDim.x) {
+    a += pg[2 * i];
+    b += pg[2 * i + 1];
+  }
+  const double s0 = block_sum(a, red);
+  const double s1 = block_sum(b, red + 8);
+  if (threadIdx.x == 0) {
+    out[(long)blockIdx.x * out_stride] = s0;
+    out[(long)blockIdx.x * out_stride + 1] = s1;
+  }
+}
+
 template <int BM, int BN, int WM, int WN, int STAGES, bool BT, int EPI, int MINB>
 static int launch_gemm(GemmArgs& p, int batch, cudaStream_t st) {
   using L = SmemLayout<BM, BN, BT, STAGES>;
@@ -309,7 +329,7 @@ static int dispatch_gemm(GemmArgs& p, int transB, int batch, cudaStream_t st) {
   }
   if (batch > 65535) return gp_fail("gemm batch too large");
   return tma_gemm(transB, p.M, p.N, p.K, p.A, p.lda, p.sA, p.B, p.ldb, p.sB, p.C, p.ldc, p.sC, batch, p.rD, p.ldrd,
-                  p.partials, EPI == EPI_QUAD, st);
+                  p.partials, EPI == EPI_QUAD, st, p.a_div, p.grp);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -325,6 +345,7 @@ struct SyrkArgs {
   int nsplit;
   int tiles_1d;    // tiles per side
   double* ws;      // [nsplit][ntiles][BM*BN]
+  long sX = 0, sW = 0, sWs = 0;   // restart strides of X, w and ws (small-M kernel: blockIdx.y = restart)
 };
 
 // ---- M <= 32: register-only variant ---------------------------------------------------------------
@@ -339,6 +360,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) wsyrk_small_kernel(SyrkArgs p) {
   extern __shared__ __align__(16) double red[];  // [8 warps][32*32]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, q = lane & 3;
+  p.X += (long)blockIdx.y * p.sX;
+  if (p.w) p.w += (long)blockIdx.y * p.sW;
+  p.ws += (long)blockIdx.y * p.sWs;
   const long cps = (p.seglen + 7) / 8;
   const long total = (long)p.nseg * cps;
   const long nwarps = (long)gridDim.x * (NTHREADS / 32), wg = (long)blockIdx.x * (NTHREADS / 32) + warp;
@@ -438,7 +462,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) wsyrk_small_kernel(SyrkArgs p) {
 // One WARP per output entry (128 CTAs instead of 4): lane l sums partials l, l + 32, ... and a shuffle tree closes the sum --
 // a fixed order, so the result is deterministic.  grid.y selects the weighted / unweighted set of the PAIR variant.
 __global__ void wsyrk_small_reduce_kernel(const double* __restrict__ ws, int nparts, int M, double* __restrict__ C0,
-                                          double* __restrict__ C1, long ldc) {
+                                          double* __restrict__ C1, long ldc, long ws_stride, long c_stride) {
+  ws += (long)blockIdx.z * ws_stride;
+  C0 += (long)blockIdx.z * c_stride;
+  if (C1) C1 += (long)blockIdx.z * c_stride;
   const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (e >= 1024) return;
   const int r = e >> 5, cc = e & 31;
@@ -472,8 +499,16 @@ static int syrk_plan(int M, int nseg, int seglen, int& bmn, int& tiles_1d, int& 
 }
 
 // launch the small-M SYRK (+ its reduction); pair != nullptr selects the one-pass weighted + unweighted variant
-static int wsyrk_small_launch(SyrkArgs& p, const SyrkArgs* pair, double* C0, double* C1, long ldc, cudaStream_t st) {
-  const int mt = (p.M + 7) / 8, nct = syrk_small_ctas();
+static int syrk_small_ctas_batched(int R) {
+  if (R <= 1) return syrk_small_ctas();
+  const int c = syrk_small_ctas() / R;
+  return c < 4 ? 4 : c;
+}
+
+static int wsyrk_small_launch(SyrkArgs& p, const SyrkArgs* pair, double* C0, double* C1, long ldc, cudaStream_t st, int R = 1,
+                              long c_stride = 0) {
+  const int mt = (p.M + 7) / 8, nct = syrk_small_ctas_batched(R);
+  p.sWs = (long)(pair ? 2 : 1) * nct * 1024;
   const size_t bytes = (size_t)(NTHREADS / 32) * 1024 * sizeof(double);
   static int attr[GP_MAX_DEVICES];
   if (gp_first_use_on_device(attr)) {
@@ -488,21 +523,21 @@ static int wsyrk_small_launch(SyrkArgs& p, const SyrkArgs* pair, double* C0, dou
   }
   if (pair) {
     switch (mt) {
-      case 1: wsyrk_small_kernel<1, true><<<nct, NTHREADS, bytes, st>>>(p); break;
-      case 2: wsyrk_small_kernel<2, true><<<nct, NTHREADS, bytes, st>>>(p); break;
-      case 3: wsyrk_small_kernel<3, true><<<nct, NTHREADS, bytes, st>>>(p); break;
-      default: wsyrk_small_kernel<4, true><<<nct, NTHREADS, bytes, st>>>(p); break;
+      case 1: wsyrk_small_kernel<1, true><<<dim3(nct, R), NTHREADS, bytes, st>>>(p); break;
+      case 2: wsyrk_small_kernel<2, true><<<dim3(nct, R), NTHREADS, bytes, st>>>(p); break;
+      case 3: wsyrk_small_kernel<3, true><<<dim3(nct, R), NTHREADS, bytes, st>>>(p); break;
+      default: wsyrk_small_kernel<4, true><<<dim3(nct, R), NTHREADS, bytes, st>>>(p); break;
     }
   } else {
     switch (mt) {
-      case 1: wsyrk_small_kernel<1, false><<<nct, NTHREADS, bytes, st>>>(p); break;
-      case 2: wsyrk_small_kernel<2, false><<<nct, NTHREADS, bytes, st>>>(p); break;
-      case 3: wsyrk_small_kernel<3, false><<<nct, NTHREADS, bytes, st>>>(p); break;
-      default: wsyrk_small_kernel<4, false><<<nct, NTHREADS, bytes, st>>>(p); break;
+      case 1: wsyrk_small_kernel<1, false><<<dim3(nct, R), NTHREADS, bytes, st>>>(p); break;
+      case 2: wsyrk_small_kernel<2, false><<<dim3(nct, R), NTHREADS, bytes, st>>>(p); break;
+      case 3: wsyrk_small_kernel<3, false><<<dim3(nct, R), NTHREADS, bytes, st>>>(p); break;
+      default: wsyrk_small_kernel<4, false><<<dim3(nct, R), NTHREADS, bytes, st>>>(p); break;
     }
   }
   GP_CUDA(cudaGetLastError());
-  wsyrk_small_reduce_kernel<<<dim3(1024 * 32 / 256, pair ? 2 : 1), 256, 0, st>>>(p.ws, nct, p.M, C0, C1, ldc);
+  wsyrk_small_reduce_kernel<<<dim3(1024 * 32 / 256, pair ? 2 : 1, R), 256, 0, st>>>(p.ws, nct, p.M, C0, C1, ldc, p.sWs, c_stride);
   GP_CUDA(cudaGetLastError());
   return 0;
 }
@@ -561,6 +596,34 @@ int gpcsd_project_quad_strided(int nx, int m, int ntrials, const double* AT, lon
   return 0;
 }
 
+/* Restart-batched form of gpcsd_project_quad_strided: R restarts x nx spatial eigen-indices in ONE launch.  Restart r uses the
+ * m x m block AT + r*strideA and the parent arrays Z / Bout / rD of restart r, which must follow each other contiguously
+ * (Z_r = Z + r*nx*bstride, rD_r = rD + r*nx*ldrd); out2[r*out_stride + {0,1}] = (quad, bsq) of restart r.
+ * partials: gpcsd_project_quad_batched_ws_doubles(R, nx, m, ntrials) doubles. */
+long gpcsd_project_quad_batched_ws_doubles(int R, int nx, int m, int ntrials) {
+  if (m > 32) return 2L * R * tma_gemm_ctas(m, ntrials, nx * R) + 2;
+  return 2L * R * nx * (((long)ntrials + 127) / 128) + 2;
+}
+
+int gpcsd_project_quad_batched(int R, int nx, int m, int ntrials, const double* AT, long lda, long strideA, const double* Z, long ldn,
+                               long bstride, const double* rD, long ldrd, double* Bout, double* partials, double* out2,
+                               long out_stride, void* stream) {
+  if (R <= 0 || nx <= 0) return 0;
+  GemmArgs p{};
+  p.A = AT; p.B = Z; p.C = Bout;
+  p.lda = lda; p.ldb = ldn; p.ldc = ldn;
+  p.sA = strideA; p.sB = bstride; p.sC = bstride;
+  p.M = m; p.N = ntrials; p.K = m;
+  p.a_div = nx; p.grp = nx;
+  p.rD = rD; p.ldrd = ldrd; p.partials = partials;
+  if ((long)R * nx > 65535) return gp_fail("project_quad_batched: R * nx too large");
+  if (int e = dispatch_gemm<EPI_QUAD>(p, 0, R * nx, (cudaStream_t)stream)) return e;
+  const long per = (m > 32) ? tma_gemm_ctas(m, ntrials, nx * R) : (long)nx * (((long)ntrials + 127) / 128);
+  reduce_pairs_grouped_kernel<<<R, 256, 0, (cudaStream_t)stream>>>(partials, per, out2, out_stride);
+  GP_CUDA(cudaGetLastError());
+  return 0;
+}
+
 long gpcsd_wsyrk_ws_doubles(int M, int nseg, int seglen) {
   int bmn, t1, kbps, nsplit;
   long total;
@@ -584,6 +647,48 @@ int gpcsd_wsyrk(int M, int nseg, int seglen, const double* X, long row_stride, l
   dim3 grid((unsigned)ntiles, (unsigned)p.nsplit);
   if (bmn == 32) return wsyrk_small_launch(p, nullptr, C, nullptr, ldc, st);
   return tma_wsyrk(M, nseg, seglen, X, row_stride, seg_stride, w, C, ldc, ws, p.nsplit, p.tiles_1d, p.kbps, p.total_kb, st);
+}
+
+/* Restart-batched SYRK: for r < R,  Cw_r = sum_seg w_r[seg] X_r,seg X_r,seg^T  (and Cp_r, the unweighted product, when Cp != NULL)
+ * with X_r = X + r*strideX, w_r = w + r*strideW, C_r = C + r*strideC -- all restarts of a multi-start batch in one launch
+ * (blockIdx.z / the tensor map's 4th dimension).  ws: gpcsd_wsyrk_batched_ws_doubles(R, M, nseg, seglen, Cp != NULL). */
+static void syrk_plan_batched(int R, int M, int nseg, int seglen, int& bmn, int& t1, int& kbps, long& total, int& nsplit) {
+  syrk_plan(M, nseg, seglen, bmn, t1, kbps, total, nsplit);
+  if (R > 1) {
+    nsplit = nsplit / R;
+    if (nsplit < 1) nsplit = 1;
+  }
+}
+
+long gpcsd_wsyrk_batched_ws_doubles(int R, int M, int nseg, int seglen, int pair) {
+  int bmn, t1, kbps, nsplit;
+  long total;
+  syrk_plan_batched(R, M, nseg, seglen, bmn, t1, kbps, total, nsplit);
+  if (bmn == 32) return (long)R * (pair ? 2 : 1) * syrk_small_ctas_batched(R) * 1024;
+  return (long)R * nsplit * ((long)t1 * (t1 + 1) / 2) * bmn * bmn;      // (the pair runs two passes through the same scratch)
+}
+
+int gpcsd_wsyrk_batched(int R, int M, int nseg, int seglen, const double* X, long row_stride, long seg_stride, long strideX,
+                        const double* w, long strideW, double* Cw, double* Cp, long ldc, long strideC, double* ws, void* stream) {
+  if (M <= 0 || R <= 0) return 0;
+  if ((row_stride | seg_stride | strideX) & 1L) return gp_fail("wsyrk: strides must be even");
+  if (((uintptr_t)X | (uintptr_t)ws) & 15) return gp_fail("wsyrk: pointers must be 16-byte aligned");
+  if (R > 65535) return gp_fail("wsyrk_batched: too many restarts");
+  cudaStream_t st = (cudaStream_t)stream;
+  SyrkArgs p{};
+  int bmn;
+  syrk_plan_batched(R, M, nseg, seglen, bmn, p.tiles_1d, p.kbps, p.total_kb, p.nsplit);
+  p.X = X; p.row_stride = row_stride; p.seg_stride = seg_stride; p.w = w;
+  p.M = M; p.nseg = nseg; p.seglen = seglen; p.ws = ws;
+  p.sX = strideX; p.sW = strideW;
+  if (bmn == 32) return wsyrk_small_launch(p, Cp ? &p : nullptr, Cw, Cp, ldc, st, R, strideC);
+  if (int e = tma_wsyrk(M, nseg, seglen, X, row_stride, seg_stride, w, Cw, ldc, ws, p.nsplit, p.tiles_1d, p.kbps, p.total_kb, st, R,
+                        strideX, strideW, strideC))
+    return e;
+  if (Cp)
+    return tma_wsyrk(M, nseg, seglen, X, row_stride, seg_stride, nullptr, Cp, ldc, ws, p.nsplit, p.tiles_1d, p.kbps, p.total_kb, st, R,
+                     strideX, 0, strideC);
+  return 0;
 }
 
 /* Cw = sum_seg w[seg] X_seg X_seg^T and Cp = sum_seg X_seg X_seg^T in ONE pass over X (M <= 32: the Ms / Ns pair of the

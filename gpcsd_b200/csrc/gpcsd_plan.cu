@@ -644,13 +644,13 @@ static size_t layout(Plan* p, char* base, long ldn, int N) {
   p->Yf = (p->s_split || p->t_fold) ? b.take<double>(slab) : nullptr;
   const int Nn = N > 0 ? N : 1;
   long pq = 0;
-  for (int o : {d.nt, p->tm, p->tms}) { long w = gpcsd_project_quad_ws_doubles(d.nx, o, Nn); if (w > pq) pq = w; }
-  p->pq_ws_doubles = pq; p->pq_ws = b.take<double>(R * pq);
+  for (int o : {d.nt, p->tm, p->tms}) { long w = gpcsd_project_quad_batched_ws_doubles((int)R, d.nx, o, Nn); if (w > pq) pq = w; }
+  p->pq_ws_doubles = pq; p->pq_ws = b.take<double>(pq);
   long st = 2, ss = 2;
-  for (int o : {d.nt, p->tm, p->tms}) { long w = gpcsd_wsyrk_ws_doubles(o, d.nx, Nn); if (w > st) st = w; }
-  for (int o : {d.nx, p->sm > 0 ? p->sm : 1}) { long w = 2 * gpcsd_wsyrk_ws_doubles(o, d.nt, Nn); if (w > ss) ss = w; }
+  for (int o : {d.nt, p->tm, p->tms}) { long w = gpcsd_wsyrk_batched_ws_doubles((int)R, o, d.nx, Nn, 0); if (w > st) st = w; }
+  for (int o : {d.nx, p->sm > 0 ? p->sm : 1}) { long w = gpcsd_wsyrk_batched_ws_doubles((int)R, o, d.nt, Nn, 1); if (w > ss) ss = w; }
   p->syrk_t_doubles = st; p->syrk_s_doubles = ss;
-  p->syrk_ws_t = b.take<double>(R * st); p->syrk_ws_s = b.take<double>(R * ss);
+  p->syrk_ws_t = b.take<double>(st); p->syrk_ws_s = b.take<double>(ss);
   p->dot_ws_doubles = 4L * gp_num_sms() + 8; p->dot_ws = b.take<double>(R * p->dot_ws_doubles);
   p->ktg_ws_doubles = 16L * (4L * gp_num_sms() + 8); p->ktg_ws = b.take<double>(R * p->ktg_ws_doubles);
   return (b.off + 255) & ~size_t(255);
@@ -923,27 +923,20 @@ int enqueue_body(Plan* p, int R, int want_grad, const Factors* fac, cudaStream_t
   PL_LAUNCH(1);
 
   // ---------------- projection A_i = Qt^T Z_i with the fused /D + quadratic form (hot loop gpcsd1d.py:124-126)
-  const double* Zuse = p->Z;
   if (N > 0) {
-    for (int r = 0; r < R; ++r) {
-      double* res = p->res + (long)r * pl::RESW;
-      double* part = p->pq_ws + (long)r * p->pq_ws_doubles;
-      const double* Zr = Zuse + r * slab;
-      double* Br = p->Bm + r * slab;
-      const double* rDr = p->rD + (long)r * nx * ldt;
-      if (use_tfold) {
-        const int m = p->tm, ms = p->tms;
-        const long lds = p->tlds, sS_ = (long)ms * lds;
-        const double* UsT = p->uT + r * sS_;
-        const double* UaT = p->uT + R * sS_ + r * ((long)m * p->tlda);
-        PL_CHECK(gpcsd_project_quad_strided(nx, ms, N, UsT, lds, Zr, ldn, row, rDr, ldt, Br, part, res + 0, st));
-        PL_CHECK(gpcsd_project_quad_strided(nx, m, N, UaT, p->tlda, Zr + (long)ms * ldn, ldn, row, rDr + ms, ldt, Br + (long)ms * ldn, part,
-                                            res + 24, st));
-        p->launches += 4;
-      } else {
-        PL_CHECK(gpcsd_project_quad(nx, nt, N, QtT + (fac ? 0 : (long)r * nt * ldt), ldt, Zr, ldn, rDr, ldt, Br, part, res + 0, st));
-        p->launches += 2;
-      }
+    // all restarts x all spatial eigen-indices in ONE launch per block (gpcsd_project_quad_batched)
+    if (use_tfold) {
+      const int m = p->tm, ms = p->tms;
+      const long lds = p->tlds, sS_ = (long)ms * lds;
+      PL_CHECK(gpcsd_project_quad_batched(R, nx, ms, N, p->uT, lds, sS_, p->Z, ldn, row, p->rD, ldt, p->Bm, p->pq_ws, p->res + 0,
+                                          pl::RESW, st));
+      PL_CHECK(gpcsd_project_quad_batched(R, nx, m, N, p->uT + R * sS_, p->tlda, (long)m * p->tlda, p->Z + (long)ms * ldn, ldn, row,
+                                          p->rD + ms, ldt, p->Bm + (long)ms * ldn, p->pq_ws, p->res + 24, pl::RESW, st));
+      p->launches += 4;
+    } else {
+      PL_CHECK(gpcsd_project_quad_batched(R, nx, nt, N, QtT, ldt, fac ? 0 : (long)nt * ldt, p->Z, ldn, row, p->rD, ldt, p->Bm, p->pq_ws,
+                                          p->res + 0, pl::RESW, st));
+      p->launches += 2;
     }
   }
 
@@ -962,21 +955,16 @@ int enqueue_body(Plan* p, int R, int want_grad, const Factors* fac, cudaStream_t
     };
     // ================= temporal branch (main stream)
     if (blockT || N == 0) PL_CHECK(zero(p->Mt, nMt, st));
-    if (N > 0) {
-      for (int r = 0; r < R; ++r) {
-        const double* Br = p->Bm + r * slab;
-        const double* lsr = ls + (fac ? 0 : (long)r * nx);
-        double* Mt = p->Mt + (long)r * nt * ldt;
-        double* wt = p->syrk_ws_t + (long)r * p->syrk_t_doubles;
-        if (blockT) {     // only the two diagonal blocks of Mt enter <dL/dKt, dKt/dtheta>
-          const int m = p->tm, ms = p->tms;
-          PL_CHECK(gpcsd_wsyrk(ms, nx, N, Br, ldn, row, lsr, Mt, ldt, wt, st));
-          PL_CHECK(gpcsd_wsyrk(m, nx, N, Br + (long)ms * ldn, ldn, row, lsr, Mt + (long)ms * ldt + ms, ldt, wt, st));
-          p->launches += 4;
-        } else {
-          PL_CHECK(gpcsd_wsyrk(nt, nx, N, Br, ldn, row, lsr, Mt, ldt, wt, st));
-          p->launches += 2;
-        }
+    if (N > 0) {   // all restarts in one launch (gpcsd_wsyrk_batched: blockIdx.z / 4th tensor-map dimension = restart)
+      if (blockT) {     // only the two diagonal blocks of Mt enter <dL/dKt, dKt/dtheta>
+        const int m = p->tm, ms = p->tms;
+        PL_CHECK(gpcsd_wsyrk_batched(R, ms, nx, N, p->Bm, ldn, row, slab, ls, nx, p->Mt, nullptr, ldt, nt * ldt, p->syrk_ws_t, st));
+        PL_CHECK(gpcsd_wsyrk_batched(R, m, nx, N, p->Bm + (long)ms * ldn, ldn, row, slab, ls, nx, p->Mt + (long)ms * ldt + ms, nullptr,
+                                     ldt, nt * ldt, p->syrk_ws_t, st));
+        p->launches += 4;
+      } else {
+        PL_CHECK(gpcsd_wsyrk_batched(R, nt, nx, N, p->Bm, ldn, row, slab, ls, nx, p->Mt, nullptr, ldt, nt * ldt, p->syrk_ws_t, st));
+        p->launches += 2;
       }
     }
     pl::grad_core_kernel<<<dim3(blocks256((long)nt * nt), R), 256, 0, st>>>(nt, p->Mt, ldt, nt * ldt, nullptr, lt, p->theta, d.P, sig_idx,
@@ -998,27 +986,16 @@ int enqueue_body(Plan* p, int R, int want_grad, const Factors* fac, cudaStream_t
     if (blockS || N == 0) PL_CHECK(zero(p->Ms, nMs, sG));
     if (vec && N == 0) PL_CHECK(zero(p->Ns, nMs, sG));
     if (N > 0) {
-      for (int r = 0; r < R; ++r) {
-        const double* Br = p->Bm + r * slab;
-        const double* ltr = lt + (fac ? 0 : (long)r * nt);
-        double* Ms = p->Ms + (long)r * nx * ldx;
-        double* wsS = p->syrk_ws_s + (long)r * p->syrk_s_doubles;
-        if (blockS) {
-          const int mh = p->sm;
-          PL_CHECK(gpcsd_wsyrk(mh, nt, N, Br, row, ldn, ltr, Ms, ldx, wsS, sG));
-          PL_CHECK(gpcsd_wsyrk(mh, nt, N, Br + (long)mh * row, row, ldn, ltr, Ms + (long)mh * ldx + mh, ldx, wsS, sG));
-          p->launches += 4;
-        } else if (vec) {  // per-electrode noise: Ms and Ns from one pass over Bm
-          PL_CHECK(gpcsd_wsyrk_pair(nx, nt, N, Br, row, ldn, ltr, Ms, p->Ns + (long)r * nx * ldx, ldx, wsS, sG));
-          p->launches += (nx <= 32) ? 2 : 4;
-        } else {
-          PL_CHECK(gpcsd_wsyrk(nx, nt, N, Br, row, ldn, ltr, Ms, ldx, wsS, sG));
-          p->launches += 2;
-        }
-        if (vec && blockS) {
-          PL_CHECK(gpcsd_wsyrk(nx, nt, N, Br, row, ldn, nullptr, p->Ns + (long)r * nx * ldx, ldx, wsS, sG));
-          p->launches += 2;
-        }
+      if (blockS) {
+        const int mh = p->sm;
+        PL_CHECK(gpcsd_wsyrk_batched(R, mh, nt, N, p->Bm, row, ldn, slab, lt, nt, p->Ms, nullptr, ldx, nx * ldx, p->syrk_ws_s, sG));
+        PL_CHECK(gpcsd_wsyrk_batched(R, mh, nt, N, p->Bm + (long)mh * row, row, ldn, slab, lt, nt, p->Ms + (long)mh * ldx + mh, nullptr,
+                                     ldx, nx * ldx, p->syrk_ws_s, sG));
+        p->launches += 4;
+      } else {         // per-electrode noise: Ms and Ns from one pass over Bm (nx <= 32)
+        PL_CHECK(gpcsd_wsyrk_batched(R, nx, nt, N, p->Bm, row, ldn, slab, lt, nt, p->Ms, vec ? p->Ns : nullptr, ldx, nx * ldx,
+                                     p->syrk_ws_s, sG));
+        p->launches += (vec && nx > 32) ? 4 : 2;
       }
     }
     pl::grad_core_kernel<<<dim3(blocks256((long)nx * nx), R), 256, 0, sG>>>(nx, p->Ms, ldx, nx * ldx, vec ? p->Ns : nullptr, ls, p->theta,

@@ -74,6 +74,13 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ double2 lds128(uint32_t addr) {
   double2 v;
   asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "r"(addr));
@@ -153,9 +160,11 @@ struct TmaGemmArgs {
   int M, N, K, batch;
   int m_tiles, n_tiles;
   int a_batched;      // 0: A shared by all batches
+  int a_div;          // A operand of batch b is slab b / a_div of the tensor map (restart-batched projection: a_div = nx)
+  int grp, ngrp;      // EPI_QUAD: batches are reduced in ngrp groups of grp consecutive batches (one group per restart)
   const double* rD;   // EPI_QUAD
   long ldrd;
-  double* partials;   // [gridDim.x][2]
+  double* partials;   // [ngrp][gridDim.x][2]
 };
 
 constexpr int TEPI_STORE = 0, TEPI_QUAD = 1;
@@ -204,7 +213,7 @@ __global__ void __launch_bounds__(T_THREADS, 1)
           mbar_expect_tx(full + s, T_TILE_BYTES + BN * BK * 8);
           uint8_t* sa = tiles + (size_t)s * T_STAGE_BYTES;
           uint8_t* sb = sa + T_TILE_BYTES;
-          tma_load_3d(sa, &tmA, full + s, kb * BK, m0, p.a_batched ? b : 0);
+          tma_load_3d(sa, &tmA, full + s, kb * BK, m0, p.a_batched ? b / p.a_div : 0);
           if (BT) {
             tma_load_3d(sb, &tmB, full + s, kb * BK, n0, b);       // box 16 k x BN rows
           } else {
@@ -225,11 +234,48 @@ __global__ void __launch_bounds__(T_THREADS, 1)
   const int pg = perm8(g);
   double quad = 0.0, bsq = 0.0;
   uint32_t it = 0;
+  // EPI_QUAD with several reduction groups (restarts): a CTA's tiles visit the groups in increasing order, so the running
+  // sums are flushed into the group's slot whenever the group changes; slots of groups this CTA never visits stay zero.
+  __shared__ double red[2][T_CONSUMERS];
+  int cur_grp = -1;
+  auto flush = [&](int grp_id) {
+    const double q0 = warp_sum(quad), b0 = warp_sum(bsq);
+    if (lane == 0) {
+      red[0][warp] = q0;
+      red[1][warp] = b0;
+    }
+    asm volatile("bar.sync 1, %0;\n" ::"n"(32 * T_CONSUMERS) : "memory");
+    if (warp == 0 && lane == 0) {
+      double s0 = 0.0, s1 = 0.0;
+      for (int w = 0; w < T_CONSUMERS; ++w) {
+        s0 += red[0][w];
+        s1 += red[1][w];
+      }
+      p.partials[2 * ((long)grp_id * gridDim.x + blockIdx.x)] = s0;
+      p.partials[2 * ((long)grp_id * gridDim.x + blockIdx.x) + 1] = s1;
+    }
+    asm volatile("bar.sync 1, %0;\n" ::"n"(32 * T_CONSUMERS) : "memory");
+    quad = bsq = 0.0;
+  };
+  if (EPI == TEPI_QUAD) {
+    for (int gi = threadIdx.x - 32 * T_PRODUCER_WARPS; gi < p.ngrp; gi += 32 * T_CONSUMERS) {
+      p.partials[2 * ((long)gi * gridDim.x + blockIdx.x)] = 0.0;
+      p.partials[2 * ((long)gi * gridDim.x + blockIdx.x) + 1] = 0.0;
+    }
+    asm volatile("bar.sync 1, %0;\n" ::"n"(32 * T_CONSUMERS) : "memory");
+  }
   for (long t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const int mt = (int)(t % p.m_tiles);
     const long r = t / p.m_tiles;
     const int nt_ = (int)(r % p.n_tiles), b = (int)(r / p.n_tiles);
     const int m0 = mt * T_BM, n0 = nt_ * BN;
+    if (EPI == TEPI_QUAD) {
+      const int gnow = b / p.grp;
+      if (gnow != cur_grp) {
+        if (cur_grp >= 0) flush(cur_grp);
+        cur_grp = gnow;
+      }
+    }
     double acc[T_MT][NTW][2];
 #pragma unroll
     for (int i = 0; i < T_MT; ++i)
@@ -283,26 +329,7 @@ __global__ void __launch_bounds__(T_THREADS, 1)
       }
     }
   }
-  if (EPI == TEPI_QUAD) {
-    // consumer-only reduction (named barrier 1, 256 threads): fixed order -> deterministic
-    __shared__ double red[2][T_CONSUMERS];
-    quad = warp_sum(quad);
-    bsq = warp_sum(bsq);
-    if (lane == 0) {
-      red[0][warp] = quad;
-      red[1][warp] = bsq;
-    }
-    asm volatile("bar.sync 1, %0;\n" ::"n"(32 * T_CONSUMERS) : "memory");
-    if (warp == 0 && lane == 0) {
-      double s0 = 0.0, s1 = 0.0;
-      for (int w = 0; w < T_CONSUMERS; ++w) {
-        s0 += red[0][w];
-        s1 += red[1][w];
-      }
-      p.partials[2 * blockIdx.x] = s0;
-      p.partials[2 * blockIdx.x + 1] = s1;
-    }
-  }
+  if (EPI == TEPI_QUAD && cur_grp >= 0) flush(cur_grp);     // consumer-only reduction, fixed order -> deterministic
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -315,7 +342,9 @@ struct TmaSyrkArgs {
   long total_kb;  // nseg * kbps
   int nsplit, tiles_1d;
   int seg_middle; // tensor-map dim order {k, seg, row} instead of {k, row, seg}
-  double* ws;     // [nsplit][ntiles][128*128] in fragment order
+  double* ws;     // [restart][nsplit][ntiles][128*128] in fragment order
+  long w_stride;  // restart strides (blockIdx.z = restart; the tensor map's 4th dimension)
+  long ws_stride;
 };
 
 __global__ void __launch_bounds__(T_THREADS, 1)
@@ -343,12 +372,13 @@ __global__ void __launch_bounds__(T_THREADS, 1)
         mbar_wait(empty + s, ((it / T_STAGES) & 1) ^ 1);
         mbar_expect_tx(full + s, diag ? T_TILE_BYTES : T_STAGE_BYTES);
         uint8_t* sa = tiles + (size_t)s * T_STAGE_BYTES;
+        const int rr = blockIdx.z;
         if (p.seg_middle) {
-          tma_load_3d(sa, &tmX, full + s, k0, seg, tm * T_BM);
-          if (!diag) tma_load_3d(sa + T_TILE_BYTES, &tmX, full + s, k0, seg, tn * T_BN);
+          tma_load_4d(sa, &tmX, full + s, k0, seg, tm * T_BM, rr);
+          if (!diag) tma_load_4d(sa + T_TILE_BYTES, &tmX, full + s, k0, seg, tn * T_BN, rr);
         } else {
-          tma_load_3d(sa, &tmX, full + s, k0, tm * T_BM, seg);
-          if (!diag) tma_load_3d(sa + T_TILE_BYTES, &tmX, full + s, k0, tn * T_BN, seg);
+          tma_load_4d(sa, &tmX, full + s, k0, tm * T_BM, seg, rr);
+          if (!diag) tma_load_4d(sa + T_TILE_BYTES, &tmX, full + s, k0, tn * T_BN, seg, rr);
         }
       }
     }
@@ -365,7 +395,7 @@ __global__ void __launch_bounds__(T_THREADS, 1)
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
   for (int it = 0; it < nkb; ++it) {
     const int s = it % T_STAGES;
-    const double wgt = p.w ? __ldg(p.w + (f0 + it) / p.kbps) : 1.0;
+    const double wgt = p.w ? __ldg(p.w + (long)blockIdx.z * p.w_stride + (f0 + it) / p.kbps) : 1.0;
     mbar_wait(full + s, (it / T_STAGES) & 1);
     const uint32_t sa = smem_u32(tiles + (size_t)s * T_STAGE_BYTES);
     if (p.w)
@@ -377,7 +407,7 @@ __global__ void __launch_bounds__(T_THREADS, 1)
   }
   // partial tile in fragment order: fully coalesced double2 stores
   const long ntiles = (long)p.tiles_1d * (p.tiles_1d + 1) / 2;
-  double* out = p.ws + ((long)split * ntiles + t) * (T_BM * T_BN);
+  double* out = p.ws + (long)blockIdx.z * p.ws_stride + ((long)split * ntiles + t) * (T_BM * T_BN);
 #pragma unroll
   for (int i = 0; i < T_MT; ++i)
 #pragma unroll
@@ -390,8 +420,10 @@ __global__ void __launch_bounds__(T_THREADS, 1)
 // are added in order through shared memory): four times the loads in flight of a one-thread-per-element sum, which was
 // latency-bound at 14 % of HBM bandwidth.
 __global__ void __launch_bounds__(256) tma_wsyrk_reduce_kernel(const double* __restrict__ ws, int nsplit, int tiles_1d, int M,
-                                                               double* __restrict__ C, long ldc) {
+                                                               double* __restrict__ C, long ldc, long ws_stride, long c_stride) {
   __shared__ double part[4][64];
+  ws += (long)blockIdx.z * ws_stride;
+  C += (long)blockIdx.z * c_stride;
   const long ntiles = (long)tiles_1d * (tiles_1d + 1) / 2;
   const int t = blockIdx.y;
   int tm = 0;
@@ -465,6 +497,33 @@ static int make_map3(CUtensorMap* m, const double* base, uint64_t d0, uint64_t d
   return 0;
 }
 
+// 4-D variant (the SYRK's {k, row | seg, seg | row, restart} view of the trial data)
+static int make_map4(CUtensorMap* m, const double* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3, uint64_t s1, uint64_t s2,
+                     uint64_t s3, uint32_t b0, uint32_t b1, uint32_t b2) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return gp_fail("cuTensorMapEncodeTiled entry point not available");
+  if (d1 == 0) d1 = 1;
+  if (d2 == 0) d2 = 1;
+  if (d3 == 0) d3 = 1;
+  if (s1 == 0) s1 = (d0 + 1) & ~1ull;
+  if (s2 == 0) s2 = s1 * d1;
+  if (s3 == 0) s3 = (s2 * d2 > s1 * d1 ? s2 * d2 : s1 * d1);
+  cuuint64_t dims[4] = {d0, d1, d2, d3};
+  cuuint64_t strides[3] = {s1 * 8, s2 * 8, s3 * 8};
+  cuuint32_t box[4] = {b0, b1, b2, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<double*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[200];
+    snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled (4-D) failed (%d): dims %llu %llu %llu %llu", (int)r, (unsigned long long)d0,
+             (unsigned long long)d1, (unsigned long long)d2, (unsigned long long)d3);
+    return gp_fail(buf);
+  }
+  return 0;
+}
+
 template <bool BT, int EPI, int NTW>
 static int launch_tma_gemm(const CUtensorMap& tA, const CUtensorMap& tB, TmaGemmArgs& p, cudaStream_t st) {
   auto kern = tma_gemm_kernel<BT, EPI, NTW>;
@@ -515,11 +574,13 @@ static int launch_tma_gemm_ntw(int ntw, const CUtensorMap& tA, const CUtensorMap
 // C_b = A_b op(B_b); epi_quad != 0 fuses the /D + quadratic-form epilogue.  Returns 0 on success.
 int tma_gemm(int transB, int M, int N, int K, const double* A, long lda, long sA, const double* B, long ldb, long sB,
              double* C, long ldc, long sC, int batch, const double* rD, long ldrd, double* partials, int epi_quad,
-             cudaStream_t st) {
+             cudaStream_t st, int a_div, int grp) {
   CUtensorMap tA, tB;
   const bool a_batched = (sA != 0 && batch > 1);
+  if (a_div < 1) a_div = 1;
+  if (grp < 1) grp = batch;
   const int ntw = pick_ntw(M, N, batch), bn = 32 * ntw;
-  if (int e = make_map3(&tA, A, K, M, a_batched ? batch : 1, lda, a_batched ? sA : 0, BK, T_BM, 1)) return e;
+  if (int e = make_map3(&tA, A, K, M, a_batched ? (batch + a_div - 1) / a_div : 1, lda, a_batched ? sA : 0, BK, T_BM, 1)) return e;
   const long sBe = (batch > 1) ? sB : 0;
   if (transB) {
     if (int e = make_map3(&tB, B, K, N, batch, ldb, sBe, BK, bn, 1)) return e;
@@ -532,6 +593,7 @@ int tma_gemm(int transB, int M, int N, int K, const double* A, long lda, long sA
   p.m_tiles = (M + T_BM - 1) / T_BM;
   p.n_tiles = (N + bn - 1) / bn;
   p.a_batched = a_batched ? 1 : 0;
+  p.a_div = a_div; p.grp = grp; p.ngrp = (batch + grp - 1) / grp;
   p.rD = rD; p.ldrd = ldrd; p.partials = partials;
   if (epi_quad) return launch_tma_gemm_ntw<false, TEPI_QUAD>(ntw, tA, tB, p, st);
   if (transB) return launch_tma_gemm_ntw<true, TEPI_STORE>(ntw, tA, tB, p, st);
@@ -539,29 +601,35 @@ int tma_gemm(int transB, int M, int N, int K, const double* A, long lda, long sA
 }
 
 int tma_wsyrk(int M, int nseg, int seglen, const double* X, long row_stride, long seg_stride, const double* w, double* C,
-              long ldc, double* ws, int nsplit, int tiles_1d, int kbps, long total_kb, cudaStream_t st) {
+              long ldc, double* ws, int nsplit, int tiles_1d, int kbps, long total_kb, cudaStream_t st, int R, long x_stride,
+              long w_stride, long c_stride) {
   CUtensorMap tX;
-  // X[m][seg][k] = X + m*row_stride + seg*seg_stride + k.  Outer tensor dims are ordered by increasing stride
-  // (seg_middle: {k, seg, row}; else {k, row, seg}); the box is 16 k x 128 rows x 1 segment either way, so the
-  // shared-memory image is always [128 rows][16 k].
+  if (R < 1) R = 1;
+  // X[restart][m][seg][k] = X + restart*x_stride + m*row_stride + seg*seg_stride + k.  Outer tensor dims are ordered by
+  // increasing stride (seg_middle: {k, seg, row, restart}; else {k, row, seg, restart}); the box is 16 k x 128 rows x 1 segment
+  // x 1 restart either way, so the shared-memory image is always [128 rows][16 k].
   const bool seg_middle = (nseg > 1) && (seg_stride < row_stride);
+  const long xs = R > 1 ? x_stride : 0;
   if (seg_middle) {
-    if (int e = make_map3(&tX, X, seglen, nseg, M, seg_stride, row_stride, BK, 1, T_BM)) return e;
+    if (int e = make_map4(&tX, X, seglen, nseg, M, R, seg_stride, row_stride, xs, BK, 1, T_BM)) return e;
   } else {
-    if (int e = make_map3(&tX, X, seglen, M, nseg, row_stride, nseg > 1 ? seg_stride : 0, BK, T_BM, 1)) return e;
+    if (int e = make_map4(&tX, X, seglen, M, nseg, R, row_stride, nseg > 1 ? seg_stride : 0, xs, BK, T_BM, 1)) return e;
   }
   TmaSyrkArgs p{};
   p.w = w; p.M = M; p.nseg = nseg; p.seglen = seglen;
   p.kbps = kbps; p.total_kb = total_kb; p.nsplit = nsplit; p.tiles_1d = tiles_1d; p.ws = ws;
   p.seg_middle = seg_middle ? 1 : 0;
+  const long ntiles = (long)tiles_1d * (tiles_1d + 1) / 2;
+  p.w_stride = w_stride;
+  p.ws_stride = (long)nsplit * ntiles * (T_BM * T_BN);
   static int attr[GP_MAX_DEVICES];
   if (gp_first_use_on_device(attr)) {
     GP_CUDA(cudaFuncSetAttribute(tma_wsyrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_SMEM_BYTES));
   }
-  const long ntiles = (long)tiles_1d * (tiles_1d + 1) / 2;
-  tma_wsyrk_kernel<<<dim3((unsigned)ntiles, (unsigned)nsplit), T_THREADS, T_SMEM_BYTES, st>>>(tX, p);
+  tma_wsyrk_kernel<<<dim3((unsigned)ntiles, (unsigned)nsplit, (unsigned)R), T_THREADS, T_SMEM_BYTES, st>>>(tX, p);
   GP_CUDA(cudaGetLastError());
-  tma_wsyrk_reduce_kernel<<<dim3(T_BM * T_BN / 64, (unsigned)ntiles), 256, 0, st>>>(ws, nsplit, tiles_1d, M, C, ldc);
+  tma_wsyrk_reduce_kernel<<<dim3(T_BM * T_BN / 64, (unsigned)ntiles, (unsigned)R), 256, 0, st>>>(ws, nsplit, tiles_1d, M, C, ldc,
+                                                                                               p.ws_stride, c_stride);
   GP_CUDA(cudaGetLastError());
   return 0;
 }

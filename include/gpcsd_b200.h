@@ -72,6 +72,14 @@ int gpcsd_project_quad(int nx, int nt, int ntrials,
 int gpcsd_project_quad_strided(int nx, int m, int ntrials, const double* AT, long lda, const double* Z, long ldn, long bstride,
                                const double* rD, long ldrd, double* Bout, double* partials, double* out2, void* stream);
 
+/* Restart-batched form: R hyperparameter vectors x nx spatial eigen-indices in ONE launch (the trial loop of loglik for every
+ * restart of fit(), gpcsd1d.py:193-211 x 124-126).  Restart r uses the m x m block AT + r*strideA; Z / Bout / rD of consecutive
+ * restarts follow each other (Z_r = Z + r*nx*bstride, rD_r = rD + r*nx*ldrd); out2[r*out_stride + {0, 1}] = (quad, bsq). */
+long gpcsd_project_quad_batched_ws_doubles(int R, int nx, int m, int ntrials);
+int gpcsd_project_quad_batched(int R, int nx, int m, int ntrials, const double* AT, long lda, long strideA, const double* Z, long ldn,
+                               long bstride, const double* rD, long ldrd, double* Bout, double* partials, double* out2,
+                               long out_stride, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Segment-weighted symmetric rank-k update (gradient of the quadratic form; replaces the autograd
  * tape of gpcsd1d.py:211 / gpcsd2d.py:250 over the trial loop):
@@ -88,6 +96,12 @@ int gpcsd_wsyrk(int M, int nseg, int seglen,
                 const double* X, long row_stride, long seg_stride,
                 const double* w, double* C, long ldc, double* ws, void* stream);
 
+/* Restart-batched SYRK (all restarts of a multi-start batch in one launch): for r < R,
+ *   Cw_r = sum_seg w_r[seg] X_r,seg X_r,seg^T   and, when Cp != NULL, Cp_r = sum_seg X_r,seg X_r,seg^T,
+ * X_r = X + r*strideX, w_r = w + r*strideW, C_r = C + r*strideC.  ws: gpcsd_wsyrk_batched_ws_doubles(R, M, nseg, seglen, pair). */
+long gpcsd_wsyrk_batched_ws_doubles(int R, int M, int nseg, int seglen, int pair);
+int gpcsd_wsyrk_batched(int R, int M, int nseg, int seglen, const double* X, long row_stride, long seg_stride, long strideX,
+                        const double* w, long strideW, double* Cw, double* Cp, long ldc, long strideC, double* ws, void* stream);
 /* Cw = sum_seg w[seg] X_seg X_seg^T and Cp = sum_seg X_seg X_seg^T in ONE pass over X when M <= 32 (the Ms / Ns pair of the
  * per-electrode-noise gradient: both read Bm); two passes above.  ws: 2 * gpcsd_wsyrk_ws_doubles(M, nseg, seglen) doubles. */
 int gpcsd_wsyrk_pair(int M, int nseg, int seglen, const double* X, long row_stride, long seg_stride, const double* w,

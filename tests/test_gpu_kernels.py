@@ -144,6 +144,48 @@ def test_wsyrk_pair_one_pass(cuda_lib, nx, nt, N):
     assert relerr(Ns[:, :nx].cpu().numpy(), np.einsum("ajr,bjr->ab", B, B)) < 1e-12
 
 
+@pytest.mark.parametrize("R,nx,nt,N", [(3, 24, 50, 50), (2, 24, 250, 96), (5, 5, 20, 9), (2, 40, 130, 33)])
+def test_batched_projection_and_syrk(cuda_lib, R, nx, nt, N):
+    """Restart-batched forms (one launch for R restarts) of the projection with the /D + quadratic-form epilogue and of the
+    segment-weighted SYRKs, against numpy per restart."""
+    from gpcsd_b200 import _lib as L
+    rng = np.random.default_rng(R * 100 + nx + nt + N)
+    ldn, ldt, ldx = (N + 7) // 8 * 8, _ld(nt), _ld(nx)
+    Z = np.zeros((R, nx, nt, ldn)); Z[..., :N] = rng.standard_normal((R, nx, nt, N)); Z[..., N:] = 55.0
+    Q = rng.standard_normal((R, nt, nt))
+    rD = rng.uniform(0.5, 2.0, (R, nx, nt))
+    ls, lt = rng.standard_normal((R, nx)), rng.standard_normal((R, nt))
+    Zd = torch.from_numpy(Z).cuda()
+    QT = torch.zeros((R, nt, ldt), dtype=F64, device="cuda"); QT[:, :, :nt] = torch.from_numpy(Q).cuda()
+    rDd = torch.zeros((R, nx, ldt), dtype=F64, device="cuda"); rDd[:, :, :nt] = torch.from_numpy(rD).cuda()
+    Bd = torch.zeros_like(Zd)
+    part = torch.zeros(L.query("gpcsd_project_quad_batched_ws_doubles", R, nx, nt, N), dtype=F64, device="cuda")
+    out = torch.zeros((R, 32), dtype=F64, device="cuda")
+    L.call("gpcsd_project_quad_batched", R, nx, nt, N, QT.data_ptr(), ldt, nt * ldt, Zd.data_ptr(), ldn, nt * ldn, rDd.data_ptr(), ldt,
+           Bd.data_ptr(), part.data_ptr(), out.data_ptr(), 32, _stream())
+    A = np.einsum("rab,ribn->rian", Q, Z[..., :N])           # A_i = QT Z_i per restart (rows of QT = eigenvectors)
+    Bm = A * rD[..., None]
+    assert relerr(Bd[..., :N].cpu().numpy(), Bm) < 1e-13
+    o = out.cpu().numpy()
+    for r in range(R):
+        assert abs(o[r, 0] - np.sum(A[r] * Bm[r])) < 1e-12 * np.sum(np.abs(A[r] * Bm[r]))
+        assert abs(o[r, 1] - np.sum(Bm[r] ** 2)) < 1e-12 * np.sum(Bm[r] ** 2)
+    # SYRKs on Bd (padding columns hold zeros there)
+    lsd, ltd = torch.from_numpy(ls).cuda(), torch.from_numpy(lt).cuda()
+    Mt = torch.zeros((R, nt, ldt), dtype=F64, device="cuda")
+    ws = torch.zeros(L.query("gpcsd_wsyrk_batched_ws_doubles", R, nt, nx, N, 0), dtype=F64, device="cuda")
+    L.call("gpcsd_wsyrk_batched", R, nt, nx, N, Bd.data_ptr(), ldn, nt * ldn, nx * nt * ldn, lsd.data_ptr(), nx, Mt.data_ptr(), None, ldt,
+           nt * ldt, ws.data_ptr(), _stream())
+    assert relerr(Mt[:, :, :nt].cpu().numpy(), np.einsum("rajn,ra,rakn->rjk", Bm, ls, Bm)) < 1e-12
+    Ms = torch.zeros((R, nx, ldx), dtype=F64, device="cuda")
+    Ns = torch.zeros((R, nx, ldx), dtype=F64, device="cuda")
+    ws = torch.zeros(L.query("gpcsd_wsyrk_batched_ws_doubles", R, nx, nt, N, 1), dtype=F64, device="cuda")
+    L.call("gpcsd_wsyrk_batched", R, nx, nt, N, Bd.data_ptr(), nt * ldn, ldn, nx * nt * ldn, ltd.data_ptr(), nt, Ms.data_ptr(), Ns.data_ptr(),
+           ldx, nx * ldx, ws.data_ptr(), _stream())
+    assert relerr(Ms[:, :, :nx].cpu().numpy(), np.einsum("rajn,rj,rbjn->rab", Bm, lt, Bm)) < 1e-12
+    assert relerr(Ns[:, :, :nx].cpu().numpy(), np.einsum("rajn,rbjn->rab", Bm, Bm)) < 1e-12
+
+
 @pytest.mark.parametrize("n", [5, 24, 100, 251])
 def test_eigh(cuda_lib, n):
     from gpcsd_b200 import _lib as L
@@ -476,6 +518,56 @@ def test_eigh_dc_full(cuda_lib, n, nmat):
         assert np.max(np.abs(Wh - lam)) <= 1e-13 * sc * max(1, n / 16)
         assert np.max(np.abs(Q.T @ Q - np.eye(n))) <= 1e-12
         assert np.max(np.abs(Ms[b] @ Q - Q * Wh)) <= 1e-13 * sc * n
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 16, 24, 25, 31, 32])
+def test_eigh_small_orders_jacobi(cuda_lib, n):
+    """Orders <= 32 take the one-CTA-per-matrix parallel Jacobi kernel: 40 stacked matrices of five families (GP spatial factor
+    with condition ~1e10, SE + Matern temporal factor, random symmetric indefinite, repeated eigenvalues, diagonal) vs numpy."""
+    from gpcsd_b200 import _lib as L
+    rng = np.random.default_rng(100 + n)
+    nmat, ld = 40, _ld(n)
+    Ms = []
+    for b in range(nmat):
+        x = np.linspace(0.0, 2300.0, n)
+        dd = x[:, None] - x[None, :]
+        fam = b % 5
+        if fam == 0:
+            K = np.exp(-0.5 * dd ** 2 / (200.0 + 30 * b) ** 2) + 1e-8 * np.eye(n)
+        elif fam == 1:
+            K = 0.5 * np.exp(-0.5 * (dd / 100.0) ** 2 / 400.0) + 0.2 * np.exp(-np.abs(dd / 100.0) / 5.0)
+        elif fam == 2:
+            K = rng.standard_normal((n, n)); K = K + K.T
+        elif fam == 3:
+            Qr = np.linalg.qr(rng.standard_normal((n, n)))[0]
+            K = (Qr * np.repeat([1.0, 2.0, 2.0, 5.0], n // 4 + 1)[:n]) @ Qr.T
+        else:
+            K = np.diag(rng.standard_normal(n))
+        Ms.append(0.5 * (K + K.T))
+    stack = torch.zeros((nmat, n, ld), dtype=F64, device="cuda")
+    for b in range(nmat):
+        stack[b, :, :n] = torch.from_numpy(Ms[b]).cuda()
+    QT = torch.zeros((nmat, n, ld), dtype=F64, device="cuda")
+    W = torch.zeros((nmat, n), dtype=F64, device="cuda")
+    info = torch.full((nmat,), 7, dtype=torch.int32, device="cuda")
+    nws = max(L.query("gpcsd_eigh_dc_ws_doubles", n, ld, nmat), 1)
+    ws = torch.zeros(nws, dtype=F64, device="cuda")
+    L.call("gpcsd_eigh_dc", n, nmat, stack.data_ptr(), ld, QT.data_ptr(), ld, W.data_ptr(), ws.data_ptr(), nws, info.data_ptr(),
+           _stream())
+    torch.cuda.synchronize()
+    assert torch.all(info == 0)
+    for b in range(nmat):
+        lam = np.linalg.eigvalsh(Ms[b])
+        sc = max(np.max(np.abs(lam)), 1e-300)
+        Wh, Q = W[b].cpu().numpy(), QT[b, :, :n].cpu().numpy().T
+        assert np.all(np.diff(Wh) >= 0)
+        assert np.max(np.abs(Wh - lam)) <= 1e-13 * sc
+        assert np.max(np.abs(Q.T @ Q - np.eye(n))) <= 1e-13
+        assert np.max(np.abs(Ms[b] @ Q - Q * Wh)) <= 1e-13 * sc * n
+        if b % 5 == 0 and n >= 16:
+            # graded SPD factor: the small eigenvalues come out to high RELATIVE accuracy (Jacobi's strength)
+            pos = lam > 1e-7 * sc
+            assert np.max(np.abs(Wh[pos] - lam[pos]) / lam[pos]) < 1e-8
 
 
 @pytest.mark.parametrize("n", [24, 30, 125, 250])
