@@ -274,6 +274,34 @@ class GPCSDModelBase:
         R_fixed = float(self.R['value'])
         eps = float(getattr(self, "eps", 0.0) or 0.0)
 
+        # closed-form priors of this package evaluate vectorised over the restarts; anything else (user-supplied priors with
+        # the reference's scalar lpdf protocol) falls back to a per-value loop
+        from .priors import GPCSDHalfNormalPrior, GPCSDInvGammaPrior
+        builtin = all(type(p) in (GPCSDHalfNormalPrior, GPCSDInvGammaPrior) for p in priors)
+        if builtin:
+            is_ig = np.array([type(p) is GPCSDInvGammaPrior for p in priors])
+            pa = np.array([float(p.alpha) if type(p) is GPCSDInvGammaPrior else 0.0 for p in priors])
+            pb = np.array([float(p.beta) if type(p) is GPCSDInvGammaPrior else 0.0 for p in priors])
+            psd = np.array([float(p.sd) if type(p) is GPCSDHalfNormalPrior else 1.0 for p in priors])
+        template = self._hyperparams()
+
+        def prior_terms(vals):
+            if builtin:
+                pos = vals > 0
+                v = np.where(pos, vals, 1.0)
+                lp = np.where(is_ig, -(pa + 1.0) * np.log(v) - pb / v, -0.5 * np.square(v / psd))       # priors.py:27, :50
+                dlp = np.where(is_ig, -(pa + 1.0) / v + pb / (v * v), -v / (psd * psd))
+                lp = np.where(pos, lp, -np.inf)
+                return np.sum(lp, axis=1), np.where(pos, dlp, 0.0)
+            lps, dlps = [], []
+            for v in vals:
+                lp = 0.0
+                for p, x in zip(priors, v):
+                    lp = lp + p.lpdf(x)
+                lps.append(lp)
+                dlps.append([_dlpdf(p, x) if x > 0 else 0.0 for p, x in zip(priors, v)])
+            return np.array(lps), np.array(dlps)
+
         def fun(X, idx):
             with np.errstate(all='ignore'):
                 X = np.atleast_2d(np.asarray(X, dtype=np.float64))
@@ -281,20 +309,11 @@ class GPCSDModelBase:
                 vals[:, :nslots] *= scales[None, :]
                 if fix_R:
                     vals[:, 0] = R_fixed
-                hps, lps, dlps = [], [], []
-                for v in vals:
-                    lp = 0.0
-                    for p, x in zip(priors, v):
-                        lp = lp + p.lpdf(x)
-                    lps.append(lp)
-                    dlps.append([_dlpdf(p, x) if x > 0 else 0.0 for p, x in zip(priors, v)])
-                    temporal = [(kinds[k], float(v[1 + nsp + 2 * k]), float(v[2 + nsp + 2 * k])) for k in range(len(kinds))]
-                    sig = float(v[nslots]) if noise_scalar else np.array(v[nslots:])
-                    hps.append(HyperParams(R=float(v[0]), ells=tuple(float(x) for x in v[1:1 + nsp]), temporal=temporal,
-                                           sig2n=sig, eps=eps))
-                ll, g, flag = engine.loglik_grad_batch(hps)
-                nll = -(ll + np.array(lps))
-                grad = -(g + np.array(dlps)) * vals
+                lps, dlps = prior_terms(vals)
+                # natural-unit theta rows in the plan's order are exactly `vals` (R, ell(s), (ell_t, sigma2_t)..., sig2n[...])
+                ll, g, flag = engine.loglik_grad_thetas(vals, template)
+                nll = -(ll + lps)
+                grad = -(g + dlps) * vals
                 if fix_R:
                     grad[:, 0] = 0.0
                 bad = flag != 0

@@ -10,8 +10,10 @@ Two callers:
 Algorithm (per problem, vectorised over the batch): limited-memory BFGS two-loop recursion on the free variables (variables
 sitting on a bound with the gradient pointing outwards are frozen for the step, as in the generalized Cauchy point of Byrd,
 Lu, Nocedal & Zhu 1995), projected backtracking line search with the Armijo condition, curvature-guarded history update.
-Stopping tests are scipy L-BFGS-B's: max |projected gradient| <= gtol, or (f_k - f_{k+1}) / max(|f_k|, |f_{k+1}|, 1) <= ftol,
-or maxiter iterations.  Problems that have stopped are dropped from the batch, so late iterations evaluate fewer points.
+Stopping tests are scipy L-BFGS-B's: max |projected gradient| <= gtol, or (f_k - f_{k+1}) / max(|f_k|, |f_{k+1}|, 1) <= ftol
+(in two consecutive iterations, the second one a scaled steepest-descent step after the memory has been dropped: a
+backtracking search, unlike scipy's Wolfe search, can return a crippled step from a poor quasi-Newton direction), or maxiter
+iterations.  Problems that have stopped are dropped from the batch, so late iterations evaluate fewer points.
 """
 import numpy as np
 
@@ -54,39 +56,41 @@ def batched_lbfgsb(fun, X0, bounds=None, m=10, maxiter=1000, gtol=1e-5, ftol=1e7
     pg = np.stack([_projected_gradient(X[b], G[b], lo, hi) for b in range(B)])
     status[(status == "running") & (np.max(np.abs(pg), axis=1) <= gtol)] = "gtol"
 
+    strikes = np.zeros(B, dtype=int)         # consecutive iterations whose decrease fell below ftol
     for _ in range(int(maxiter)):
         act = np.where(status == "running")[0]
         if act.size == 0:
             break
-        # ---- search directions (two-loop recursion on the free variables)
-        D = np.zeros((act.size, n))
-        for a, b in enumerate(act):
-            g = G[b]
-            free = ~(((X[b] <= lo) & (g > 0)) | ((X[b] >= hi) & (g < 0)))
-            q = np.where(free, g, 0.0)
-            k = nhist[b]
-            alpha = np.zeros(k)
-            for i in range(k - 1, -1, -1):
-                alpha[i] = rho[b, i] * np.dot(S[b, i], q)
-                q = q - alpha[i] * Yh[b, i]
-            if k > 0:
-                gamma = np.dot(S[b, k - 1], Yh[b, k - 1]) / max(np.dot(Yh[b, k - 1], Yh[b, k - 1]), 1e-300)
-            else:
-                gamma = 1.0 / max(np.linalg.norm(q), 1e-300)      # first step of length ~1 like scipy's initial trial
-            r = gamma * q
-            for i in range(k):
-                beta = rho[b, i] * np.dot(Yh[b, i], r)
-                r = r + S[b, i] * (alpha[i] - beta)
-            d = np.where(free, -r, 0.0)
-            if not np.dot(d, g) < 0.0:                            # not a descent direction: restart from steepest descent
-                d = np.where(free, -g, 0.0)
-                nhist[b] = 0
-            D[a] = d
+        # ---- search directions: two-loop recursion on the free variables, vectorised over the active problems (history is
+        #      stored left-aligned: slots >= nhist[b] hold zeros and rho = 0, so they drop out of both loops)
+        Xa, Ga = X[act], G[act]
+        free = ~(((Xa <= lo) & (Ga > 0)) | ((Xa >= hi) & (Ga < 0)))
+        q = np.where(free, Ga, 0.0)
+        Sa, Ya, ra, ka = S[act], Yh[act], rho[act], nhist[act]
+        alpha = np.zeros((act.size, m))
+        for i in range(m - 1, -1, -1):
+            alpha[:, i] = ra[:, i] * np.einsum("an,an->a", Sa[:, i], q)
+            q = q - alpha[:, i, None] * Ya[:, i]
+        newest = np.maximum(ka - 1, 0)
+        ar = np.arange(act.size)
+        sy = np.einsum("an,an->a", Sa[ar, newest], Ya[ar, newest])
+        yy = np.einsum("an,an->a", Ya[ar, newest], Ya[ar, newest])
+        gamma = np.where(ka > 0, sy / np.maximum(yy, 1e-300), 1.0 / np.maximum(np.linalg.norm(q, axis=1), 1e-300))
+        r = gamma[:, None] * q
+        for i in range(m):
+            beta = ra[:, i] * np.einsum("an,an->a", Ya[:, i], r)
+            r = r + Sa[:, i] * (alpha[:, i] - beta)[:, None]
+        D = np.where(free, -r, 0.0)
+        notdesc = ~(np.einsum("an,an->a", D, Ga) < 0.0)          # not a descent direction: restart from steepest descent
+        if np.any(notdesc):
+            D[notdesc] = np.where(free[notdesc], -Ga[notdesc], 0.0)
+            bad = act[notdesc]
+            nhist[bad] = 0
+            S[bad], Yh[bad], rho[bad] = 0.0, 0.0, 0.0
         # ---- projected backtracking line search, all active problems together
         step = np.ones(act.size)
         done = np.zeros(act.size, dtype=bool)
         Xn, Fn, Gn = X[act].copy(), F[act].copy(), G[act].copy()
-        slope0 = np.einsum("an,an->a", D, G[act])
         for _ls in range(int(maxls)):
             todo = np.where(~done)[0]
             if todo.size == 0:
@@ -95,11 +99,12 @@ def batched_lbfgsb(fun, X0, bounds=None, m=10, maxiter=1000, gtol=1e-5, ftol=1e7
             ft, gt = fun(Xt, act[todo])
             nfev += 1
             ft = np.where(np.isfinite(ft), ft, np.inf)
+            gt = np.asarray(gt, dtype=np.float64)
             # Armijo on the projected step: f(x+) <= f + c1 g.(x+ - x)
             dec = np.einsum("an,an->a", G[act[todo]], Xt - X[act[todo]])
             ok = np.isfinite(ft) & (ft <= F[act[todo]] + 1e-4 * dec) & np.all(np.isfinite(gt), axis=1)
             sel = todo[ok]
-            Xn[sel], Fn[sel], Gn[sel] = Xt[ok], ft[ok], np.asarray(gt)[ok]
+            Xn[sel], Fn[sel], Gn[sel] = Xt[ok], ft[ok], gt[ok]
             done[sel] = True
             step[todo[~ok]] *= 0.5
         # ---- accept / stop
@@ -123,7 +128,17 @@ def batched_lbfgsb(fun, X0, bounds=None, m=10, maxiter=1000, gtol=1e-5, ftol=1e7
             if np.max(np.abs(pgb)) <= gtol:
                 status[b] = "gtol"
             elif (f_old - F[b]) <= ftol * max(abs(f_old), abs(F[b]), 1.0):
-                status[b] = "ftol"
+                # scipy's L-BFGS-B can trust this test because its Wolfe line search never returns a crippled step; a
+                # backtracking search can (a poor quasi-Newton direction, cut to a tiny step).  So the first strike only
+                # drops the memory -- the next step is scaled steepest descent -- and a second consecutive one stops.
+                strikes[b] += 1
+                if strikes[b] >= 2:
+                    status[b] = "ftol"
+                else:
+                    nhist[b] = 0
+                    S[b], Yh[b], rho[b] = 0.0, 0.0, 0.0
+            else:
+                strikes[b] = 0
         if callback is not None:
             callback(X, F, status)
     status[status == "running"] = "maxiter"

@@ -672,6 +672,27 @@ class KronEngine:
         P = out.shape[1] - 4
         return out[:, 0].copy(), out[:, 1:1 + P].copy(), out[:, 1 + P].copy()
 
+    def loglik_grad_thetas(self, thetas, template, want_grad=True):
+        """loglik_grad_batch for hyperparameters already laid out as rows of natural-unit theta vectors (the plan's order);
+        `template` is any HyperParams of the same structure (temporal kernel kinds, scalar / per-electrode noise, eps)."""
+        thetas = np.ascontiguousarray(thetas, dtype=np.float64)
+        R = thetas.shape[0]
+        key = (tuple(k for k, _, _ in template.temporal), self.nx if template.vector_noise else 1, float(template.eps))
+        have = self._plans.get(key)
+        chunk = R if (R == 1 or (have is not None and have.rmax >= R)) else self.max_batch(template, R)
+        outs = []
+        for lo in range(0, R, chunk):
+            part = thetas[lo: lo + chunk]
+            n = part.shape[0]
+            npad = min(1 << (n - 1).bit_length(), max(chunk, n)) if n > 1 else 1
+            pl = self._plan_for(template, npad)
+            th = part if npad == n else np.concatenate([part, np.repeat(part[-1:], npad - n, axis=0)], axis=0)
+            outs.append(pl.evaluate(th, want_grad)[:n])
+            self.n_launches += max(pl.last_launches(), 0)
+        out = np.concatenate(outs, axis=0)
+        P = out.shape[1] - 4
+        return out[:, 0].copy(), out[:, 1:1 + P].copy(), out[:, 1 + P].copy()
+
     def loglik(self, hp, factors=None):
         """Marginal log-likelihood (gpcsd1d.py:113-128 / gpcsd2d.py:136-151); all-reduced over trial shards.
         factors: optional caller-supplied (Qs, ls, Qt, lt), see _given_factors."""

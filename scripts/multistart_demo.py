@@ -18,9 +18,10 @@ sys.path.insert(0, ROOT)
 
 
 def main():
-    nt = int(sys.argv[1]) if len(sys.argv) > 1 else 50
-    ntrials = int(sys.argv[2]) if len(sys.argv) > 2 else 50
-    n_restarts = int(sys.argv[3]) if len(sys.argv) > 3 else 64
+    args = [a for a in sys.argv[1:] if a != "--sequential"]
+    nt = int(args[0]) if len(args) > 0 else 50
+    ntrials = int(args[1]) if len(args) > 1 else 50
+    n_restarts = int(args[2]) if len(args) > 2 else 64
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -36,13 +37,24 @@ def main():
     x, t = synth.geometry_1d(24, nt)
     om = synth.model_1d(x, t, sig2n=1e-2)
     lfp = synth.matched_lfp(om, ntrials, 1000)
-    count = {"n": 0}
-    orig = KronEngine.loglik_grad
+    count = {"n": 0, "calls": 0}
+    orig = KronEngine.loglik_grad_batch
 
-    def counted(self, hp):
-        count["n"] += 1
-        return orig(self, hp)
-    KronEngine.loglik_grad = counted
+    def counted(self, hps, want_grad=True):
+        hps = list(hps)
+        count["n"] += len(hps)                     # evaluations (restart x step)
+        count["calls"] += 1                        # native calls (one per lock step)
+        return orig(self, hps, want_grad)
+    KronEngine.loglik_grad_batch = counted
+    orig_t = KronEngine.loglik_grad_thetas
+
+    def counted_t(self, thetas, template, want_grad=True):
+        count["n"] += len(thetas)
+        count["calls"] += 1
+        return orig_t(self, thetas, template, want_grad)
+    KronEngine.loglik_grad_thetas = counted_t
+    lockstep = "--sequential" not in sys.argv
+    sys.argv = [a for a in sys.argv if a != "--sequential"]
     np.random.seed(1)
     m = GPCSD1D(lfp, x, t, distributed_restarts=(world > 1))
     m.loglik()                                             # upload + warm-up
@@ -50,7 +62,7 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    m.fit(n_restarts=n_restarts)
+    m.fit(n_restarts=n_restarts, lockstep=lockstep)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     n = torch.tensor([float(count["n"]), dt], dtype=torch.float64, device="cuda")
@@ -64,8 +76,9 @@ def main():
         nev, wall = float(n[0]), dt
     if rank == 0:
         p = m.extract_model_params()
-        print("multi-start fit 24x%dx%d: %d restarts on %d GPU(s): %d loglik+grad evaluations in %.2f s -> %.0f evals/s; "
-              "R %.1f ell %.1f sig2n %.4f" % (nt, ntrials, n_restarts, world, nev, wall, nev / wall, p['R'], p['spatial_ell'], p['sig2n']))
+        print("multi-start fit 24x%dx%d (%s): %d restarts on %d GPU(s): %d loglik+grad evaluations in %.2f s -> %.0f evals/s; "
+              "R %.1f ell %.1f sig2n %.4f" % (nt, ntrials, "lock step" if lockstep else "scipy per restart", n_restarts, world, nev, wall,
+                                               nev / wall, p['R'], p['spatial_ell'], p['sig2n']))
     if world > 1:
         dist.destroy_process_group()
 
