@@ -318,7 +318,17 @@ def secondary_lines(torch, device, K):
     run(m2, tp2, max(5, K), "BASELINE.json configs[2]: GPCSD2D Neuropixels-shaped 384 ch x 250 t x 500 trials, ngl 30x120, eps=1, "
         "scalar noise (P=8)", {"flops_per_eval_algorithmic": 4.0 * 500 * 384 * 250 * (384 + 250)})
     out[-1]["tflops_algorithmic"] = out[-1]["flops_per_eval_algorithmic"] / (out[-1]["ms_per_eval"] * 1e-3) * 1e-12
-    del m0, m2
+    del m2, lfp2
+    torch.cuda.empty_cache()
+    # configs[4]: one point of the GPCSD2D scaling sweep (the whole sweep: scripts/sweep_2d.py, profiles/r02_sweep_2d.md):
+    # 384 ch x 1000 t x 1000 trials -- temporal halves of order 500 take the cuSOLVER syevd branch
+    t4 = (0.4 * np.arange(1000, dtype=np.float64))[:, None]
+    lfp4 = torch.randn((384, 1000, 1000), dtype=torch.float64, device=device).cpu().numpy()
+    m4 = GPCSD2D(lfp4, X, t4, a1=-16.0, b1=64.0, a2=-100.0, b2=float(X[:, 1].max()) + 100.0, ngl1=30, ngl2=120, eps=1.0)
+    run(m4, tp2, 3, "BASELINE.json configs[4] sample point: GPCSD2D 384 ch x 1000 t x 1000 trials, ngl 30x120 (sweep: "
+        "profiles/r02_sweep_2d.md)", {"flops_per_eval_algorithmic": 4.0 * 1000 * 384 * 1000 * (384 + 1000)})
+    out[-1]["tflops_algorithmic"] = out[-1]["flops_per_eval_algorithmic"] / (out[-1]["ms_per_eval"] * 1e-3) * 1e-12
+    del m0, m4, lfp4
     torch.cuda.empty_cache()
     return out
 
