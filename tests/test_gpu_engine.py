@@ -241,3 +241,22 @@ def test_spatial_reflection_symmetry_split(cuda_lib):
     eng3, hp3 = engine_from_oracle(om1, lfp1)
     assert eng3.s_pairs is not None
     assert abs(eng3.loglik(hp3) - O.loglik(om1, lfp1)) / abs(O.loglik(om1, lfp1)) < 1e-8
+
+
+def test_predict_against_multiprecision_arbiter(cuda_lib):
+    """Engine predict vs a 40-digit mpmath solve of the same system (oracle/arbiter_mp.py) at cond(K) ~ 6e8: the engine's
+    Kronecker form agrees with the arbiter far below the 1e-8 gate; tests/test_predict_arbiter.py shows on the CPU that the
+    reference's dense formulation is the less accurate side when the two float64 results differ."""
+    from oracle import synth
+    from oracle.arbiter_mp import predict_arbiter
+    x, t = synth.geometry_1d(10, 14)
+    om = synth.model_1d(x, t, sig2n=1e-7)
+    lfp = synth.matched_lfp(om, 2, 5)
+    z = np.linspace(100.0, 2200.0, 5)[:, None]
+    eng, hp = engine_from_oracle(om, lfp)
+    out = eng.predict(hp, z, t, "csd")
+    arb = predict_arbiter(om, lfp, z, "csd")
+    for c in range(2):
+        err = relerr(out["csd_pred_list"][c], arb[c])
+        print("\n[predict vs 40-digit arbiter] component %d: %.2e" % (c, err))
+        assert err < 1e-10
