@@ -948,6 +948,40 @@ __global__ void __launch_bounds__(JAC_MAXN* JAC_MAXN / 2) jacobi_small_kernel(in
     V[r][c] = (r == c) ? 1.0 : 0.0;
   }
   __syncthreads();
+  if (!bad && n >= 4) {
+    // Pre-rotation by the orthonormal DCT-II basis C (C[i][k] = sqrt((k ? 2 : 1) / n) cos(pi (2i+1) k / (2n))): it nearly
+    // diagonalises the (near-)Toeplitz covariance factors this solver is fed, so Jacobi starts close to diagonal
+    // (5 sweeps instead of 9-12 on the GP spatial and temporal factors); for any other matrix it is a harmless orthogonal
+    // similarity.  A <- C^T A C, V <- C; T = A C goes through V's storage.
+    for (int e = tid; e < n * n; e += blockDim.x) {
+      const int i = e / n, c = e - i * n;
+      V[i][c] = sqrt((c ? 2.0 : 1.0) / n) * cospi((double)((2 * i + 1) * c) / (double)(2 * n));
+    }
+    __syncthreads();
+    double tacc[4];                                   // T[i][c] = sum_l A[i][l] C[l][c]; each thread owns <= 4 entries
+    int cnt = 0;
+    for (int e = tid; e < n * n; e += blockDim.x, ++cnt) {
+      const int i = e / n, c = e - i * n;
+      double a0 = 0.0;
+      for (int l = 0; l < n; ++l) a0 += A[i][l] * V[l][c];
+      tacc[cnt & 3] = a0;
+    }
+    __syncthreads();
+    cnt = 0;
+    for (int e = tid; e < n * n; e += blockDim.x, ++cnt) A[e / n][e % n] = tacc[cnt & 3];     // A now holds T
+    __syncthreads();
+    cnt = 0;
+    for (int e = tid; e < n * n; e += blockDim.x, ++cnt) {     // A' [i][c] = sum_l C[l][i] T[l][c]
+      const int i = e / n, c = e - i * n;
+      double a0 = 0.0;
+      for (int l = 0; l < n; ++l) a0 += V[l][i] * A[l][c];
+      tacc[cnt & 3] = a0;
+    }
+    __syncthreads();
+    cnt = 0;
+    for (int e = tid; e < n * n; e += blockDim.x, ++cnt) A[e / n][e % n] = tacc[cnt & 3];
+    __syncthreads();
+  }
   if (tid == 0) {                                    // scale of the matrix (fixed order: results are bit-reproducible)
     double mx = 0.0;
     for (int i = 0; i < n; ++i)
@@ -962,6 +996,7 @@ __global__ void __launch_bounds__(JAC_MAXN* JAC_MAXN / 2) jacobi_small_kernel(in
     return;
   }
   const double tiny = 2.7755575615628914e-17 * fro;     // eps/8 max|a_ij|: LAPACK-grade absolute accuracy, see the header comment
+  // (V starts as the pre-rotation C, or the identity for n < 4 / after the load loop above)
   // Round-robin pairing in closed form (circle method on np players, np even): in round r player np-1 meets player r, and for
   // k = 1..m-1 player (r + k) mod (np-1) meets player (r - k) mod (np-1) -- m disjoint pairs, every pair once per sweep.
   // Three barriers per round: rotation parameters | row update | column update.
@@ -985,17 +1020,21 @@ __global__ void __launch_bounds__(JAC_MAXN* JAC_MAXN / 2) jacobi_small_kernel(in
         double c = 1.0, sv = 0.0;
         if (q < n) {
           const double apq = 0.5 * (A[p][q] + A[q][p]), app = A[p][p], aqq = A[q][q];
-          const double thr = fmax(1.7763568394002505e-15 * sqrt(fabs(app * aqq)), tiny);     // 8 eps sqrt(|a_pp a_qq|)
-          if (fabs(apq) > thr) {
-            // symmetric Schur rotation: tau = (aqq - app) / (2 apq), t = sign(tau) / (|tau| + sqrt(1 + tau^2)),
-            // c = 1 / sqrt(1 + t^2), s = t c; reciprocal / rsqrt from single-precision seeds + Newton when in range
-            const double den = 2.0 * apq, ad = fabs(den);
-            const double rden = (ad > 1e-30 && ad < 1e30) ? copysign(refine_recip(ad, (double)__frcp_rn((float)ad)), den) : 1.0 / den;
-            const double tau = (aqq - app) * rden, at = fabs(tau);
-            const double u = 1.0 + tau * tau;
-            const double root = (u < 1e30) ? u * fast_rsqrt(u) : sqrt(u);
-            const double dd = at + root;                                   // >= 1
-            const double t = copysign((dd < 1e30) ? refine_recip(dd, (double)__frcp_rn((float)dd)) : 1.0 / dd, tau);
+          // rotate when |a_pq| > max(8 eps sqrt(|a_pp a_qq|), eps/8 max|a|), tested on squares (no sqrt on this chain)
+          if (apq * apq > fmax(3.1554436208840472e-30 * fabs(app * aqq), tiny * tiny)) {
+            // symmetric Schur rotation t = sign(D) 2 a_pq / (|D| + sqrt(D^2 + 4 a_pq^2)), D = a_qq - a_pp.  The angle is
+            // formed in single precision (this chain sits on the critical path of every round: ~40 dependent FP64
+            // operations otherwise); c = 1 / sqrt(1 + t^2), s = t c are then normalised in double, so the rotation is
+            // orthogonal to double precision whatever the angle -- an inexact angle only leaves a_pq reduced by ~1e-7
+            // instead of annihilated, which the next sweep finishes (the final sweeps see tiny angles anyway).
+            const double dl = aqq - app, ap2 = 2.0 * apq;
+            // common power-of-two scale (from the exponent bits of the larger magnitude) so the floats neither overflow nor flush
+            const double big = fmax(fabs(dl), fabs(ap2));                 // > 0 here
+            const int ex = ((__double2hiint(big) >> 20) & 0x7ff) - 1023;
+            const double sc2 = __hiloint2double((1023 - max(-1000, min(1000, ex))) << 20, 0);        // 2^-ex
+            const float df = (float)(dl * sc2), af = (float)(ap2 * sc2);
+            const float tf = copysignf(1.0f, df) * af / (fabsf(df) + sqrtf(df * df + af * af));
+            const double t = (double)tf;
             c = fast_rsqrt(1.0 + t * t);
             sv = t * c;
             rotated = 1;
@@ -1014,10 +1053,10 @@ __global__ void __launch_bounds__(JAC_MAXN* JAC_MAXN / 2) jacobi_small_kernel(in
         A[q][j] = sv * x + c * y;
       }
       __syncthreads();
-      if (act) {               // columns p, q of A (the annihilated pair is set to exactly zero) and of V
+      if (act) {               // columns p, q of A and of V
         const double x = A[j][p], y = A[j][q];
-        A[j][p] = (j == q) ? 0.0 : c * x - sv * y;
-        A[j][q] = (j == p) ? 0.0 : sv * x + c * y;
+        A[j][p] = c * x - sv * y;
+        A[j][q] = sv * x + c * y;
         const double u = V[j][p], w = V[j][q];
         V[j][p] = c * u - sv * w;
         V[j][q] = sv * u + c * w;
@@ -1129,10 +1168,9 @@ int gpcsd_eigh_dc(int n, int nmat, const double* M, long ldm, double* QT, long l
                   int* info, void* stream) {
   if (n < 1 || n > DC_MAXN) return gp_fail("gpcsd_eigh_dc: order must be in 1..256");
   cudaStream_t st = (cudaStream_t)stream;
-  // Orders <= 32: the Jacobi kernel (one CTA per matrix, ~240 us whatever the batch) when the cluster solver (8 SMs per
-  // matrix, ~155 us per wave of 18 matrices) would need more than one wave -- i.e. for restart batches; single models keep
-  // the lower latency of the cluster solver.  Orders 1 and 2 always go to Jacobi.
-  if (n <= JAC_MAXN && (n < 3 || (long)nmat * TRD_CLUSTER > gp_num_sms())) {
+  // Orders <= 32: the Jacobi kernel -- one CTA per matrix, ~80 us (n = 24) to ~125 us (n = 32) WHATEVER the batch, against
+  // ~140-155 us per wave of 18 matrices for the cluster solver below (8 SMs per matrix; profiles/r02i_small_eigh.md).
+  if (n <= JAC_MAXN) {
     if (nmat <= 0) return 0;
     const int m = (n + 1) / 2;
     jacobi_small_kernel<<<nmat, m * 2 * m, 0, st>>>(n, M, ldm, QT, ldq, W, info);
