@@ -28,6 +28,7 @@
 #include <stddef.h>
 
 #include <mutex>
+#include <type_traits>
 #include <unordered_map>
 
 #include "common.h"
@@ -102,12 +103,18 @@ __device__ long long g_eig_trace[8 * 16 * 12];
 #endif
 
 struct TridiagSmem {
-  double p[2][TRD_MAXN];          // tau * A22 * v of one column, all-gathered (every row warp stores its entries into every CTA)
-  double rowb[2][TRD_MAXN];       // row k+1 of the matrix as it stands BEFORE reflector k is applied (stored by its owner)
+  double2 pc[2][TRD_MAXN];        // the per-column exchange, by parity: .x = p_i = tau * (A v)_i of the column just built,
+                                  // .y = a_{i,k+1}, row i's element of the NEXT pivot column (every row warp stores its pair into every CTA)
   double vs[TRD_WARPS][TRD_MAXN]; // per-warp private copy of the current reflector (single-element reads without shuffles)
-  double stage[2][TRD_MAXN];      // source of the owner's bulk row copies (by slot parity)
-  uint64_t bar[2];                // transaction barriers of the per-column exchange, by exchange parity
+  uint64_t bar[2];                // transaction barriers of the exchange, by parity
 };
+
+// 16-byte remote store that also signals 16 transaction bytes on an mbarrier of the same remote CTA
+__device__ __forceinline__ void dsmem_store2_signal(uint32_t addr, double v0, double v1, uint32_t mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];\n" ::"r"(addr), "d"(v0),
+               "d"(v1), "r"(mbar)
+               : "memory");
+}
 
 // 1/sqrt(s) and 1/x to full double precision from the single-precision hardware approximations plus two Newton steps: the
 // library sqrt and division are ~30 dependent FP64 instructions each (~1000 cycles for sqrt + div on this part, measured
@@ -125,25 +132,47 @@ __device__ __forceinline__ double refine_recip(double x, double y0) {
   return fma(y0 * r, 1.0 + r, y0);                    // y (1 + r + r^2)
 }
 
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, N>(f);
+  }
+}
+
 // Register-resident, single-exchange Householder tridiagonalisation.  grid = 8 * nmat CTAs, cluster (8,1,1), up to 16 warps
 // per CTA.  Every matrix row lives in the REGISTERS of one warp (slot s = i / 8 belongs to warp s % 16 of CTA i % 8; lane l
 // holds columns l, l+32, ...; both triangles are kept current), so the symv p = tau A v and the rank-2 update
 // A -= v w^T + w v^T never touch shared memory for the matrix.
 //
 // The classical algorithm needs two cluster-wide exchanges per column (broadcast the reflector, all-gather p).  Here there
-// is ONE: exchange k+1 carries every p_i of column k AND the not-yet-updated row k+1 of its owner.  After receiving it every
-// warp redundantly (and bit-identically) finishes column k (w = p - tau/2 (p.v) v), applies that rank-2 update to the
-// received row to obtain column k+1 of the current matrix, builds reflector k+1 from it, updates its own rows and computes
-// its p_i for column k+1.  Exchanges are st.async stores that complete transaction bytes on an mbarrier of the receiving
-// CTA (double buffered by parity): no cluster barrier (it costs a MEMBAR.ALL.GPU that also waits for the reflector stores
-// to global memory), no fence, no CTA-wide barrier, no shared-memory reduction -- the per-column critical path is three
-// warp reductions, one rsqrt, one reciprocal and one distributed-shared-memory latency.  A CTA cannot run more than one
-// exchange ahead of the slowest one because every p_i of exchange k+1 needs all of exchange k.
+// is ONE, and no warp is special in it: with its p_i of column k every row warp also sends a_{i,k+1}, its element of the
+// next pivot column (= row k+1 by symmetry), so that after the exchange every warp holds p AND the next pivot row and
+// redundantly (bit-identically) finishes column k (w = p - tau/2 (p.v) v), applies that rank-2 update to the received row
+// to obtain column k+1 of the current matrix and builds reflector k+1 from it.  Per column:
+//     wait -> p.v (warp reduction) -> x -> { |x|^2, A x, w.x, v.x } (ONE merged warp reduction) -> rsqrt/reciprocal -> send:
+//  * the symv runs on the UNNORMALISED pivot column x (A v = a_{:,k+1} + scal * A x_tail), so it shares the reduction
+//    with the norm instead of waiting for the reflector;
+//  * it runs on the rows as they stand BEFORE the previous reflector's update (A' x = A x - v (w.x) - w (v.x), two more sums
+//    in the same reduction); that rank-2 update of the own rows, the normalised reflector and its store to global memory
+//    are done AFTER the send, under the latency of the exchange.
+// With 16 warps per SM executing this in lock step the loop is bound by instruction ISSUE (4 warps per scheduler), not by
+// latency (clock64 trace: every phase advances at the same pace in all warps), so the body is specialised at compile time
+// on NR = ceil(n / 32) register blocks per row and on M0 = k / 32, the first live block: no per-block predicates, no work
+// on dead blocks; only blocks M0 and M0+1 carry lane masks.  Out-of-range columns (j >= n) need no masks either: the rows
+// and the exchange buffers are zero there and stay zero.
+// Exchanges are st.async stores that complete transaction bytes on an mbarrier of the receiving CTA (double buffered by
+// parity): no cluster barrier (it costs a MEMBAR.ALL.GPU that also waits for the reflector stores to global memory), no
+// fence, no CTA-wide barrier, no shared-memory reduction.  A CTA cannot run more than one exchange ahead of the slowest one
+// because every p_i of exchange k+1 needs all of exchange k.
 // M: [nmat][n][ldm] symmetric.  Out: d[nmat][n], e[nmat][n] (e[k] = T[k+1][k]), V[nmat][n][ldv] (row k holds reflector k:
 // V[k][j] for j > k+1, implicit 1 at j = k+1), tau[nmat][n].
+template <int NR>
 __global__ void __cluster_dims__(TRD_CLUSTER, 1, 1) __launch_bounds__(32 * TRD_WARPS, 1)
     tridiag_cluster_kernel(int n, const double* __restrict__ M, long ldm, double* __restrict__ d, double* __restrict__ e,
                            double* __restrict__ V, long ldv, double* __restrict__ tau) {
+  static_assert(TRD_RPW == 2, "the send below maps lanes 0-7 / 8-15 to the two row slots of a warp");
+  constexpr int RPW = NR > TRD_NR / 2 ? 2 : 1;       // n <= 128: the second row slot of every warp is empty
   __shared__ __align__(16) TridiagSmem S;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
@@ -155,13 +184,13 @@ __global__ void __cluster_dims__(TRD_CLUSTER, 1, 1) __launch_bounds__(32 * TRD_W
   tau += (long)mat * n;
   V += (long)mat * n * ldv;
 
-  int row[TRD_RPW];
-  double a[TRD_RPW][TRD_NR];
+  int row[RPW];
+  double a[RPW][NR];
 #pragma unroll
-  for (int q = 0; q < TRD_RPW; ++q) {
+  for (int q = 0; q < RPW; ++q) {
     row[q] = rank + (warp + q * TRD_WARPS) * TRD_CLUSTER;
 #pragma unroll
-    for (int m = 0; m < TRD_NR; ++m) {
+    for (int m = 0; m < NR; ++m) {
       const int j = lane + 32 * m;
       a[q][m] = (row[q] < n && j < n) ? M[(long)row[q] * ldm + j] : 0.0;
     }
@@ -169,7 +198,7 @@ __global__ void __cluster_dims__(TRD_CLUSTER, 1, 1) __launch_bounds__(32 * TRD_W
   double* vs = S.vs[warp];
 #pragma unroll
   for (int m = 0; m < TRD_NR; ++m) vs[lane + 32 * m] = 0.0;
-  const int peer_rank = lane & (TRD_CLUSTER - 1);
+  for (int i = threadIdx.x; i < 2 * TRD_MAXN; i += blockDim.x) (&S.pc[0][0])[i] = make_double2(0.0, 0.0);
   if (threadIdx.x == 0) {
     mbar_init(&S.bar[0], 1);
     mbar_init(&S.bar[1], 1);
@@ -177,185 +206,217 @@ __global__ void __cluster_dims__(TRD_CLUSTER, 1, 1) __launch_bounds__(32 * TRD_W
   }
   cluster.sync();                       // every CTA's shared memory and barriers are live before remote stores
 
-  // the owner of row r ships entries j >= (r & ~1) of that row into rowb[pb] of every CTA (signalling bar[pb]): registers ->
-  // own shared memory -> one bulk copy per peer
-  auto send_row = [&](const double (&x)[TRD_NR], int r, int pb) {
-    double* stg = S.stage[(r >> 3) & 1];
-#pragma unroll
-    for (int m = 0; m < TRD_NR; ++m) stg[lane + 32 * m] = x[m];
-    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-    __syncwarp();
-    const int j0 = r & ~1;
-    const uint32_t bytes = 8u * (uint32_t)(((n + 1) & ~1) - j0);
-    if (lane < TRD_CLUSTER)
-      dsmem_bulk_copy(dsmem_addr(&S.rowb[pb][j0], lane), smem_addr(stg + j0), bytes, dsmem_addr(&S.bar[pb], lane));
-  };
+  // lanes 0-7 send the pair of row slot 0 to CTAs 0-7, lanes 8-15 the pair of row slot 1
+  const int peer_rank = lane & (TRD_CLUSTER - 1);
+  const int send_row = (lane < TRD_CLUSTER) ? row[0] : ((RPW > 1 && lane < 2 * TRD_CLUSTER) ? row[RPW - 1] : TRD_MAXN);
+  // (the peer's TridiagSmem sits at the same offset of its shared-memory window: one mapa, constant offsets)
+  const uint32_t remote = dsmem_addr(&S, peer_rank) + 16u * (uint32_t)send_row;
+  const uint32_t remote_bar = dsmem_addr(&S.bar[0], peer_rank);
+  constexpr uint32_t PC1 = (uint32_t)sizeof(double2) * TRD_MAXN;
 
   // A warp takes part in column k while it owns a row >= k; afterwards it leaves the loop (it would neither send nor be
   // waited for).  The warp that owns the CTA's LAST row stays longest and arms the CTA's barriers.
   int last_row = -1;
 #pragma unroll
-  for (int q = 0; q < TRD_RPW; ++q)
+  for (int q = 0; q < RPW; ++q)
     if (row[q] < n) last_row = row[q];
   const bool armer = lane == 0 && last_row >= 0 && last_row + TRD_CLUSTER >= n;
 
-  // exchange 0: row 0 only
-  if (armer) mbar_expect_tx(&S.bar[0], 8u * (uint32_t)((n + 1) & ~1));
-#pragma unroll
-  for (int q = 0; q < TRD_RPW; ++q)
-    if (row[q] == 0) send_row(a[q], 0, 0);
+  // exchange 0: column 0 of every row (p = 0)
+  if (armer) mbar_expect_tx(&S.bar[0], 16u * (uint32_t)n);
+  {
+    double e0 = __shfl_sync(0xffffffffu, a[0][0], 0);
+    if (RPW > 1) {
+      const double e1 = __shfl_sync(0xffffffffu, a[RPW - 1][0], 0);
+      if (lane >= TRD_CLUSTER) e0 = e1;
+    }
+    if (send_row < n) dsmem_store2_signal(remote, 0.0, e0, remote_bar);
+  }
 
-  double vprev[TRD_NR];                 // reflector k-1 (zero before the first column)
+  double vprev[NR];                     // reflector k-1 (zero before the first column)
 #pragma unroll
-  for (int m = 0; m < TRD_NR; ++m) vprev[m] = 0.0;
+  for (int m = 0; m < NR; ++m) vprev[m] = 0.0;
   double tprev = 0.0;
+  bool live = true;
+  int k = 0;
 
   EIG_PROF_DECL
-  for (int k = 0; k <= n - 2; ++k) {    // k = n-2: only finishes column n-3
+  // one column, specialised on the first live register block M0 = k / 32; returns false when this warp is done
+  auto column = [&](auto M0c) -> bool {
+    constexpr int M0 = decltype(M0c)::value;
+    constexpr bool HAS1 = M0 + 1 < NR;  // block M0+1 exists
     EIG_PROF(0)
     const int pb = k & 1;               // exchange k: p of column k-1 and row k
-    const bool build = k < n - 2;
+    const bool build = k < n - 2;       // k = n-2: only finishes column n-3
     // (a warp whose last row is exactly k has nothing left to send either -- nobody waits for it, so it must not wait on
     //  barriers that may run ahead of it; the owner of row n-2 stays for the final update, after which nothing runs ahead)
-    if (last_row < k || (last_row == k && k < n - 2)) break;
-    if (armer && build)                 // arm exchange k+1: p of column k (rows i > k) and row k+1 (entries j >= k+1)
-      mbar_expect_tx(&S.bar[pb ^ 1], 8u * (uint32_t)(n - k - 1) +
-                                         ((k + 1 < n - 2) ? 8u * (uint32_t)(((n + 1) & ~1) - ((k + 1) & ~1)) : 0u));
-    const int m0 = k >> 5;              // lane blocks below m0 only hold columns < k: nothing to do there
+    if (last_row < k || (last_row == k && build)) return false;
+    if (armer && build) mbar_expect_tx(&S.bar[pb ^ 1], 16u * (uint32_t)(n - k - 1));     // exchange k+1: rows i > k
+    const int kl = k & 31;
+    const bool wrap = kl == 31;         // column k+1 is lane 0 of block M0+1
+    const int l1 = (kl + 1) & 31;       // lane of column k+1
     mbar_wait_cluster(&S.bar[pb], (uint32_t)((k >> 1) & 1));
     EIG_PROF(1)
-    // ---- finish column k-1: w = p - (tau/2)(p.v) v
-    double w[TRD_NR];
+    // ---- finish column k-1: w = p - (tau/2)(p.v) v   (k = 0: p = v = 0; v^{k-1}_j = 0 for j < k, 1 at j = k)
+    double w[NR], x[NR];
     double pv0 = 0.0, pv1 = 0.0;
 #pragma unroll
-    for (int m = 0; m < TRD_NR; ++m) {
-      const int j = lane + 32 * m;
-      w[m] = (m >= m0 && k > 0 && j >= k && j < n) ? S.p[pb][j] : 0.0;
-      if (m & 1) pv1 += w[m] * vprev[m]; else pv0 += w[m] * vprev[m];
+    for (int m = M0; m < NR; ++m) {
+      const double2 t2 = S.pc[pb][lane + 32 * m];
+      w[m] = t2.x;
+      x[m] = t2.y;
+    }
+    if (lane < kl) w[M0] = 0.0;         // rows < k are finished: their p is stale
+#pragma unroll
+    for (int m = M0; m < NR; ++m) {
+      if ((m - M0) & 1) pv1 += w[m] * vprev[m]; else pv0 += w[m] * vprev[m];
     }
     const double pv = pv0 + pv1;
-    const double pk = (k > 0) ? S.p[pb][k] : 0.0;            // p_k, r_k, r_{k+1}: uniform loads
-    const double rk = S.rowb[pb][k], rk1 = S.rowb[pb][k + 1];
+    const double2 ek = S.pc[pb][k], ek1 = S.pc[pb][k + 1];   // (p_k, r_k), (p_{k+1}, r_{k+1}): uniform loads
     const double vk1 = vs[k + 1];                            // v^{k-1}_{k+1}
-    double vi[TRD_RPW], pi[TRD_RPW];
+    double vi[RPW], wi[RPW], ae[RPW];
+    bool act[RPW];
 #pragma unroll
-    for (int q = 0; q < TRD_RPW; ++q) {
-      const int r = (row[q] < n) ? row[q] : 0;
+    for (int q = 0; q < RPW; ++q) {
+      act[q] = row[q] >= k && row[q] < n;                    // warp-uniform
+      const int r = act[q] ? row[q] : k;
       vi[q] = vs[r];
-      pi[q] = (k > 0) ? S.p[pb][r] : 0.0;
+      wi[q] = S.pc[pb][r].x;                                 // p_i for now
+      // a_{i,k+1} of the own rows (as the registers hold them: before the update by reflector k-1)
+      double sel = a[q][M0];
+      if (HAS1 && wrap) sel = a[q][HAS1 ? M0 + 1 : M0];
+      ae[q] = __shfl_sync(0xffffffffu, sel, l1);
     }
     const double c = 0.5 * tprev * warp_sum(pv);
     EIG_PROF(2)
 #pragma unroll
-    for (int m = 0; m < TRD_NR; ++m)
-      if (m >= m0) w[m] -= c * vprev[m];
-    // ---- apply it to the own rows (rows i >= k; rows below are final)
+    for (int m = M0; m < NR; ++m) w[m] -= c * vprev[m];
 #pragma unroll
-    for (int q = 0; q < TRD_RPW; ++q) {
-      if (k > 0 && row[q] >= k && row[q] < n) {
-        const double wi = pi[q] - c * vi[q];
+    for (int q = 0; q < RPW; ++q) wi[q] -= c * vi[q];
+    if (!build) {                       // last pass: only the update of rows n-2, n-1 by reflector n-3 is left
 #pragma unroll
-        for (int m = 0; m < TRD_NR; ++m)
-          if (m >= m0) a[q][m] -= vi[q] * w[m] + wi * vprev[m];
-      }
+      for (int q = 0; q < RPW; ++q)
+        if (act[q]) {
+#pragma unroll
+          for (int m = M0; m < NR; ++m) a[q][m] = fma(-wi[q], vprev[m], fma(-vi[q], w[m], a[q][m]));
+        }
+      return false;
     }
-    if (!build) break;
-    EIG_PROF(3)
-    // ---- the owner of row k+1 ships it (as it stands now, before reflector k) with the next exchange
-    if (k + 1 < n - 2) {
+    // ---- row k of the current matrix (== column k), rebuilt from the received elements; v^{k-1}_k = 1, so
+    //      x_j = r_j - w_j - w_k v_j with w_k = p_k - c
+    const double wk = ek.x - c, wk1 = ek1.x - c * vk1;
+    const double akk = ek.y - 2.0 * wk;
+    const double alpha = ek1.y - wk1 - wk * vk1;
 #pragma unroll
-      for (int q = 0; q < TRD_RPW; ++q)
-        if (row[q] == k + 1) send_row(a[q], k + 1, pb ^ 1);
+    for (int m = M0; m < NR; ++m) x[m] = (x[m] - w[m]) - wk * vprev[m];
+    if (lane <= kl + 1) x[M0] = 0.0;    // columns <= k+1
+    if (HAS1 && wrap && lane == 0) x[HAS1 ? M0 + 1 : M0] = 0.0;
+    double ss = 0.0, wx = 0.0, vx = 0.0, sx[RPW];
+#pragma unroll
+    for (int q = 0; q < RPW; ++q) sx[q] = 0.0;
+#pragma unroll
+    for (int m = M0; m < NR; ++m) {
+      ss += x[m] * x[m];
+      wx += w[m] * x[m];
+      vx += vprev[m] * x[m];
+#pragma unroll
+      for (int q = 0; q < RPW; ++q) sx[q] += a[q][m] * x[m];
+    }
+    EIG_PROF(3)
+    // ---- ONE reduction for the norm, the two correction sums and the row sums of A x
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      wx += __shfl_xor_sync(0xffffffffu, wx, o);
+      vx += __shfl_xor_sync(0xffffffffu, vx, o);
+#pragma unroll
+      for (int q = 0; q < RPW; ++q) sx[q] += __shfl_xor_sync(0xffffffffu, sx[q], o);
     }
     EIG_PROF(4)
-    // ---- row k of the current matrix (== column k), rebuilt from the received pre-update row; reflector k.
-    //      v^{k-1}_k = 1 (0 before the first column), so x_j = r_j - vk w_j - wk v_j with wk = p_k - c vk.
+    const double xnorm2 = ss;
+    double t = 0.0, beta = alpha, scal = 0.0;
+    if (xnorm2 > 0.0) {
+      const double s2 = alpha * alpha + xnorm2, aa = fabs(alpha);
+      const double rn = fast_rsqrt(s2);                    // 1 / |beta|
+      const double ab = s2 * rn;                           // |beta|
+      beta = -copysign(ab, alpha);
+      t = 1.0 + aa * rn;                                   // (beta - alpha) / beta
+      const double den = aa + ab;                          // |alpha - beta|
+      double rden;
+      if (s2 > 1e-30 && s2 < 1e30) {                       // single-precision seed computed off the critical path
+        const float sf = (float)s2;
+        rden = refine_recip(den, (double)__frcp_rn((float)aa + sqrtf(sf)));
+      } else {
+        rden = 1.0 / den;
+      }
+      scal = copysign(rden, alpha);                        // 1 / (alpha - beta)
+    }
+    EIG_PROF(5)
+    // ---- p_i = tau (A' v)_i, A' = the rows after the update by reflector k-1, v = (1, scal * x_tail):
+    //      a'_{i,k+1} + scal * ((A x)_i - v_i (w.x) - w_i (v.x)); sent with a'_{i,k+1} (row k+1 of the next exchange)
     {
-      const double vk = (k > 0) ? 1.0 : 0.0, wk = pk - c * vk;
-      const double akk = rk - 2.0 * vk * wk;
-      const double alpha = rk1 - vk * ((k > 0 ? S.p[pb][k + 1] : 0.0) - c * vk1) - wk * vk1;
-      double x[TRD_NR];
-      double ss0 = 0.0, ss1 = 0.0;
+      double pn[RPW], an[RPW];
 #pragma unroll
-      for (int m = 0; m < TRD_NR; ++m) {
-        const int j = lane + 32 * m;
-        x[m] = (m >= m0 && j > k + 1 && j < n) ? S.rowb[pb][j] - vk * w[m] - wk * vprev[m] : 0.0;
-        if (m & 1) ss1 += x[m] * x[m]; else ss0 += x[m] * x[m];
+      for (int q = 0; q < RPW; ++q) {
+        an[q] = ae[q] - (vi[q] * wk1 + wi[q] * vk1);
+        pn[q] = t * (an[q] + scal * ((sx[q] - vi[q] * wx) - wi[q] * vx));
       }
-      const double xnorm2 = warp_sum(ss0 + ss1);
-      EIG_PROF(5)
-      double t = 0.0, beta = alpha, scal = 0.0;
-      if (xnorm2 > 0.0) {
-        const double s2 = alpha * alpha + xnorm2, aa = fabs(alpha);
-        const double rn = fast_rsqrt(s2);                    // 1 / |beta|
-        const double ab = s2 * rn;                           // |beta|
-        beta = -copysign(ab, alpha);
-        t = 1.0 + aa * rn;                                   // (beta - alpha) / beta
-        const double den = aa + ab;                          // |alpha - beta|
-        double rden;
-        if (s2 > 1e-30 && s2 < 1e30) {                       // single-precision seed computed off the critical path
-          const float sf = (float)s2;
-          rden = refine_recip(den, (double)__frcp_rn((float)aa + sqrtf(sf)));
-        } else {
-          rden = 1.0 / den;
-        }
-        scal = copysign(rden, alpha);                        // 1 / (alpha - beta)
+      if (RPW > 1 && lane >= TRD_CLUSTER) {
+        pn[0] = pn[RPW - 1];
+        an[0] = an[RPW - 1];
       }
+      if (send_row > k && send_row < n) dsmem_store2_signal(remote + (pb ? 0u : PC1), pn[0], an[0], remote_bar + (pb ? 0u : 8u));
+    }
+    EIG_PROF(6)
+    // ---- under the latency of the exchange: the own rows catch up with reflector k-1 ...
+    if (k > 0) {
 #pragma unroll
-      for (int m = 0; m < TRD_NR; ++m) {
-        const int j = lane + 32 * m;
-        vprev[m] = (j == k + 1) ? 1.0 : x[m] * scal;
-        vs[j] = vprev[m];
-      }
-      tprev = t;
-      EIG_PROF(6)
-      if (row[0] == k + 1 || row[TRD_RPW - 1] == k + 1) {     // one warp of the cluster (an active one) records the column
+      for (int q = 0; q < RPW; ++q) {
+        if (act[q]) {
 #pragma unroll
-        for (int m = 0; m < TRD_NR; ++m) {
-          const int j = lane + 32 * m;
-          if (j > k + 1 && j < n) V[(long)k * ldv + j] = vprev[m];
-        }
-        if (lane == 0) {
-          d[k] = akk;
-          e[k] = beta;
-          tau[k] = t;
+          for (int m = M0; m < NR; ++m) a[q][m] = fma(-wi[q], vprev[m], fma(-vi[q], w[m], a[q][m]));
         }
       }
     }
     EIG_PROF(7)
-    // ---- p_i = tau * sum_j A_ij v_j for the own rows i > k, stored into every CTA
-    double acc[TRD_RPW], acc1[TRD_RPW];
+    // ---- ... and reflector k is normalised, kept (registers + the warp's shared-memory copy) and recorded
 #pragma unroll
-    for (int q = 0; q < TRD_RPW; ++q) acc[q] = acc1[q] = 0.0;
+    for (int m = M0; m < NR; ++m) vprev[m] = x[m] * scal;
+    if (lane == l1) {
+      if (HAS1 && wrap) vprev[HAS1 ? M0 + 1 : M0] = 1.0; else vprev[M0] = 1.0;
+    }
 #pragma unroll
-    for (int m = 0; m < TRD_NR; ++m)
-      if (m >= m0) {
+    for (int m = M0; m < NR; ++m) vs[lane + 32 * m] = vprev[m];
+    tprev = t;
+    if (row[0] == k + 1 || row[RPW - 1] == k + 1) {         // one warp of the cluster (an active one) records the column
 #pragma unroll
-        for (int q = 0; q < TRD_RPW; ++q) {
-          if (m & 1) acc1[q] += a[q][m] * vprev[m]; else acc[q] += a[q][m] * vprev[m];
-        }
+      for (int m = M0; m < NR; ++m) {
+        const int j = lane + 32 * m;
+        if (j > k + 1 && j < n) V[(long)k * ldv + j] = vprev[m];
       }
-#pragma unroll
-    for (int q = 0; q < TRD_RPW; ++q) acc[q] += acc1[q];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-      for (int q = 0; q < TRD_RPW; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
-#pragma unroll
-    for (int q = 0; q < TRD_RPW; ++q)
-      if (row[q] > k && row[q] < n && lane < TRD_CLUSTER)
-        dsmem_store_signal(dsmem_addr(&S.p[pb ^ 1][row[q]], peer_rank), acc[q] * tprev, dsmem_addr(&S.bar[pb ^ 1], peer_rank));
+      if (lane == 0) {
+        d[k] = akk;
+        e[k] = beta;
+        tau[k] = t;
+      }
+    }
     EIG_PROF(8)
     __syncwarp();     // vs[] written above is read (by other lanes of this warp) in the next column
-  }
+    return true;
+  };
+  static_for<0, NR>([&](auto M0c) {
+    constexpr int M0 = decltype(M0c)::value;
+    const int kend = min(32 * (M0 + 1), n - 1);            // columns k = 0 .. n-2
+    for (; live && k < kend; ++k) live = column(M0c);
+  });
   EIG_PROF_DUMP(last_row == n - 1, 9)
   // last 2x2 block (rows n-2 and n-1 are final now)
 #pragma unroll
-  for (int q = 0; q < TRD_RPW; ++q) {
+  for (int q = 0; q < RPW; ++q) {
     if (row[q] == n - 2 || row[q] == n - 1) {
       double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-      for (int m = 0; m < TRD_NR; ++m) {
+      for (int m = 0; m < NR; ++m) {
         if (lane + 32 * m == row[q]) s0 = a[q][m];
         if (lane + 32 * m == n - 1) s1 = a[q][m];
       }
@@ -1111,7 +1172,14 @@ int gpcsd_tridiag(int n, int nmat, const double* M, long ldm, double* d, double*
   if (n < 3 || n > TRD_MAXN) return gp_fail("gpcsd_tridiag: order must be in 3..256");
   const int slots = (n + TRD_CLUSTER - 1) / TRD_CLUSTER;               // rows per CTA
   const int threads = 32 * (slots < TRD_WARPS ? slots : TRD_WARPS);
-  tridiag_cluster_kernel<<<TRD_CLUSTER * nmat, threads, 0, (cudaStream_t)stream>>>(n, M, ldm, d, e, V, ldv, tau);
+  const int grid = TRD_CLUSTER * nmat;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nr = (n + 31) / 32;                                        // register blocks per row (compile-time specialisation)
+  if (nr <= 1) tridiag_cluster_kernel<1><<<grid, threads, 0, st>>>(n, M, ldm, d, e, V, ldv, tau);
+  else if (nr <= 2) tridiag_cluster_kernel<2><<<grid, threads, 0, st>>>(n, M, ldm, d, e, V, ldv, tau);
+  else if (nr <= 4) tridiag_cluster_kernel<4><<<grid, threads, 0, st>>>(n, M, ldm, d, e, V, ldv, tau);
+  else if (nr <= 6) tridiag_cluster_kernel<6><<<grid, threads, 0, st>>>(n, M, ldm, d, e, V, ldv, tau);
+  else tridiag_cluster_kernel<8><<<grid, threads, 0, st>>>(n, M, ldm, d, e, V, ldv, tau);
   GP_CUDA(cudaGetLastError());
   return 0;
 }

@@ -4,7 +4,7 @@ import numpy as np, torch
 from gpcsd_b200 import _lib as L
 lib = L.load()
 st = torch.cuda.current_stream().cuda_stream
-names = ["looptop", "wait", "pv-sum", "update", "rowsend", "x+ss-sum", "rsqrt+v", "record", "symv+send"]
+names = ["looptop", "wait", "pv-sum", "x+partials", "merged-reduce", "scalars", "p+send", "deferred-update", "reflector+record"]
 for n in (24, 125, 250):
     ld = n + (n&1); nmat = 1
     A = torch.randn(nmat,n,n,dtype=torch.float64,device="cuda"); A = A + A.transpose(1,2)

@@ -3,7 +3,7 @@ import numpy as np, torch
 from gpcsd_b200 import _lib as L
 lib = L.load()
 st = torch.cuda.current_stream().cuda_stream
-names = ["top", "wait", "pvsum", "upd", "rsend", "x+ss", "rsqrt", "rec", "symv"]
+names = ["top", "wait", "pvsum", "x+part", "reduce", "scalars", "send", "update", "reflect"]
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 24
 ld = n + (n&1); nmat = 1
 A = torch.randn(nmat,n,n,dtype=torch.float64,device="cuda"); A = A + A.transpose(1,2)

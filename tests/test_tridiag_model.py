@@ -1,8 +1,10 @@
 """CPU model of the single-exchange Householder tridiagonalisation implemented by tridiag_cluster_kernel
-(gpcsd_b200/csrc/gpcsd_eig.cu): per column, every participant receives p of the previous column and the owner's row as it
-stood BEFORE the previous reflector was applied, finishes the previous column (w = p - tau/2 (p.v) v), rebuilds the current
-row from the received one, builds the reflector with the kernel's formulas (1 + |alpha|/|beta|, sign(alpha)/(|alpha|+|beta|)),
-and only then updates its own rows.  The test pins that algebra against LAPACK."""
+(gpcsd_b200/csrc/gpcsd_eig.cu).  Per column every row owner sends the pair (p_i of the column just built, a_{i,k+1} = its
+element of the NEXT pivot column); every participant then finishes the previous column (w = p - tau/2 (p.v) v), rebuilds
+the current pivot row from the received elements, and builds the reflector with the kernel's formulas
+(1 + |alpha|/|beta|, sign(alpha)/(|alpha|+|beta|)).  The symv runs on the UNNORMALISED pivot column and on rows that have
+not yet been updated by the previous reflector (A' x = A x - v (w.x) - w (v.x)); the own rows catch up after the send.
+The test pins that algebra against LAPACK."""
 import numpy as np
 import pytest
 import scipy.linalg
@@ -10,42 +12,46 @@ import scipy.linalg
 
 def tridiag_single_exchange(M):
     n = M.shape[0]
-    A = M.copy()                      # rows as the owning warps hold them (updated lazily, one column behind)
+    A = M.copy()                      # rows as the owning warps hold them (updated lazily: one reflector behind at the symv)
     d, e, tau = np.zeros(n), np.zeros(n), np.zeros(n)
     V = np.zeros((n, n))
-    vprev, tprev, p_prev = np.zeros(n), 0.0, np.zeros(n)
-    rowb = A[0].copy()                # exchange 0: row 0
+    vprev, tprev = np.zeros(n), 0.0
+    p_recv, r_recv = np.zeros(n), A[:, 0].copy()      # exchange 0: column 0 of every row, p = 0
     for k in range(n - 1):
-        # finish column k-1
-        c = 0.5 * tprev * float(p_prev @ vprev)
-        w = p_prev - c * vprev
-        if k > 0:
-            A[k:] -= np.outer(vprev[k:], w) + np.outer(w[k:], vprev)         # own rows i >= k
+        # finish column k-1 (v^{k-1}_k = 1)
+        c = 0.5 * tprev * float(p_recv[k:] @ vprev[k:])
+        w = np.zeros(n)
+        w[k:] = p_recv[k:] - c * vprev[k:]
+        vi, wi = vprev.copy(), p_recv - c * vprev      # per own row i: v_i, w_i
         if k == n - 2:
+            A[k:] -= np.outer(vi[k:], w) + np.outer(wi[k:], vprev)
             break
-        row_next = A[k + 1].copy()    # shipped with the next exchange: row k+1 BEFORE reflector k
-        # row k of the current matrix rebuilt from the received pre-update row
-        vk = 1.0 if k > 0 else 0.0
-        wk = (p_prev[k] if k > 0 else 0.0) - c * vk
-        x = rowb - vk * w - wk * vprev
-        d[k] = rowb[k] - 2.0 * vk * wk
-        alpha = x[k + 1]
-        xnorm2 = float(x[k + 2:] @ x[k + 2:])
-        v = np.zeros(n)
-        v[k + 1] = 1.0
-        t, beta = 0.0, alpha
+        wk, wk1, vk1 = p_recv[k] - c, p_recv[k + 1] - c * vprev[k + 1], vprev[k + 1]
+        d[k] = r_recv[k] - 2.0 * wk
+        alpha = r_recv[k + 1] - wk1 - wk * vk1
+        x = np.zeros(n)
+        x[k + 2:] = (r_recv[k + 2:] - w[k + 2:]) - wk * vprev[k + 2:]
+        xnorm2, wx, vx = float(x @ x), float(w @ x), float(vprev @ x)
+        sx = A @ x                    # rows as held: BEFORE the update by reflector k-1
+        t, beta, scal = 0.0, alpha, 0.0
         if xnorm2 > 0.0:
             s2 = alpha * alpha + xnorm2
             rn = 1.0 / np.sqrt(s2)
             ab = s2 * rn
             beta = -np.copysign(ab, alpha)
             t = 1.0 + abs(alpha) * rn
-            v[k + 2:] = x[k + 2:] * np.copysign(1.0 / (abs(alpha) + ab), alpha)
+            scal = np.copysign(1.0 / (abs(alpha) + ab), alpha)
+        an = A[:, k + 1] - (vi * wk1 + wi * vk1)       # a'_{i,k+1}: next pivot column after reflector k-1
+        pn = t * (an + scal * ((sx - vi * wx) - wi * vx))
+        p_next, r_next = np.zeros(n), np.zeros(n)
+        p_next[k + 1:], r_next[k + 1:] = pn[k + 1:], an[k + 1:]          # rows i > k send
+        # after the send: own rows catch up with reflector k-1; reflector k is normalised and recorded
+        if k > 0:
+            A[k:] -= np.outer(vi[k:], w) + np.outer(wi[k:], vprev)
+        v = x * scal
+        v[k + 1] = 1.0
         e[k], tau[k], V[k] = beta, t, v
-        # symv on the own rows i > k
-        p = np.zeros(n)
-        p[k + 1:] = t * (A[k + 1:] @ v)
-        vprev, tprev, p_prev, rowb = v, t, p, row_next
+        vprev, tprev, p_recv, r_recv = v, t, p_next, r_next
     d[n - 2], e[n - 2], d[n - 1] = A[n - 2, n - 2], A[n - 2, n - 1], A[n - 1, n - 1]
     return d, e, V, tau
 
