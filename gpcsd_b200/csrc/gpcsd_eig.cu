@@ -82,8 +82,8 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
 
 constexpr int TRD_CLUSTER = 8;        // CTAs per matrix
 constexpr int TRD_MAXN = 256;
-constexpr int TRD_WARPS = 16;                      // warps per CTA
-constexpr int TRD_RPW = TRD_MAXN / (TRD_CLUSTER * TRD_WARPS);   // rows per warp (2): row i lives in CTA i % 8, slot i / 8
+constexpr int TRD_WARPS = 8;                       // warps per CTA
+constexpr int TRD_RPW = TRD_MAXN / (TRD_CLUSTER * TRD_WARPS);   // rows per warp (up to 4): row i lives in CTA i % 8, slot i / 8, warp slot % 8
 constexpr int TRD_NR = TRD_MAXN / 32;              // row elements per lane
 
 // -DGPCSD_EIG_PROF: clock64 phase timers of the cluster kernels (developer builds only; scripts/eig_prof_tridiag.py, scripts/eig_prof_dc.py, scripts/eig_trace_tridiag.py)
@@ -106,8 +106,32 @@ struct TridiagSmem {
   double2 pc[2][TRD_MAXN];        // the per-column exchange, by parity: .x = p_i = tau * (A v)_i of the column just built,
                                   // .y = a_{i,k+1}, row i's element of the NEXT pivot column (every row warp stores its pair into every CTA)
   double vs[TRD_WARPS][TRD_MAXN]; // per-warp private copy of the current reflector (single-element reads without shuffles)
+  double ael[TRD_WARPS][TRD_RPW]; // per warp: a_{i,k+1} of its rows, handed from the lane that holds column k+1 to the sending lanes
   uint64_t bar[2];                // transaction barriers of the exchange, by parity
 };
+
+// Warp totals of eight values with 9 shuffles instead of 40: every stage halves the number of values a lane carries (the
+// upper half-warp keeps v[4..7] and hands v[0..3] to its partner, ...), so lane L ends up with the total of v[L >> 2].
+// Partners add the same two numbers, so the four lanes of a group (and every warp given the same inputs) agree bit for bit.
+__device__ __forceinline__ double warp_reduce8_transposed(const double (&v)[8], int lane) {
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+  double u[4], t[2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double keep = b4 ? v[i + 4] : v[i], give = b4 ? v[i] : v[i + 4];
+    u[i] = keep + __shfl_xor_sync(0xffffffffu, give, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const double keep = b3 ? u[i + 2] : u[i], give = b3 ? u[i] : u[i + 2];
+    t[i] = keep + __shfl_xor_sync(0xffffffffu, give, 8);
+  }
+  const double keep = b2 ? t[1] : t[0], give = b2 ? t[0] : t[1];
+  double r = keep + __shfl_xor_sync(0xffffffffu, give, 4);
+  r += __shfl_xor_sync(0xffffffffu, r, 2);
+  r += __shfl_xor_sync(0xffffffffu, r, 1);
+  return r;
+}
 
 // 16-byte remote store that also signals 16 transaction bytes on an mbarrier of the same remote CTA
 __device__ __forceinline__ void dsmem_store2_signal(uint32_t addr, double v0, double v1, uint32_t mbar) {
@@ -156,11 +180,15 @@ __device__ __forceinline__ void static_for(F&& f) {
 //  * it runs on the rows as they stand BEFORE the previous reflector's update (A' x = A x - v (w.x) - w (v.x), two more sums
 //    in the same reduction); that rank-2 update of the own rows, the normalised reflector and its store to global memory
 //    are done AFTER the send, under the latency of the exchange.
-// With 16 warps per SM executing this in lock step the loop is bound by instruction ISSUE (4 warps per scheduler), not by
-// latency (clock64 trace: every phase advances at the same pace in all warps), so the body is specialised at compile time
-// on NR = ceil(n / 32) register blocks per row and on M0 = k / 32, the first live block: no per-block predicates, no work
-// on dead blocks; only blocks M0 and M0+1 carry lane masks.  Out-of-range columns (j >= n) need no masks either: the rows
-// and the exchange buffers are zero there and stay zero.
+// With every warp of the SM executing this in lock step the loop is bound by instruction ISSUE, not by latency (clock64
+// trace: every phase advances at the same pace in all warps; a first version with 16 warps x 2 rows and per-block
+// predicates issued 916 instructions per warp and column), so
+//  * the body is specialised at compile time on NR = ceil(n / 32) register blocks per row and on M0 = k / 32, the first
+//    live block: no per-block predicates, no work on dead blocks; only blocks M0 and M0+1 carry lane masks.  Out-of-range
+//    columns (j >= n) need no masks either: the rows and the exchange buffers are zero there and stay zero;
+//  * 8 warps hold up to 4 rows each (the redundant per-warp part -- w, x, the reflector -- is issued 8 times per SM, not 16);
+//  * the seven sums of the merged reduction go through ONE transposed butterfly (warp_reduce8_transposed);
+//  * the per-row send arithmetic is done by the 8 lanes that send that row, not replicated for every row in every lane.
 // Exchanges are st.async stores that complete transaction bytes on an mbarrier of the receiving CTA (double buffered by
 // parity): no cluster barrier (it costs a MEMBAR.ALL.GPU that also waits for the reflector stores to global memory), no
 // fence, no CTA-wide barrier, no shared-memory reduction.  A CTA cannot run more than one exchange ahead of the slowest one
@@ -171,8 +199,8 @@ template <int NR>
 __global__ void __cluster_dims__(TRD_CLUSTER, 1, 1) __launch_bounds__(32 * TRD_WARPS, 1)
     tridiag_cluster_kernel(int n, const double* __restrict__ M, long ldm, double* __restrict__ d, double* __restrict__ e,
                            double* __restrict__ V, long ldv, double* __restrict__ tau) {
-  static_assert(TRD_RPW == 2, "the send below maps lanes 0-7 / 8-15 to the two row slots of a warp");
-  constexpr int RPW = NR > TRD_NR / 2 ? 2 : 1;       // n <= 128: the second row slot of every warp is empty
+  constexpr int RPW = (NR + 1) / 2;     // row slots per warp that can be occupied at this order (n <= 32 NR)
+  static_assert(RPW <= TRD_RPW && RPW + 3 <= 8, "row sums + three shared sums go through one 8-value reduction");
   __shared__ __align__(16) TridiagSmem S;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
@@ -206,9 +234,10 @@ __global__ void __cluster_dims__(TRD_CLUSTER, 1, 1) __launch_bounds__(32 * TRD_W
   }
   cluster.sync();                       // every CTA's shared memory and barriers are live before remote stores
 
-  // lanes 0-7 send the pair of row slot 0 to CTAs 0-7, lanes 8-15 the pair of row slot 1
-  const int peer_rank = lane & (TRD_CLUSTER - 1);
-  const int send_row = (lane < TRD_CLUSTER) ? row[0] : ((RPW > 1 && lane < 2 * TRD_CLUSTER) ? row[RPW - 1] : TRD_MAXN);
+  // lanes 8q .. 8q+7 send the pair of row slot q to CTAs 0-7
+  const int peer_rank = lane & (TRD_CLUSTER - 1), myq = lane >> 3;
+  const int send_row = rank + (warp + myq * TRD_WARPS) * TRD_CLUSTER;       // < 256
+  const bool sender = myq < RPW && send_row < n;
   // (the peer's TridiagSmem sits at the same offset of its shared-memory window: one mapa, constant offsets)
   const uint32_t remote = dsmem_addr(&S, peer_rank) + 16u * (uint32_t)send_row;
   const uint32_t remote_bar = dsmem_addr(&S.bar[0], peer_rank);
@@ -225,12 +254,13 @@ __global__ void __cluster_dims__(TRD_CLUSTER, 1, 1) __launch_bounds__(32 * TRD_W
   // exchange 0: column 0 of every row (p = 0)
   if (armer) mbar_expect_tx(&S.bar[0], 16u * (uint32_t)n);
   {
-    double e0 = __shfl_sync(0xffffffffu, a[0][0], 0);
-    if (RPW > 1) {
-      const double e1 = __shfl_sync(0xffffffffu, a[RPW - 1][0], 0);
-      if (lane >= TRD_CLUSTER) e0 = e1;
+    double e0 = 0.0;
+#pragma unroll
+    for (int q = 0; q < RPW; ++q) {
+      const double eq = __shfl_sync(0xffffffffu, a[q][0], 0);
+      if (myq == q) e0 = eq;
     }
-    if (send_row < n) dsmem_store2_signal(remote, 0.0, e0, remote_bar);
+    if (sender) dsmem_store2_signal(remote, 0.0, e0, remote_bar);
   }
 
   double vprev[NR];                     // reflector k-1 (zero before the first column)
@@ -245,6 +275,7 @@ __global__ void __cluster_dims__(TRD_CLUSTER, 1, 1) __launch_bounds__(32 * TRD_W
   auto column = [&](auto M0c) -> bool {
     constexpr int M0 = decltype(M0c)::value;
     constexpr bool HAS1 = M0 + 1 < NR;  // block M0+1 exists
+    constexpr int M1 = HAS1 ? M0 + 1 : M0;
     EIG_PROF(0)
     const int pb = k & 1;               // exchange k: p of column k-1 and row k
     const bool build = k < n - 2;       // k = n-2: only finishes column n-3
@@ -253,8 +284,13 @@ __global__ void __cluster_dims__(TRD_CLUSTER, 1, 1) __launch_bounds__(32 * TRD_W
     if (last_row < k || (last_row == k && build)) return false;
     if (armer && build) mbar_expect_tx(&S.bar[pb ^ 1], 16u * (uint32_t)(n - k - 1));     // exchange k+1: rows i > k
     const int kl = k & 31;
-    const bool wrap = kl == 31;         // column k+1 is lane 0 of block M0+1
+    const bool wrap = HAS1 && kl == 31; // column k+1 is lane 0 of block M0+1
     const int l1 = (kl + 1) & 31;       // lane of column k+1
+    // a_{i,k+1} of the own rows (as the registers hold them: before the update by reflector k-1) -> the sending lanes
+    if (lane == l1) {
+#pragma unroll
+      for (int q = 0; q < RPW; ++q) S.ael[warp][q] = wrap ? a[q][M1] : a[q][M0];
+    }
     mbar_wait_cluster(&S.bar[pb], (uint32_t)((k >> 1) & 1));
     EIG_PROF(1)
     // ---- finish column k-1: w = p - (tau/2)(p.v) v   (k = 0: p = v = 0; v^{k-1}_j = 0 for j < k, 1 at j = k)
@@ -272,9 +308,11 @@ __global__ void __cluster_dims__(TRD_CLUSTER, 1, 1) __launch_bounds__(32 * TRD_W
       if ((m - M0) & 1) pv1 += w[m] * vprev[m]; else pv0 += w[m] * vprev[m];
     }
     const double pv = pv0 + pv1;
+    // every load from the exchange buffer happens BEFORE this warp's send: once all warps have sent, the peers may run on
+    // and overwrite this parity with exchange k+2
     const double2 ek = S.pc[pb][k], ek1 = S.pc[pb][k + 1];   // (p_k, r_k), (p_{k+1}, r_{k+1}): uniform loads
     const double vk1 = vs[k + 1];                            // v^{k-1}_{k+1}
-    double vi[RPW], wi[RPW], ae[RPW];
+    double vi[RPW], wi[RPW];
     bool act[RPW];
 #pragma unroll
     for (int q = 0; q < RPW; ++q) {
@@ -282,17 +320,18 @@ __global__ void __cluster_dims__(TRD_CLUSTER, 1, 1) __launch_bounds__(32 * TRD_W
       const int r = act[q] ? row[q] : k;
       vi[q] = vs[r];
       wi[q] = S.pc[pb][r].x;                                 // p_i for now
-      // a_{i,k+1} of the own rows (as the registers hold them: before the update by reflector k-1)
-      double sel = a[q][M0];
-      if (HAS1 && wrap) sel = a[q][HAS1 ? M0 + 1 : M0];
-      ae[q] = __shfl_sync(0xffffffffu, sel, l1);
     }
+    const double vim = vs[send_row];                         // the same for the row this lane sends
+    double wim = S.pc[pb][send_row].x;
+    __syncwarp();
+    const double aem = S.ael[warp][myq & (TRD_RPW - 1)];
     const double c = 0.5 * tprev * warp_sum(pv);
     EIG_PROF(2)
 #pragma unroll
     for (int m = M0; m < NR; ++m) w[m] -= c * vprev[m];
 #pragma unroll
     for (int q = 0; q < RPW; ++q) wi[q] -= c * vi[q];
+    wim -= c * vim;
     if (!build) {                       // last pass: only the update of rows n-2, n-1 by reflector n-3 is left
 #pragma unroll
       for (int q = 0; q < RPW; ++q)
@@ -310,30 +349,25 @@ __global__ void __cluster_dims__(TRD_CLUSTER, 1, 1) __launch_bounds__(32 * TRD_W
 #pragma unroll
     for (int m = M0; m < NR; ++m) x[m] = (x[m] - w[m]) - wk * vprev[m];
     if (lane <= kl + 1) x[M0] = 0.0;    // columns <= k+1
-    if (HAS1 && wrap && lane == 0) x[HAS1 ? M0 + 1 : M0] = 0.0;
-    double ss = 0.0, wx = 0.0, vx = 0.0, sx[RPW];
+    if (wrap && lane == 0) x[M1] = 0.0;
+    double red[8];
 #pragma unroll
-    for (int q = 0; q < RPW; ++q) sx[q] = 0.0;
+    for (int i = 0; i < 8; ++i) red[i] = 0.0;
 #pragma unroll
     for (int m = M0; m < NR; ++m) {
-      ss += x[m] * x[m];
-      wx += w[m] * x[m];
-      vx += vprev[m] * x[m];
 #pragma unroll
-      for (int q = 0; q < RPW; ++q) sx[q] += a[q][m] * x[m];
+      for (int q = 0; q < RPW; ++q) red[q] += a[q][m] * x[m];         // (A x)_i, rows as held
+      red[4] += w[m] * x[m];
+      red[5] += vprev[m] * x[m];
+      red[6] += x[m] * x[m];
     }
     EIG_PROF(3)
     // ---- ONE reduction for the norm, the two correction sums and the row sums of A x
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      ss += __shfl_xor_sync(0xffffffffu, ss, o);
-      wx += __shfl_xor_sync(0xffffffffu, wx, o);
-      vx += __shfl_xor_sync(0xffffffffu, vx, o);
-#pragma unroll
-      for (int q = 0; q < RPW; ++q) sx[q] += __shfl_xor_sync(0xffffffffu, sx[q], o);
-    }
+    const double tot = warp_reduce8_transposed(red, lane);             // lane L: total of red[L >> 2]
+    const double sxm = __shfl_sync(0xffffffffu, tot, (4 * myq) & 31);  // (A x)_i of the row this lane sends
+    const double wx = __shfl_sync(0xffffffffu, tot, 16), vx = __shfl_sync(0xffffffffu, tot, 20);
+    const double xnorm2 = __shfl_sync(0xffffffffu, tot, 24);
     EIG_PROF(4)
-    const double xnorm2 = ss;
     double t = 0.0, beta = alpha, scal = 0.0;
     if (xnorm2 > 0.0) {
       const double s2 = alpha * alpha + xnorm2, aa = fabs(alpha);
@@ -355,17 +389,9 @@ __global__ void __cluster_dims__(TRD_CLUSTER, 1, 1) __launch_bounds__(32 * TRD_W
     // ---- p_i = tau (A' v)_i, A' = the rows after the update by reflector k-1, v = (1, scal * x_tail):
     //      a'_{i,k+1} + scal * ((A x)_i - v_i (w.x) - w_i (v.x)); sent with a'_{i,k+1} (row k+1 of the next exchange)
     {
-      double pn[RPW], an[RPW];
-#pragma unroll
-      for (int q = 0; q < RPW; ++q) {
-        an[q] = ae[q] - (vi[q] * wk1 + wi[q] * vk1);
-        pn[q] = t * (an[q] + scal * ((sx[q] - vi[q] * wx) - wi[q] * vx));
-      }
-      if (RPW > 1 && lane >= TRD_CLUSTER) {
-        pn[0] = pn[RPW - 1];
-        an[0] = an[RPW - 1];
-      }
-      if (send_row > k && send_row < n) dsmem_store2_signal(remote + (pb ? 0u : PC1), pn[0], an[0], remote_bar + (pb ? 0u : 8u));
+      const double an = aem - (vim * wk1 + wim * vk1);
+      const double pn = t * (an + scal * ((sxm - vim * wx) - wim * vx));
+      if (sender && send_row > k) dsmem_store2_signal(remote + (pb ? 0u : PC1), pn, an, remote_bar + (pb ? 0u : 8u));
     }
     EIG_PROF(6)
     // ---- under the latency of the exchange: the own rows catch up with reflector k-1 ...
@@ -383,12 +409,15 @@ __global__ void __cluster_dims__(TRD_CLUSTER, 1, 1) __launch_bounds__(32 * TRD_W
 #pragma unroll
     for (int m = M0; m < NR; ++m) vprev[m] = x[m] * scal;
     if (lane == l1) {
-      if (HAS1 && wrap) vprev[HAS1 ? M0 + 1 : M0] = 1.0; else vprev[M0] = 1.0;
+      if (wrap) vprev[M1] = 1.0; else vprev[M0] = 1.0;
     }
 #pragma unroll
     for (int m = M0; m < NR; ++m) vs[lane + 32 * m] = vprev[m];
     tprev = t;
-    if (row[0] == k + 1 || row[RPW - 1] == k + 1) {         // one warp of the cluster (an active one) records the column
+    bool recorder = false;
+#pragma unroll
+    for (int q = 0; q < RPW; ++q) recorder |= row[q] == k + 1;
+    if (recorder) {                     // one warp of the cluster (an active one) records the column
 #pragma unroll
       for (int m = M0; m < NR; ++m) {
         const int j = lane + 32 * m;
