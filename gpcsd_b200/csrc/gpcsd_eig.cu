@@ -103,9 +103,10 @@ __device__ long long g_eig_trace[8 * 16 * 12];
 #endif
 
 struct TridiagSmem {
-  double2 pc[2][TRD_MAXN];        // the per-column exchange, by parity: .x = p_i = tau * (A v)_i of the column just built,
-                                  // .y = a_{i,k+1}, row i's element of the NEXT pivot column (every row warp stores its pair into every CTA)
-  double vs[TRD_WARPS][TRD_MAXN]; // per-warp private copy of the current reflector (single-element reads without shuffles)
+  double2 pc[2][TRD_MAXN];        // the per-column exchange, by parity: .x = (A x)_i (p_i = tau (.y + scal .x) is completed by
+                                  // the receiver), .y = a_{i,k+1}, row i's element of the NEXT pivot column (every row warp
+                                  // stores its pair into every CTA)
+  double vs[TRD_WARPS][TRD_MAXN]; // per-warp private copy of the current (unnormalised) reflector (single-element reads without shuffles)
   double ael[TRD_WARPS][TRD_RPW]; // per warp: a_{i,k+1} of its rows, handed from the lane that holds column k+1 to the sending lanes
   uint64_t bar[2];                // transaction barriers of the exchange, by parity
 };
@@ -174,12 +175,17 @@ __device__ __forceinline__ void static_for(F&& f) {
 // next pivot column (= row k+1 by symmetry), so that after the exchange every warp holds p AND the next pivot row and
 // redundantly (bit-identically) finishes column k (w = p - tau/2 (p.v) v), applies that rank-2 update to the received row
 // to obtain column k+1 of the current matrix and builds reflector k+1 from it.  Per column:
-//     wait -> p.v (warp reduction) -> x -> { |x|^2, A x, w.x, v.x } (ONE merged warp reduction) -> rsqrt/reciprocal -> send:
+//     wait -> { S1, S2 (warp reduction) || rsqrt/reciprocal of the previous reflector } -> x -> { |x|^2, A x, w.x, v.x }
+//     (ONE merged warp reduction) -> send:
 //  * the symv runs on the UNNORMALISED pivot column x (A v = a_{:,k+1} + scal * A x_tail), so it shares the reduction
 //    with the norm instead of waiting for the reflector;
 //  * it runs on the rows as they stand BEFORE the previous reflector's update (A' x = A x - v (w.x) - w (v.x), two more sums
 //    in the same reduction); that rank-2 update of the own rows, the normalised reflector and its store to global memory
-//    are done AFTER the send, under the latency of the exchange.
+//    are done AFTER the send, under the latency of the exchange;
+//  * what is sent is the RAW pair ((A' x)_i, a'_{i,k+1}) and the reflector is kept UNNORMALISED (x, not v = scal x): every
+//    use of tau and scal = 1/(alpha - beta) becomes a uniform coefficient that is first needed at the END of the next
+//    column's p.v reduction, so the ~20 dependent FP64 operations of the rsqrt / reciprocal chain are issued in the shadow
+//    of that reduction instead of between the merged reduction and the send.
 // With every warp of the SM executing this in lock step the loop is bound by instruction ISSUE, not by latency (clock64
 // trace: every phase advances at the same pace in all warps; a first version with 16 warps x 2 rows and per-block
 // predicates issued 916 instructions per warp and column), so
@@ -263,10 +269,10 @@ __global__ void __cluster_dims__(TRD_CLUSTER, 1, 1) __launch_bounds__(32 * TRD_W
     if (sender) dsmem_store2_signal(remote, 0.0, e0, remote_bar);
   }
 
-  double vprev[NR];                     // reflector k-1 (zero before the first column)
+  double xp[NR];                        // UNNORMALISED reflector k-1: the pivot column beyond the subdiagonal (zero for j <= k)
 #pragma unroll
-  for (int m = 0; m < NR; ++m) vprev[m] = 0.0;
-  double tprev = 0.0;
+  for (int m = 0; m < NR; ++m) xp[m] = 0.0;
+  double alpha_p = 0.0, xn2_p = 0.0;    // its alpha and |x|^2: tau, beta, 1/(alpha - beta) are formed one exchange later
   bool live = true;
   int k = 0;
 
@@ -276,8 +282,9 @@ __global__ void __cluster_dims__(TRD_CLUSTER, 1, 1) __launch_bounds__(32 * TRD_W
     constexpr int M0 = decltype(M0c)::value;
     constexpr bool HAS1 = M0 + 1 < NR;  // block M0+1 exists
     constexpr int M1 = HAS1 ? M0 + 1 : M0;
+    constexpr int Q0 = M0 / 2;          // row slots below Q0 (rows < 64 Q0 <= k) are finished in every warp
     EIG_PROF(0)
-    const int pb = k & 1;               // exchange k: p of column k-1 and row k
+    const int pb = k & 1;               // exchange k: raw pairs of column k-1 / row k
     const bool build = k < n - 2;       // k = n-2: only finishes column n-3
     // (a warp whose last row is exactly k has nothing left to send either -- nobody waits for it, so it must not wait on
     //  barriers that may run ahead of it; the owner of row n-2 stays for the final update, after which nothing runs ahead)
@@ -289,146 +296,207 @@ __global__ void __cluster_dims__(TRD_CLUSTER, 1, 1) __launch_bounds__(32 * TRD_W
     // a_{i,k+1} of the own rows (as the registers hold them: before the update by reflector k-1) -> the sending lanes
     if (lane == l1) {
 #pragma unroll
-      for (int q = 0; q < RPW; ++q) S.ael[warp][q] = wrap ? a[q][M1] : a[q][M0];
+      for (int q = Q0; q < RPW; ++q) S.ael[warp][q] = wrap ? a[q][M1] : a[q][M0];
     }
     mbar_wait_cluster(&S.bar[pb], (uint32_t)((k >> 1) & 1));
     EIG_PROF(1)
-    // ---- finish column k-1: w = p - (tau/2)(p.v) v   (k = 0: p = v = 0; v^{k-1}_j = 0 for j < k, 1 at j = k)
-    double w[NR], x[NR];
-    double pv0 = 0.0, pv1 = 0.0;
+    // ---- the received raw pairs (s_j, a_j): p_j = tau (a_j + scal s_j) with the scalars of reflector k-1, v_k = 1 and
+    //      v_j = scal x_j beyond, so  p.v = tau (a_k + scal (s_k + S1 + scal S2)),  S1 = sum a_j x_j, S2 = sum s_j x_j:
+    //      the two sums do not need the scalars, whose rsqrt / reciprocal chain (~20 dependent operations) is issued next to
+    //      the reduction instead of in front of it.  (x_j = 0 for j <= k: stale entries of finished rows drop out.)
+    //      Every load from the exchange buffer happens BEFORE this warp's send: once all warps have sent, the peers may
+    //      run on and overwrite this parity with exchange k+2.
+    double sp[NR], x[NR];
+    double S1 = 0.0, S2 = 0.0, S1b = 0.0, S2b = 0.0;
 #pragma unroll
     for (int m = M0; m < NR; ++m) {
       const double2 t2 = S.pc[pb][lane + 32 * m];
-      w[m] = t2.x;
+      sp[m] = t2.x;
       x[m] = t2.y;
+      if ((m - M0) & 1) {
+        S1b += t2.y * xp[m];
+        S2b += t2.x * xp[m];
+      } else {
+        S1 += t2.y * xp[m];
+        S2 += t2.x * xp[m];
+      }
     }
-    if (lane < kl) w[M0] = 0.0;         // rows < k are finished: their p is stale
-#pragma unroll
-    for (int m = M0; m < NR; ++m) {
-      if ((m - M0) & 1) pv1 += w[m] * vprev[m]; else pv0 += w[m] * vprev[m];
-    }
-    const double pv = pv0 + pv1;
-    // every load from the exchange buffer happens BEFORE this warp's send: once all warps have sent, the peers may run on
-    // and overwrite this parity with exchange k+2
-    const double2 ek = S.pc[pb][k], ek1 = S.pc[pb][k + 1];   // (p_k, r_k), (p_{k+1}, r_{k+1}): uniform loads
-    const double vk1 = vs[k + 1];                            // v^{k-1}_{k+1}
+    S1 += S1b;
+    S2 += S2b;
+    const double2 ek = S.pc[pb][k], ek1 = S.pc[pb][k + 1];   // (s_k, a_k), (s_{k+1}, a_{k+1}): uniform loads
+    const double xk1 = vs[k + 1];                            // x^{k-1}_{k+1}
     double vi[RPW], wi[RPW];
+    double2 pr[RPW];
     bool act[RPW];
 #pragma unroll
-    for (int q = 0; q < RPW; ++q) {
-      act[q] = row[q] >= k && row[q] < n;                    // warp-uniform
+    for (int q = Q0; q < RPW; ++q) {
+      act[q] = row[q] > k && row[q] < n;                     // warp-uniform; row k itself is final
       const int r = act[q] ? row[q] : k;
-      vi[q] = vs[r];
-      wi[q] = S.pc[pb][r].x;                                 // p_i for now
+      vi[q] = vs[r];                                         // x_i for now
+      pr[q] = S.pc[pb][r];
     }
-    const double vim = vs[send_row];                         // the same for the row this lane sends
-    double wim = S.pc[pb][send_row].x;
+    double vim = vs[send_row];                               // the same for the row this lane sends
+    const double2 prm = S.pc[pb][send_row];
     __syncwarp();
     const double aem = S.ael[warp][myq & (TRD_RPW - 1)];
-    const double c = 0.5 * tprev * warp_sum(pv);
-    EIG_PROF(2)
-#pragma unroll
-    for (int m = M0; m < NR; ++m) w[m] -= c * vprev[m];
-#pragma unroll
-    for (int q = 0; q < RPW; ++q) wi[q] -= c * vi[q];
-    wim -= c * vim;
-    if (!build) {                       // last pass: only the update of rows n-2, n-1 by reflector n-3 is left
-#pragma unroll
-      for (int q = 0; q < RPW; ++q)
-        if (act[q]) {
-#pragma unroll
-          for (int m = M0; m < NR; ++m) a[q][m] = fma(-wi[q], vprev[m], fma(-vi[q], w[m], a[q][m]));
-        }
-      return false;
+    // reflector k-1: tau = 1 + |alpha| / |beta|, beta = -sign(alpha) sqrt(alpha^2 + |x|^2), scal = 1 / (alpha - beta);
+    // fast path without branches (MUFU seeds + Newton, see fast_rsqrt / refine_recip), discarded when out of range
+    const double s2 = fma(alpha_p, alpha_p, xn2_p), aa = fabs(alpha_p);
+    const bool nz = xn2_p > 0.0, fastp = s2 > 1e-30 && s2 < 1e30;
+    double tt, abv, rden;
+    {
+      // (single MUFU instructions without the denormal / range fix-up branches of rsqrtf, sqrtf and __frcp_rn: the chain
+      //  stays in ONE basic block with the reduction below, so the scheduler interleaves the two)
+      const float sf = (float)s2;
+      float yf, y0f;
+      asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(yf) : "f"(sf));
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y0f) : "f"(fmaf(sf, yf, (float)aa)));      // ~ 1 / (|alpha| + sqrt(s2))
+      const double y = (double)yf;
+      const double r = fma(-s2 * y, y, 1.0);
+      const double rn = fma(y * r, fma(r, 0.375, 0.5), y);   // 1 / |beta|
+      abv = s2 * rn;                                         // |beta|
+      tt = fma(aa, rn, 1.0);
+      const double den = aa + abv;                           // |alpha - beta|
+      const double y0 = (double)y0f;
+      const double r2 = fma(-den, y0, 1.0);
+      rden = fma(y0 * r2, 1.0 + r2, y0);
     }
-    // ---- row k of the current matrix (== column k), rebuilt from the received elements; v^{k-1}_k = 1, so
-    //      x_j = r_j - w_j - w_k v_j with w_k = p_k - c
-    const double wk = ek.x - c, wk1 = ek1.x - c * vk1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      S1 += __shfl_xor_sync(0xffffffffu, S1, o);
+      S2 += __shfl_xor_sync(0xffffffffu, S2, o);
+    }
+    if (!fastp && nz) {                 // rare: outside the single-precision range
+      const double rn = 1.0 / sqrt(s2);
+      abv = s2 * rn;
+      tt = fma(aa, rn, 1.0);
+      rden = 1.0 / (aa + abv);
+    }
+    const double t = nz ? tt : 0.0, beta = nz ? -copysign(abv, alpha_p) : alpha_p, scal = nz ? copysign(rden, alpha_p) : 0.0;
+    EIG_PROF(2)
+    const double pv = t * (ek.y + scal * ((S1 + ek.x) + scal * S2));
+    const double c = 0.5 * t * pv;
+    const double ts = t * scal, cs = c * scal;
+    const double wk = t * fma(scal, ek.x, ek.y) - c;         // w_k = p_k - c v_k, v_k = 1
+    const double vk1 = scal * xk1;
+    const double wk1 = t * fma(scal, ek1.x, ek1.y) - c * vk1;
     const double akk = ek.y - 2.0 * wk;
     const double alpha = ek1.y - wk1 - wk * vk1;
+    const double wks = wk * scal;
+    // ---- finish column k-1: w_j = p_j - c v_j = tau a_j + (tau scal) s_j - (c scal) x_j   (j > k; column k is dead)
+    double w[NR];
 #pragma unroll
-    for (int m = M0; m < NR; ++m) x[m] = (x[m] - w[m]) - wk * vprev[m];
+    for (int m = M0; m < NR; ++m) w[m] = fma(-cs, xp[m], fma(ts, sp[m], t * x[m]));
+    if (lane < kl) w[M0] = 0.0;         // columns < k: stale pairs of finished rows
+#pragma unroll
+    for (int q = Q0; q < RPW; ++q) {
+      vi[q] *= scal;
+      wi[q] = t * fma(scal, pr[q].x, pr[q].y) - c * vi[q];
+      if (!act[q]) vi[q] = wi[q] = 0.0;                      // finished rows: the update below leaves them alone
+    }
+    vim *= scal;
+    const double wim = t * fma(scal, prm.x, prm.y) - c * vim;
+    bool recorder = false;              // one warp of the cluster (an active one: the owner of row k+1) records
+#pragma unroll
+    for (int q = Q0; q < RPW; ++q) recorder |= row[q] == k + 1;
+    auto record_prev = [&]() {          // column k-1: reflector, tau, subdiagonal
+      if (k > 0) {
+#pragma unroll
+        for (int m = M0; m < NR; ++m) {
+          const int j = lane + 32 * m;
+          if (j > k && j < n) V[(long)(k - 1) * ldv + j] = xp[m] * scal;
+        }
+        if (lane == 0) {
+          e[k - 1] = beta;
+          tau[k - 1] = t;
+        }
+      }
+    };
+    if (!build) {                       // last pass: rows n-2 (= k) and n-1 by reflector n-3; here column k is alive (v_k = 1)
+      double v[NR];
+#pragma unroll
+      for (int m = M0; m < NR; ++m) v[m] = xp[m] * scal;
+      if (lane == kl) {
+        v[M0] = 1.0;
+        w[M0] = wk;
+      }
+#pragma unroll
+      for (int q = Q0; q < RPW; ++q) {
+        if (row[q] >= k && row[q] < n) {
+          const double vq = (row[q] == k) ? 1.0 : vi[q], wq = (row[q] == k) ? wk : wi[q];
+#pragma unroll
+          for (int m = M0; m < NR; ++m) a[q][m] = fma(-wq, v[m], fma(-vq, w[m], a[q][m]));
+        }
+      }
+      if (recorder) record_prev();
+      return false;
+    }
+    // ---- row k of the current matrix (== column k) beyond the subdiagonal, rebuilt from the received elements:
+    //      x_j = a_j - w_j - w_k v_j
+#pragma unroll
+    for (int m = M0; m < NR; ++m) x[m] = (x[m] - w[m]) - wks * xp[m];
     if (lane <= kl + 1) x[M0] = 0.0;    // columns <= k+1
     if (wrap && lane == 0) x[M1] = 0.0;
-    double red[8];
+    double red[8], redb[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) red[i] = 0.0;
+    for (int i = 0; i < 8; ++i) red[i] = redb[i] = 0.0;
 #pragma unroll
     for (int m = M0; m < NR; ++m) {
+      if ((m - M0) & 1) {
 #pragma unroll
-      for (int q = 0; q < RPW; ++q) red[q] += a[q][m] * x[m];         // (A x)_i, rows as held
-      red[4] += w[m] * x[m];
-      red[5] += vprev[m] * x[m];
-      red[6] += x[m] * x[m];
+        for (int q = Q0; q < RPW; ++q) redb[q] += a[q][m] * x[m];
+        redb[4] += w[m] * x[m];
+        redb[5] += xp[m] * x[m];
+        redb[6] += x[m] * x[m];
+      } else {
+#pragma unroll
+        for (int q = Q0; q < RPW; ++q) red[q] += a[q][m] * x[m];      // (A x)_i, rows as held
+        red[4] += w[m] * x[m];
+        red[5] += xp[m] * x[m];
+        red[6] += x[m] * x[m];
+      }
     }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[i] += redb[i];
     EIG_PROF(3)
     // ---- ONE reduction for the norm, the two correction sums and the row sums of A x
     const double tot = warp_reduce8_transposed(red, lane);             // lane L: total of red[L >> 2]
     const double sxm = __shfl_sync(0xffffffffu, tot, (4 * myq) & 31);  // (A x)_i of the row this lane sends
-    const double wx = __shfl_sync(0xffffffffu, tot, 16), vx = __shfl_sync(0xffffffffu, tot, 20);
+    const double wx = __shfl_sync(0xffffffffu, tot, 16), vx = scal * __shfl_sync(0xffffffffu, tot, 20);
     const double xnorm2 = __shfl_sync(0xffffffffu, tot, 24);
     EIG_PROF(4)
-    double t = 0.0, beta = alpha, scal = 0.0;
-    if (xnorm2 > 0.0) {
-      const double s2 = alpha * alpha + xnorm2, aa = fabs(alpha);
-      const double rn = fast_rsqrt(s2);                    // 1 / |beta|
-      const double ab = s2 * rn;                           // |beta|
-      beta = -copysign(ab, alpha);
-      t = 1.0 + aa * rn;                                   // (beta - alpha) / beta
-      const double den = aa + ab;                          // |alpha - beta|
-      double rden;
-      if (s2 > 1e-30 && s2 < 1e30) {                       // single-precision seed computed off the critical path
-        const float sf = (float)s2;
-        rden = refine_recip(den, (double)__frcp_rn((float)aa + sqrtf(sf)));
-      } else {
-        rden = 1.0 / den;
-      }
-      scal = copysign(rden, alpha);                        // 1 / (alpha - beta)
-    }
-    EIG_PROF(5)
-    // ---- p_i = tau (A' v)_i, A' = the rows after the update by reflector k-1, v = (1, scal * x_tail):
-    //      a'_{i,k+1} + scal * ((A x)_i - v_i (w.x) - w_i (v.x)); sent with a'_{i,k+1} (row k+1 of the next exchange)
+    // ---- send the raw pair of the row this lane looks after: (A' x)_i = (A x)_i - v_i (w.x) - w_i (v.x) and a'_{i,k+1},
+    //      A' = the rows after the update by reflector k-1
     {
       const double an = aem - (vim * wk1 + wim * vk1);
-      const double pn = t * (an + scal * ((sxm - vim * wx) - wim * vx));
-      if (sender && send_row > k) dsmem_store2_signal(remote + (pb ? 0u : PC1), pn, an, remote_bar + (pb ? 0u : 8u));
+      const double spn = (sxm - vim * wx) - wim * vx;
+      if (sender && send_row > k) dsmem_store2_signal(remote + (pb ? 0u : PC1), spn, an, remote_bar + (pb ? 0u : 8u));
+    }
+    EIG_PROF(5)
+    // ---- under the latency of the exchange: column k-1 is recorded, the own rows catch up with reflector k-1
+    //      (columns j > k: a_ij -= v_i w_j + w_i scal x_j), the new unnormalised reflector is kept
+    if (recorder) {
+      record_prev();
+      if (lane == 0) d[k] = akk;
     }
     EIG_PROF(6)
-    // ---- under the latency of the exchange: the own rows catch up with reflector k-1 ...
     if (k > 0) {
 #pragma unroll
-      for (int q = 0; q < RPW; ++q) {
-        if (act[q]) {
+      for (int q = Q0; q < RPW; ++q) {
+        const double wis = wi[q] * scal;
 #pragma unroll
-          for (int m = M0; m < NR; ++m) a[q][m] = fma(-wi[q], vprev[m], fma(-vi[q], w[m], a[q][m]));
-        }
+        for (int m = M0; m < NR; ++m) a[q][m] = fma(-wis, xp[m], fma(-vi[q], w[m], a[q][m]));
       }
     }
     EIG_PROF(7)
-    // ---- ... and reflector k is normalised, kept (registers + the warp's shared-memory copy) and recorded
+    __syncwarp();     // every lane has read vs[] (x of column k-1) above
 #pragma unroll
-    for (int m = M0; m < NR; ++m) vprev[m] = x[m] * scal;
-    if (lane == l1) {
-      if (wrap) vprev[M1] = 1.0; else vprev[M0] = 1.0;
+    for (int m = M0; m < NR; ++m) {
+      xp[m] = x[m];
+      vs[lane + 32 * m] = x[m];
     }
-#pragma unroll
-    for (int m = M0; m < NR; ++m) vs[lane + 32 * m] = vprev[m];
-    tprev = t;
-    bool recorder = false;
-#pragma unroll
-    for (int q = 0; q < RPW; ++q) recorder |= row[q] == k + 1;
-    if (recorder) {                     // one warp of the cluster (an active one) records the column
-#pragma unroll
-      for (int m = M0; m < NR; ++m) {
-        const int j = lane + 32 * m;
-        if (j > k + 1 && j < n) V[(long)k * ldv + j] = vprev[m];
-      }
-      if (lane == 0) {
-        d[k] = akk;
-        e[k] = beta;
-        tau[k] = t;
-      }
-    }
+    alpha_p = alpha;
+    xn2_p = xnorm2;
     EIG_PROF(8)
     __syncwarp();     // vs[] written above is read (by other lanes of this warp) in the next column
     return true;

@@ -4,7 +4,7 @@ import numpy as np, torch
 from gpcsd_b200 import _lib as L
 lib = L.load()
 st = torch.cuda.current_stream().cuda_stream
-names = ["looptop", "wait", "pv-sum", "x+partials", "merged-reduce", "scalars", "p+send", "deferred-update", "reflector+record"]
+names = ["looptop", "wait", "S-sums||scalars", "coeffs+x+partials", "merged-reduce", "send", "record", "deferred-update", "keep"]
 for n in (24, 125, 250):
     ld = n + (n&1); nmat = 1
     A = torch.randn(nmat,n,n,dtype=torch.float64,device="cuda"); A = A + A.transpose(1,2)

@@ -15,9 +15,9 @@ out = (ctypes.c_longlong*(8*16*12))()
 lib.gpcsd_dbg_trace(out)
 T = np.array(list(out), dtype=np.int64).reshape(8,16,12)
 t0 = T[0,:3,0].min()
-nw = min(16, (n+7)//8)
+nw = min(8, (n+7)//8)
 for kk in range(8):
     k = kk+4
     for w in range(nw):
-        rows = [w*8, (w+16)*8]
+        rows = [w*8, (w+8)*8, (w+16)*8, (w+24)*8]
         print("k=%d warp %d (rows %s)%s: "%(k, w, rows, " OWNER(k+1)" if (k+1) in rows else ""), " ".join("%s@%d"%(nm, T[kk,w,i]-t0) for i,nm in enumerate(names)))
