@@ -328,6 +328,16 @@ static int dispatch_gemm(GemmArgs& p, int transB, int batch, cudaStream_t st) {
     return launch_gemm<32, 128, 32, 16, 3, false, EPI, 2>(p, batch, st);
   }
   if (batch > 65535) return gp_fail("gemm batch too large");
+  if (EPI == EPI_STORE) {
+    // Latency mode: a product whose 128 x 64 tiles would occupy less than half of the SMs (the 250-order rotations
+    // Q C Q^T of the gradient, the eigenvector products of gpcsd_eigh_dc: 16 tiles, ~22 us each on 16 SMs) is cut into
+    // 32 x 32 tiles instead -- 16 times the CTAs, each with a sixteenth of the k-loop work.
+    const long big = (long)((p.M + 127) / 128) * ((p.N + 63) / 64) * batch;
+    if (2 * big <= gp_num_sms()) {
+      if (transB) return launch_gemm<32, 32, 8, 16, 4, true, EPI, 2>(p, batch, st);
+      return launch_gemm<32, 32, 8, 16, 4, false, EPI, 2>(p, batch, st);
+    }
+  }
   return tma_gemm(transB, p.M, p.N, p.K, p.A, p.lda, p.sA, p.B, p.ldb, p.sB, p.C, p.ldc, p.sC, batch, p.rD, p.ldrd,
                   p.partials, EPI == EPI_QUAD, st, p.a_div, p.grp);
 }
