@@ -1,6 +1,8 @@
 // ABI entry points of the GEMM-shaped stages (gpcsd_dgemm, gpcsd_project_quad, gpcsd_wsyrk) and the small-M
 // kernels: cp.async DMMA GEMM for M <= 32 and the register-only small-M SYRK.  Everything with M > 32 is
 // dispatched to the persistent TMA + mbarrier kernels in gpcsd_tma.cu.  See include/gpcsd_b200.h.
+#include <stdlib.h>
+
 #include "common.h"
 #include "dmma_gemm.cuh"
 
@@ -12,8 +14,8 @@ int tma_gemm(int transB, int M, int N, int K, const double* A, long lda, long sA
              cudaStream_t st, int a_div = 1, int grp = 0);
 int tma_gemm_ctas(int M, int N, int batch);
 int tma_wsyrk(int M, int nseg, int seglen, const double* X, long row_stride, long seg_stride, const double* w, double* C,
-              long ldc, double* ws, int nsplit, int tiles_1d, int kbps, long total_kb, cudaStream_t st, int R = 1, long x_stride = 0,
-              long w_stride = 0, long c_stride = 0);
+              long ldc, double* ws, int nsplit, int tiles_1d, int kbps, long total_kb, cudaStream_t st, int R, long x_stride,
+              long w_stride, long c_stride, int bm);
 
 struct GemmArgs {
   const double* A;
@@ -490,8 +492,24 @@ __global__ void wsyrk_small_reduce_kernel(const double* __restrict__ ws, int npa
 
 static int syrk_small_ctas() { return 2 * gp_num_sms(); }
 
+// tile edge of the TMA SYRK: 64 where the lower triangle in 64-tiles is at most 0.65 of the area 128-tiles would compute
+// (M = 192: 6 x 64^2 against 3 x 128^2 = 0.50 -> 398 us becomes 208 us at the Neuropixels shape).  At M = 250 the ratio is
+// 0.83, but 64-tiles read every row panel twice as often (16 x 64 rows against 4 x 128 rows per k-block) and measured 240 us
+// against 156 us, so the larger tiles stay.  GPCSD_SYRK_TILE=128|64 overrides.
+static int syrk_tile_edge(int M) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("GPCSD_SYRK_TILE");
+    forced = e ? atoi(e) : 0;
+  }
+  if (forced == 64 || forced == 128) return forced;
+  const long t128 = (M + 127) / 128, t64 = (M + 63) / 64;
+  const long a128 = t128 * (t128 + 1) / 2 * 128 * 128, a64 = t64 * (t64 + 1) / 2 * 64 * 64;
+  return (a64 * 100 <= a128 * 65) ? 64 : 128;
+}
+
 static int syrk_plan(int M, int nseg, int seglen, int& bmn, int& tiles_1d, int& kbps, long& total_kb, int& nsplit) {
-  bmn = (M <= 32) ? 32 : 128;
+  bmn = (M <= 32) ? 32 : syrk_tile_edge(M);
   tiles_1d = (M + bmn - 1) / bmn;
   const long ntiles = (long)tiles_1d * (tiles_1d + 1) / 2;
   kbps = (seglen + BK - 1) / BK;
@@ -656,7 +674,8 @@ int gpcsd_wsyrk(int M, int nseg, int seglen, const double* X, long row_stride, l
   const long ntiles = (long)p.tiles_1d * (p.tiles_1d + 1) / 2;
   dim3 grid((unsigned)ntiles, (unsigned)p.nsplit);
   if (bmn == 32) return wsyrk_small_launch(p, nullptr, C, nullptr, ldc, st);
-  return tma_wsyrk(M, nseg, seglen, X, row_stride, seg_stride, w, C, ldc, ws, p.nsplit, p.tiles_1d, p.kbps, p.total_kb, st);
+  return tma_wsyrk(M, nseg, seglen, X, row_stride, seg_stride, w, C, ldc, ws, p.nsplit, p.tiles_1d, p.kbps, p.total_kb, st, 1, 0, 0,
+                   0, bmn);
 }
 
 /* Restart-batched SYRK: for r < R,  Cw_r = sum_seg w_r[seg] X_r,seg X_r,seg^T  (and Cp_r, the unweighted product, when Cp != NULL)
@@ -693,11 +712,11 @@ int gpcsd_wsyrk_batched(int R, int M, int nseg, int seglen, const double* X, lon
   p.sX = strideX; p.sW = strideW;
   if (bmn == 32) return wsyrk_small_launch(p, Cp ? &p : nullptr, Cw, Cp, ldc, st, R, strideC);
   if (int e = tma_wsyrk(M, nseg, seglen, X, row_stride, seg_stride, w, Cw, ldc, ws, p.nsplit, p.tiles_1d, p.kbps, p.total_kb, st, R,
-                        strideX, strideW, strideC))
+                        strideX, strideW, strideC, bmn))
     return e;
   if (Cp)
     return tma_wsyrk(M, nseg, seglen, X, row_stride, seg_stride, nullptr, Cp, ldc, ws, p.nsplit, p.tiles_1d, p.kbps, p.total_kb, st, R,
-                     strideX, 0, strideC);
+                     strideX, 0, strideC, bmn);
   return 0;
 }
 

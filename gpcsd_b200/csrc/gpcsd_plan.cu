@@ -269,14 +269,35 @@ __global__ void eig_D_rows_kernel(Dims d, const double* __restrict__ theta, cons
   }
 }
 
-__global__ void eig_D_cols_kernel(Dims d, const double* __restrict__ ls, const double* __restrict__ rD, long ldrd,
-                                  const double* __restrict__ rowC, const double* __restrict__ rowL, double* __restrict__ colB,
-                                  double* __restrict__ res) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+// colB[j] = sum_i ls_i / D_ij.  Block = 32 columns x 8 row groups (row group g sums i = g, g + 8, ... with four loads in
+// flight; the eight group sums are added in order through shared memory): one thread per column walking all nx rows was a
+// chain of nx dependent-latency loads on a single CTA (142 us at nx = 384).
+__global__ void __launch_bounds__(256) eig_D_cols_kernel(Dims d, const double* __restrict__ ls, const double* __restrict__ rD,
+                                                         long ldrd, const double* __restrict__ rowC,
+                                                         const double* __restrict__ rowL, double* __restrict__ colB,
+                                                         double* __restrict__ res) {
+  __shared__ double part[8][32];
+  const int tx = threadIdx.x & 31, gq = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + tx, r = blockIdx.y;
   const double* lsr = ls + (long)r * d.nx;
+  const double* rDr = rD + (long)r * d.nx * ldrd;
+  double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
   if (j < d.nt) {
+    int i = gq;
+    for (; i + 24 < d.nx; i += 32) {
+      b0 += lsr[i] * rDr[(long)i * ldrd + j];
+      b1 += lsr[i + 8] * rDr[(long)(i + 8) * ldrd + j];
+      b2 += lsr[i + 16] * rDr[(long)(i + 16) * ldrd + j];
+      b3 += lsr[i + 24] * rDr[(long)(i + 24) * ldrd + j];
+    }
+    for (; i < d.nx; i += 8) b0 += lsr[i] * rDr[(long)i * ldrd + j];
+  }
+  part[gq][tx] = (b0 + b1) + (b2 + b3);
+  __syncthreads();
+  if (gq == 0 && j < d.nt) {
     double b = 0.0;
-    for (int i = 0; i < d.nx; ++i) b += lsr[i] * rD[((long)r * d.nx + i) * ldrd + j];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) b += part[q][tx];
     colB[(long)r * d.nt + j] = b;
   }
   if (blockIdx.x == 0 && threadIdx.x < 32) {          // warp 0: the two scalars (fixed lane order -> deterministic)
@@ -919,7 +940,7 @@ int enqueue_body(Plan* p, int R, int want_grad, const Factors* fac, cudaStream_t
   }
   pl::eig_D_rows_kernel<<<dim3(nx, R), 256, 0, st>>>(d, p->theta, ls, lt, p->rD, ldt, p->rowA, p->rowC, p->rowL);
   PL_LAUNCH(1);
-  pl::eig_D_cols_kernel<<<dim3(blocks256(nt), R), 256, 0, st>>>(d, ls, p->rD, ldt, p->rowC, p->rowL, p->colB, p->res);
+  pl::eig_D_cols_kernel<<<dim3((nt + 31) / 32, R), 256, 0, st>>>(d, ls, p->rD, ldt, p->rowC, p->rowL, p->colB, p->res);
   PL_LAUNCH(1);
 
   // ---------------- projection A_i = Qt^T Z_i with the fused /D + quadratic form (hot loop gpcsd1d.py:124-126)

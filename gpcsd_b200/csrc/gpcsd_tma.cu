@@ -101,12 +101,13 @@ __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.
 //   aBase/bBase: shared-memory byte addresses of the stage's A / B tiles
 //   B_KMAJOR: B tile stored [n rows][16 k] (NT / SYRK) else 8 boxes [16 k][16 n] (NN)
 // NTW = 8-column MMA tiles per warp (warp tile 64 x 8*NTW; CTA tile 128 x 32*NTW)
-template <bool B_KMAJOR, bool SCALE_A, int NTW = 4>
-__device__ __forceinline__ void tma_mma_kblock(uint32_t aBase, uint32_t bBase, double (&acc)[T_MT][NTW][2], int wm, int wn, int g,
+template <bool B_KMAJOR, bool SCALE_A, int NTW = 4, int MT = T_MT>
+__device__ __forceinline__ void tma_mma_kblock(uint32_t aBase, uint32_t bBase, double (&acc)[MT][NTW][2], int wm, int wn, int g,
                                                int q, double ascale) {
+  static_assert(MT % 4 == 0, "row tiles are processed four at a time");
   const int pg = perm8(g);
   // (row & 7) == pg for every row tile (rows advance by 8), so the swizzle XOR term is loop-invariant
-  const uint32_t aRow = aBase + (wm * T_WM + pg) * 128;
+  const uint32_t aRow = aBase + (wm * 8 * MT + pg) * 128;
   constexpr int WN = 8 * NTW;
   const uint32_t bRow = bBase + (wn * WN + pg) * 128;
 #pragma unroll
@@ -132,7 +133,7 @@ __device__ __forceinline__ void tma_mma_kblock(uint32_t aBase, uint32_t bBase, d
       }
     }
 #pragma unroll
-    for (int ih = 0; ih < T_MT / 4; ++ih) {  // 4 row tiles at a time: keeps only 4 A fragments live
+    for (int ih = 0; ih < MT / 4; ++ih) {  // 4 row tiles at a time: keeps only 4 A fragments live
       double2 af[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -185,11 +186,13 @@ __device__ __forceinline__ void pipeline_setup(uint8_t*& tiles, uint64_t*& full,
   __syncthreads();
 }
 
-// C_b = A_b * op(B_b): persistent tiles, TMA producer + 8 DMMA consumer warps.
-template <bool BT, int EPI, int NTW>
+// C_b = A_b * op(B_b): persistent tiles, TMA producer + 8 DMMA consumer warps.  TBM = rows of the CTA tile: 128, or 64 for
+// operands whose row count pads badly to 128 (the 192-order halves of a Neuropixels spatial factor: 256 -> 192 rows computed).
+template <bool BT, int EPI, int NTW, int TBM>
 __global__ void __launch_bounds__(T_THREADS, 1)
     tma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TmaGemmArgs p) {
-  constexpr int BN = 32 * NTW, WN = 8 * NTW;     // CTA tile 128 x BN, warp tile 64 x WN
+  constexpr int BN = 32 * NTW, WN = 8 * NTW;     // CTA tile TBM x BN, warp tile TBM/2 x WN
+  constexpr int WM = TBM / T_WARPS_M, MT = WM / 8;
   uint8_t* tiles;
   uint64_t *full, *empty;
   pipeline_setup(tiles, full, empty);
@@ -206,11 +209,11 @@ __global__ void __launch_bounds__(T_THREADS, 1)
         const int mt = (int)(t % p.m_tiles);
         const long r = t / p.m_tiles;
         const int nt_ = (int)(r % p.n_tiles), b = (int)(r / p.n_tiles);
-        const int m0 = mt * T_BM, n0 = nt_ * BN;
+        const int m0 = mt * TBM, n0 = nt_ * BN;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % T_STAGES;
           mbar_wait(empty + s, ((it / T_STAGES) & 1) ^ 1);
-          mbar_expect_tx(full + s, T_TILE_BYTES + BN * BK * 8);
+          mbar_expect_tx(full + s, TBM * BK * 8 + BN * BK * 8);
           uint8_t* sa = tiles + (size_t)s * T_STAGE_BYTES;
           uint8_t* sb = sa + T_TILE_BYTES;
           tma_load_3d(sa, &tmA, full + s, kb * BK, m0, p.a_batched ? b / p.a_div : 0);
@@ -268,7 +271,7 @@ __global__ void __launch_bounds__(T_THREADS, 1)
     const int mt = (int)(t % p.m_tiles);
     const long r = t / p.m_tiles;
     const int nt_ = (int)(r % p.n_tiles), b = (int)(r / p.n_tiles);
-    const int m0 = mt * T_BM, n0 = nt_ * BN;
+    const int m0 = mt * TBM, n0 = nt_ * BN;
     if (EPI == TEPI_QUAD) {
       const int gnow = b / p.grp;
       if (gnow != cur_grp) {
@@ -276,24 +279,24 @@ __global__ void __launch_bounds__(T_THREADS, 1)
         cur_grp = gnow;
       }
     }
-    double acc[T_MT][NTW][2];
+    double acc[MT][NTW][2];
 #pragma unroll
-    for (int i = 0; i < T_MT; ++i)
+    for (int i = 0; i < MT; ++i)
 #pragma unroll
       for (int j = 0; j < NTW; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     for (int kb = 0; kb < nkb; ++kb, ++it) {
       const int s = it % T_STAGES;
       mbar_wait(full + s, (it / T_STAGES) & 1);
       const uint32_t sa = smem_u32(tiles + (size_t)s * T_STAGE_BYTES);
-      tma_mma_kblock<BT, false, NTW>(sa, sa + T_TILE_BYTES, acc, wm, wn, g, q, 1.0);
+      tma_mma_kblock<BT, false, NTW, MT>(sa, sa + T_TILE_BYTES, acc, wm, wn, g, q, 1.0);
       __syncwarp();
       if (lane == 0) mbar_arrive(empty + s);
     }
     // epilogue (overlaps the producer's prefetch of the next tile)
     double* C = p.C + (long)b * p.sC;
 #pragma unroll
-    for (int i = 0; i < T_MT; ++i) {
-      const int m = m0 + wm * T_WM + 8 * i + pg;
+    for (int i = 0; i < MT; ++i) {
+      const int m = m0 + wm * WM + 8 * i + pg;
       if (m >= p.M) continue;
       double rr = 1.0;
       if (EPI == TEPI_QUAD) rr = __ldg(p.rD + (long)b * p.ldrd + m);
@@ -347,8 +350,10 @@ struct TmaSyrkArgs {
   long ws_stride;
 };
 
+template <int TBM>     // tile edge: 128, or 64 where 128-tiles would compute much more than the lower triangle (syrk_plan)
 __global__ void __launch_bounds__(T_THREADS, 1)
     tma_wsyrk_kernel(const __grid_constant__ CUtensorMap tmX, TmaSyrkArgs p) {
+  constexpr int WM = TBM / T_WARPS_M, MT = WM / 8, NTW = TBM / 32;
   uint8_t* tiles;
   uint64_t *full, *empty;
   pipeline_setup(tiles, full, empty);
@@ -370,15 +375,15 @@ __global__ void __launch_bounds__(T_THREADS, 1)
         const int seg = (int)(f / p.kbps);
         const int k0 = (int)(f - (long)seg * p.kbps) * BK;
         mbar_wait(empty + s, ((it / T_STAGES) & 1) ^ 1);
-        mbar_expect_tx(full + s, diag ? T_TILE_BYTES : T_STAGE_BYTES);
+        mbar_expect_tx(full + s, (diag ? 1 : 2) * TBM * BK * 8);
         uint8_t* sa = tiles + (size_t)s * T_STAGE_BYTES;
         const int rr = blockIdx.z;
         if (p.seg_middle) {
-          tma_load_4d(sa, &tmX, full + s, k0, seg, tm * T_BM, rr);
-          if (!diag) tma_load_4d(sa + T_TILE_BYTES, &tmX, full + s, k0, seg, tn * T_BN, rr);
+          tma_load_4d(sa, &tmX, full + s, k0, seg, tm * TBM, rr);
+          if (!diag) tma_load_4d(sa + T_TILE_BYTES, &tmX, full + s, k0, seg, tn * TBM, rr);
         } else {
-          tma_load_4d(sa, &tmX, full + s, k0, tm * T_BM, seg, rr);
-          if (!diag) tma_load_4d(sa + T_TILE_BYTES, &tmX, full + s, k0, tn * T_BN, seg, rr);
+          tma_load_4d(sa, &tmX, full + s, k0, tm * TBM, seg, rr);
+          if (!diag) tma_load_4d(sa + T_TILE_BYTES, &tmX, full + s, k0, tn * TBM, seg, rr);
         }
       }
     }
@@ -388,31 +393,31 @@ __global__ void __launch_bounds__(T_THREADS, 1)
   const int warp = (threadIdx.x >> 5) - T_PRODUCER_WARPS;
   const int g = lane >> 2, q = lane & 3;
   const int wm = warp % T_WARPS_M, wn = warp / T_WARPS_M;
-  double acc[T_MT][4][2];
+  double acc[MT][NTW][2];
 #pragma unroll
-  for (int i = 0; i < T_MT; ++i)
+  for (int i = 0; i < MT; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < NTW; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
   for (int it = 0; it < nkb; ++it) {
     const int s = it % T_STAGES;
     const double wgt = p.w ? __ldg(p.w + (long)blockIdx.z * p.w_stride + (f0 + it) / p.kbps) : 1.0;
     mbar_wait(full + s, (it / T_STAGES) & 1);
     const uint32_t sa = smem_u32(tiles + (size_t)s * T_STAGE_BYTES);
     if (p.w)
-      tma_mma_kblock<true, true>(sa, diag ? sa : sa + T_TILE_BYTES, acc, wm, wn, g, q, wgt);
+      tma_mma_kblock<true, true, NTW, MT>(sa, diag ? sa : sa + T_TILE_BYTES, acc, wm, wn, g, q, wgt);
     else
-      tma_mma_kblock<true, false>(sa, diag ? sa : sa + T_TILE_BYTES, acc, wm, wn, g, q, 1.0);
+      tma_mma_kblock<true, false, NTW, MT>(sa, diag ? sa : sa + T_TILE_BYTES, acc, wm, wn, g, q, 1.0);
     __syncwarp();
     if (lane == 0) mbar_arrive(empty + s);
   }
   // partial tile in fragment order: fully coalesced double2 stores
   const long ntiles = (long)p.tiles_1d * (p.tiles_1d + 1) / 2;
-  double* out = p.ws + (long)blockIdx.z * p.ws_stride + ((long)split * ntiles + t) * (T_BM * T_BN);
+  double* out = p.ws + (long)blockIdx.z * p.ws_stride + ((long)split * ntiles + t) * (TBM * TBM);
 #pragma unroll
-  for (int i = 0; i < T_MT; ++i)
+  for (int i = 0; i < MT; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      *reinterpret_cast<double2*>(out + ((((warp * T_MT + i) * 4 + j) * 32 + lane) << 1)) = make_double2(acc[i][j][0], acc[i][j][1]);
+    for (int j = 0; j < NTW; ++j)
+      *reinterpret_cast<double2*>(out + ((((warp * MT + i) * NTW + j) * 32 + lane) << 1)) = make_double2(acc[i][j][0], acc[i][j][1]);
 }
 
 // sum the split-K partials in fixed order, un-permute the fragment layout, mirror the upper triangle.
@@ -420,7 +425,9 @@ __global__ void __launch_bounds__(T_THREADS, 1)
 // are added in order through shared memory): four times the loads in flight of a one-thread-per-element sum, which was
 // latency-bound at 14 % of HBM bandwidth.
 __global__ void __launch_bounds__(256) tma_wsyrk_reduce_kernel(const double* __restrict__ ws, int nsplit, int tiles_1d, int M,
-                                                               double* __restrict__ C, long ldc, long ws_stride, long c_stride) {
+                                                               double* __restrict__ C, long ldc, long ws_stride, long c_stride,
+                                                               int bm) {
+  const int te = bm * bm, mt_ = bm / (8 * T_WARPS_M), ntw = bm / 32;     // tile elements, row tiles / column tiles per warp
   __shared__ double part[4][64];
   ws += (long)blockIdx.z * ws_stride;
   C += (long)blockIdx.z * c_stride;
@@ -434,18 +441,18 @@ __global__ void __launch_bounds__(256) tma_wsyrk_reduce_kernel(const double* __r
   double s0 = 0.0, s1 = 0.0;
   int sp = grp;
   for (; sp + 4 < nsplit; sp += 8) {
-    s0 += ws[((long)sp * ntiles + t) * (T_BM * T_BN) + e];
-    s1 += ws[((long)(sp + 4) * ntiles + t) * (T_BM * T_BN) + e];
+    s0 += ws[((long)sp * ntiles + t) * te + e];
+    s1 += ws[((long)(sp + 4) * ntiles + t) * te + e];
   }
-  if (sp < nsplit) s0 += ws[((long)sp * ntiles + t) * (T_BM * T_BN) + e];
+  if (sp < nsplit) s0 += ws[((long)sp * ntiles + t) * te + e];
   part[grp][el] = s0 + s1;
   __syncthreads();
   if (grp != 0) return;
   const double s = (part[0][el] + part[1][el]) + (part[2][el] + part[3][el]);
-  const int v = e & 1, lane = (e >> 1) & 31, j = (e >> 6) & 3, i = (e >> 8) % T_MT, warp = (e >> 8) / T_MT;
+  const int v = e & 1, lane = (e >> 1) & 31, j = (e >> 6) % ntw, i = ((e >> 6) / ntw) % mt_, warp = (e >> 6) / (ntw * mt_);
   const int g = lane >> 2, q = lane & 3, wm = warp % T_WARPS_M, wn = warp / T_WARPS_M;
-  const int r = wm * T_WM + 8 * i + perm8(g), c = wn * T_WN + 8 * j + q + 4 * v;
-  const int m = tm * T_BM + r, n = tn * T_BN + c;
+  const int r = wm * 8 * mt_ + 8 * i + perm8(g), c = wn * 8 * ntw + 8 * j + q + 4 * v;
+  const int m = tm * bm + r, n = tn * bm + c;
   if (m >= M || n >= M) return;
   C[(long)m * ldc + n] = s;
   if (tm != tn) C[(long)n * ldc + m] = s;
@@ -524,9 +531,9 @@ static int make_map4(CUtensorMap* m, const double* base, uint64_t d0, uint64_t d
   return 0;
 }
 
-template <bool BT, int EPI, int NTW>
+template <bool BT, int EPI, int NTW, int TBM>
 static int launch_tma_gemm(const CUtensorMap& tA, const CUtensorMap& tB, TmaGemmArgs& p, cudaStream_t st) {
-  auto kern = tma_gemm_kernel<BT, EPI, NTW>;
+  auto kern = tma_gemm_kernel<BT, EPI, NTW, TBM>;
   static int attr[GP_MAX_DEVICES];
   if (gp_first_use_on_device(attr)) {
     GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_SMEM_BYTES));
@@ -541,8 +548,16 @@ static int launch_tma_gemm(const CUtensorMap& tA, const CUtensorMap& tB, TmaGemm
 // Tile width: 128, 96 or 64 columns.  Persistent CTAs run ceil(tiles / SMs) rounds of cost ~BN each, so the
 // narrower tiles win when they shave the ragged last round or the padded last column tile
 // (configs[1]: N = 2000 -> 16 x 128 = 2048 columns in 11 rounds vs 21 x 96 = 2016 columns in 14 rounds: -4.5 %).
+// Tile height: 64-row tiles where they cut the row padding by more than ~13 % (M = 192: 256 -> 192 rows; M = 250 pads to 256
+// either way and keeps the more efficient 128-row tiles).
+static int pick_bm(int M) {
+  const long p128 = (long)((M + 127) / 128) * 128, p64 = (long)((M + 63) / 64) * 64;
+  return (p128 * 100 > p64 * 115) ? 64 : 128;
+}
+
 static int pick_ntw(int M, int N, int batch) {
-  const long mt = (M + T_BM - 1) / T_BM, sms = gp_num_sms();
+  const int bm = pick_bm(M);
+  const long mt = (M + bm - 1) / bm, sms = gp_num_sms();
   int best = 4;
   double best_cost = 1e300;
   for (int ntw = 4; ntw >= 2; --ntw) {
@@ -559,16 +574,21 @@ static int pick_ntw(int M, int N, int batch) {
 }
 
 int tma_gemm_ctas(int M, int N, int batch) {
-  const int bn = 32 * pick_ntw(M, N, batch);
-  const long ntiles = (long)((M + T_BM - 1) / T_BM) * ((N + bn - 1) / bn) * batch;
+  const int bn = 32 * pick_ntw(M, N, batch), bm = pick_bm(M);
+  const long ntiles = (long)((M + bm - 1) / bm) * ((N + bn - 1) / bn) * batch;
   return (int)(ntiles < gp_num_sms() ? ntiles : gp_num_sms());
 }
 
 template <bool BT, int EPI>
-static int launch_tma_gemm_ntw(int ntw, const CUtensorMap& tA, const CUtensorMap& tB, TmaGemmArgs& p, cudaStream_t st) {
-  if (ntw == 4) return launch_tma_gemm<BT, EPI, 4>(tA, tB, p, st);
-  if (ntw == 3) return launch_tma_gemm<BT, EPI, 3>(tA, tB, p, st);
-  return launch_tma_gemm<BT, EPI, 2>(tA, tB, p, st);
+static int launch_tma_gemm_ntw(int ntw, int bm, const CUtensorMap& tA, const CUtensorMap& tB, TmaGemmArgs& p, cudaStream_t st) {
+  if (bm == 64) {
+    if (ntw == 4) return launch_tma_gemm<BT, EPI, 4, 64>(tA, tB, p, st);
+    if (ntw == 3) return launch_tma_gemm<BT, EPI, 3, 64>(tA, tB, p, st);
+    return launch_tma_gemm<BT, EPI, 2, 64>(tA, tB, p, st);
+  }
+  if (ntw == 4) return launch_tma_gemm<BT, EPI, 4, 128>(tA, tB, p, st);
+  if (ntw == 3) return launch_tma_gemm<BT, EPI, 3, 128>(tA, tB, p, st);
+  return launch_tma_gemm<BT, EPI, 2, 128>(tA, tB, p, st);
 }
 
 // C_b = A_b op(B_b); epi_quad != 0 fuses the /D + quadratic-form epilogue.  Returns 0 on success.
@@ -579,8 +599,8 @@ int tma_gemm(int transB, int M, int N, int K, const double* A, long lda, long sA
   const bool a_batched = (sA != 0 && batch > 1);
   if (a_div < 1) a_div = 1;
   if (grp < 1) grp = batch;
-  const int ntw = pick_ntw(M, N, batch), bn = 32 * ntw;
-  if (int e = make_map3(&tA, A, K, M, a_batched ? (batch + a_div - 1) / a_div : 1, lda, a_batched ? sA : 0, BK, T_BM, 1)) return e;
+  const int ntw = pick_ntw(M, N, batch), bn = 32 * ntw, bm = pick_bm(M);
+  if (int e = make_map3(&tA, A, K, M, a_batched ? (batch + a_div - 1) / a_div : 1, lda, a_batched ? sA : 0, BK, bm, 1)) return e;
   const long sBe = (batch > 1) ? sB : 0;
   if (transB) {
     if (int e = make_map3(&tB, B, K, N, batch, ldb, sBe, BK, bn, 1)) return e;
@@ -590,19 +610,30 @@ int tma_gemm(int transB, int M, int N, int K, const double* A, long lda, long sA
   TmaGemmArgs p{};
   p.C = C; p.ldc = ldc; p.sC = sC;
   p.M = M; p.N = N; p.K = K; p.batch = batch;
-  p.m_tiles = (M + T_BM - 1) / T_BM;
+  p.m_tiles = (M + bm - 1) / bm;
   p.n_tiles = (N + bn - 1) / bn;
   p.a_batched = a_batched ? 1 : 0;
   p.a_div = a_div; p.grp = grp; p.ngrp = (batch + grp - 1) / grp;
   p.rD = rD; p.ldrd = ldrd; p.partials = partials;
-  if (epi_quad) return launch_tma_gemm_ntw<false, TEPI_QUAD>(ntw, tA, tB, p, st);
-  if (transB) return launch_tma_gemm_ntw<true, TEPI_STORE>(ntw, tA, tB, p, st);
-  return launch_tma_gemm_ntw<false, TEPI_STORE>(ntw, tA, tB, p, st);
+  if (epi_quad) return launch_tma_gemm_ntw<false, TEPI_QUAD>(ntw, bm, tA, tB, p, st);
+  if (transB) return launch_tma_gemm_ntw<true, TEPI_STORE>(ntw, bm, tA, tB, p, st);
+  return launch_tma_gemm_ntw<false, TEPI_STORE>(ntw, bm, tA, tB, p, st);
+}
+
+template <int TBM>
+static int launch_tma_wsyrk(const CUtensorMap& tX, const TmaSyrkArgs& p, dim3 grid, cudaStream_t st) {
+  static int attr[GP_MAX_DEVICES];
+  if (gp_first_use_on_device(attr)) {
+    GP_CUDA(cudaFuncSetAttribute(tma_wsyrk_kernel<TBM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_SMEM_BYTES));
+  }
+  tma_wsyrk_kernel<TBM><<<grid, T_THREADS, T_SMEM_BYTES, st>>>(tX, p);
+  GP_CUDA(cudaGetLastError());
+  return 0;
 }
 
 int tma_wsyrk(int M, int nseg, int seglen, const double* X, long row_stride, long seg_stride, const double* w, double* C,
               long ldc, double* ws, int nsplit, int tiles_1d, int kbps, long total_kb, cudaStream_t st, int R, long x_stride,
-              long w_stride, long c_stride) {
+              long w_stride, long c_stride, int bm) {
   CUtensorMap tX;
   if (R < 1) R = 1;
   // X[restart][m][seg][k] = X + restart*x_stride + m*row_stride + seg*seg_stride + k.  Outer tensor dims are ordered by
@@ -611,9 +642,9 @@ int tma_wsyrk(int M, int nseg, int seglen, const double* X, long row_stride, lon
   const bool seg_middle = (nseg > 1) && (seg_stride < row_stride);
   const long xs = R > 1 ? x_stride : 0;
   if (seg_middle) {
-    if (int e = make_map4(&tX, X, seglen, nseg, M, R, seg_stride, row_stride, xs, BK, 1, T_BM)) return e;
+    if (int e = make_map4(&tX, X, seglen, nseg, M, R, seg_stride, row_stride, xs, BK, 1, bm)) return e;
   } else {
-    if (int e = make_map4(&tX, X, seglen, M, nseg, R, row_stride, nseg > 1 ? seg_stride : 0, xs, BK, T_BM, 1)) return e;
+    if (int e = make_map4(&tX, X, seglen, M, nseg, R, row_stride, nseg > 1 ? seg_stride : 0, xs, BK, bm, 1)) return e;
   }
   TmaSyrkArgs p{};
   p.w = w; p.M = M; p.nseg = nseg; p.seglen = seglen;
@@ -621,15 +652,11 @@ int tma_wsyrk(int M, int nseg, int seglen, const double* X, long row_stride, lon
   p.seg_middle = seg_middle ? 1 : 0;
   const long ntiles = (long)tiles_1d * (tiles_1d + 1) / 2;
   p.w_stride = w_stride;
-  p.ws_stride = (long)nsplit * ntiles * (T_BM * T_BN);
-  static int attr[GP_MAX_DEVICES];
-  if (gp_first_use_on_device(attr)) {
-    GP_CUDA(cudaFuncSetAttribute(tma_wsyrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T_SMEM_BYTES));
-  }
-  tma_wsyrk_kernel<<<dim3((unsigned)ntiles, (unsigned)nsplit, (unsigned)R), T_THREADS, T_SMEM_BYTES, st>>>(tX, p);
-  GP_CUDA(cudaGetLastError());
-  tma_wsyrk_reduce_kernel<<<dim3(T_BM * T_BN / 64, (unsigned)ntiles, (unsigned)R), 256, 0, st>>>(ws, nsplit, tiles_1d, M, C, ldc,
-                                                                                               p.ws_stride, c_stride);
+  p.ws_stride = (long)nsplit * ntiles * ((long)bm * bm);
+  const dim3 grid((unsigned)ntiles, (unsigned)nsplit, (unsigned)R);
+  if (int e = (bm == 64) ? launch_tma_wsyrk<64>(tX, p, grid, st) : launch_tma_wsyrk<128>(tX, p, grid, st)) return e;
+  tma_wsyrk_reduce_kernel<<<dim3(bm * bm / 64, (unsigned)ntiles, (unsigned)R), 256, 0, st>>>(ws, nsplit, tiles_1d, M, C, ldc,
+                                                                                           p.ws_stride, c_stride, bm);
   GP_CUDA(cudaGetLastError());
   return 0;
 }
