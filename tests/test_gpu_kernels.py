@@ -28,7 +28,9 @@ def _stream():
 
 @pytest.mark.parametrize("M,N,K,batch", [(128, 128, 16, 1), (500, 2000, 500, 3), (24, 1003, 24, 1), (7, 50, 5, 2),
                                           (33, 65, 17, 2), (384, 777, 384, 1), (130, 258, 131, 1), (1, 9, 300, 1),
-                                          (24, 100008, 24, 1), (32, 4101, 32, 2), (9, 17, 31, 3), (24, 24, 24, 1), (30, 8, 3, 1)])
+                                          (24, 100008, 24, 1), (32, 4101, 32, 2), (9, 17, 31, 3), (24, 24, 24, 1), (30, 8, 3, 1),
+                                          # 64-row TMA tiles (M pads badly to 128), latency mode (few 128 x 64 tiles)
+                                          (192, 3000, 192, 2), (150, 2100, 70, 1), (250, 250, 250, 2), (192, 192, 192, 2)])
 @pytest.mark.parametrize("transB", [0, 1])
 def test_dgemm(cuda_lib, M, N, K, batch, transB):
     from gpcsd_b200 import _lib as L
@@ -91,7 +93,7 @@ def test_project_quad(cuda_lib, nx, nt, N):
     assert abs(o[1] - np.sum(Bm * Bm)) / np.sum(Bm * Bm) < 1e-13
 
 
-@pytest.mark.parametrize("nx,nt,N", [(24, 50, 50), (5, 140, 300), (130, 9, 33), (3, 3, 1)])
+@pytest.mark.parametrize("nx,nt,N", [(24, 50, 50), (5, 140, 300), (130, 9, 33), (3, 3, 1), (192, 7, 40), (6, 250, 64), (64, 3, 24)])
 @pytest.mark.parametrize("weighted", [True, False])
 def test_wsyrk_both_orientations(cuda_lib, nx, nt, N, weighted):
     from gpcsd_b200 import _lib as L
@@ -396,7 +398,8 @@ def test_eigh_batched_small_orders(cuda_lib, n, batch):
         assert relerr(Q.T @ Q, np.eye(n)) < 1e-12
 
 
-@pytest.mark.parametrize("n,nmat", [(5, 1), (64, 2), (131, 2), (192, 2), (250, 2), (256, 1)])
+@pytest.mark.parametrize("n,nmat", [(5, 1), (32, 1), (33, 1), (64, 2), (65, 1), (97, 1), (128, 1), (129, 2), (131, 2), (161, 1),
+                                    (192, 2), (193, 1), (250, 2), (256, 1)])
 def test_cluster_tridiagonalisation_and_backtransform(cuda_lib, n, nmat):
     """M = H T H^T on 8-CTA clusters: T has M's eigenvalues; eigenvectors of T mapped back are eigenvectors of M."""
     import scipy.linalg
