@@ -90,16 +90,29 @@ DC_HD void secular_eval(int k, int isplit, int org, double mu, const double* dl,
                         double& dpsi, double& dphi) {
   const double dlo = dl[org];
   double ps = 0.0, ph = 0.0, dps = 0.0, dph = 0.0;
-  for (int j = X::lane(); j < k; j += X::L) {
-    const double del = (dl[j] - dlo) - mu;
-    const double t = w[j] * rcp(del);
-    const double wt = w[j] * t, tt = t * t;
-    if (j <= isplit) {
-      ps += wt;
-      dps += tt;
-    } else {
-      ph += wt;
-      dph += tt;
+  // four poles per trip: the reciprocals (MUFU seed + Newton steps, ~80 cycles of dependent latency each) are independent
+  // and overlap; a one-pole loop with a runtime trip count is a serial chain of them
+  for (int j0 = X::lane(); j0 < k; j0 += 4 * X::L) {
+    double t[4], wj[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u * X::L;
+      const bool in = j < k;
+      wj[u] = in ? w[j] : 0.0;
+      const double del = in ? (dl[j] - dlo) - mu : 1.0;
+      t[u] = wj[u] * rcp(del);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u * X::L;
+      const double wt = wj[u] * t[u], tt = t[u] * t[u];
+      if (j <= isplit) {
+        ps += wt;
+        dps += tt;
+      } else {
+        ph += wt;
+        dph += tt;
+      }
     }
   }
   psi = X::sum(ps);
@@ -213,9 +226,19 @@ DC_HD double delta_ji(const double* dl, int j, int org_i, double mu_i) { return 
 template <class X>
 DC_HD double zhat_component(int k, int j, const double* dl, const double* w, const double* mu, const int* org) {
   double p = 1.0;
-  for (int i = X::lane(); i < k; i += X::L) {
-    const double del = delta_ji(dl, j, org[i], mu[i]);
-    p *= (i == j) ? fabs(del) : fabs(del * rcp(dl[j] - dl[i]));
+  for (int i0 = X::lane(); i0 < k; i0 += 4 * X::L) {      // four factors per trip (independent reciprocals)
+    double f[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * X::L;
+      if (i < k) {
+        const double del = delta_ji(dl, j, org[i], mu[i]);
+        f[u] = (i == j) ? fabs(del) : fabs(del * rcp(dl[j] - dl[i]));
+      } else {
+        f[u] = 1.0;
+      }
+    }
+    p *= (f[0] * f[1]) * (f[2] * f[3]);
   }
   p = X::prod(p);
   return copysign(fsqrt(p), w[j]);

@@ -93,7 +93,9 @@ __device__ long long g_eig_prof[64];
 __device__ long long g_eig_trace[8 * 16 * 12];
 #define EIG_PROF(i) { const long long t_ = clock64(); prof_t[i] += t_ - prof_last; prof_last = t_; \
     if (rank == 0 && k >= 4 && k < 12 && lane == 0) g_eig_trace[((k - 4) * 16 + warp) * 12 + i] = t_; }
-#define EIG_PROF2(i) { const long long t_ = clock64(); prof_t[i] += t_ - prof_last; prof_last = t_; }
+__device__ long long g_eig_lp[16 * 16];     // [level][phase] of the divide-and-conquer kernel
+#define EIG_PROF2(i) { const long long t_ = clock64(); prof_t[i] += t_ - prof_last; \
+    if (rank == 0 && tid == 0 && mat == 0 && prof_level >= 0) g_eig_lp[prof_level * 16 + (i)] = t_ - prof_last; prof_last = t_; }
 #define EIG_PROF_DUMP(cond, cnt) if ((cond) && (threadIdx.x & 31) == 0) { for (int i_ = 0; i_ < (cnt); ++i_) g_eig_prof[i_] = prof_t[i_]; }
 #else
 #define EIG_PROF_DECL
@@ -537,7 +539,7 @@ constexpr int DC_WARPS = DC_THREADS / 32;
 constexpr int DC_MAXN = 256;
 constexpr int DC_MAXNODES = DC_MAXN / 2;
 constexpr int DC_TM = 64, DC_TN = 64, DC_TK = 16;     // eigenvector-update tile (rows = new eigenvectors, cols = components)
-constexpr int DC_DIRECT_MAX = 32;                     // merge nodes up to this size use the one-thread-per-element update
+constexpr int DC_DIRECT_MAX = 16;                     // merge nodes up to this size use the one-thread-per-element update
 
 struct DcSmem {
   // replicated in every CTA (each CTA runs the O(n) bookkeeping redundantly, bit-identically)
@@ -550,7 +552,7 @@ struct DcSmem {
   double mu[DC_MAXN], zh[DC_MAXN];
   int org[DC_MAXN];
   // eigenvector-update tiles
-  double As[DC_TK][DC_TM + 2], Bs[DC_TK][DC_TN + 2];
+  double As[DC_TK][DC_TM + 4], Bs[DC_TK][DC_TN + 4];   // row stride 68: conflict-free DMMA fragment reads (lane = 4 g + q reads [k0 + q][g])
   double nrm[DC_THREADS / DC_TM][DC_TM];
   double inv[DC_TM];
   double red[DC_WARPS];
@@ -691,6 +693,9 @@ __global__ void __cluster_dims__(DC_CLUSTER, 1, 1) __launch_bounds__(DC_THREADS,
   double* Qold = Qa;
   double* Qnew = Qb;
   EIG_PROF_DECL
+#ifdef GPCSD_EIG_PROF
+  int prof_level = 0;
+#endif
   cluster.sync();
   EIG_PROF2(0)
 
@@ -700,6 +705,7 @@ __global__ void __cluster_dims__(DC_CLUSTER, 1, 1) __launch_bounds__(DC_THREADS,
   for (int L = 1; L <= levels; ++L) {
 #ifdef GPCSD_EIG_PROF
     const long long lvl_t0 = clock64();
+    prof_level = L;
 #endif
     const int nodes = 1 << (levels - L);
     const int mmax = (n + nodes - 1) / nodes;
@@ -903,9 +909,13 @@ __global__ void __cluster_dims__(DC_CLUSTER, 1, 1) __launch_bounds__(DC_THREADS,
         Qnew[(long)g * ldq + col] = out;
       }
     } else {
+      // 64 x 64 output tiles on the FP64 tensor path: 16 warps x (16 x 16) = 2 x 2 DMMA.8x8x4 tiles per warp.  (A first
+      // version with a 2 x 4 register tile per thread read 48 bytes of shared memory per 8 FMAs and was bound by
+      // shared-memory bandwidth: 6.8 k cycles per 16-deep k-step.)
       const int tr = (mmax + DC_TM - 1) / DC_TM, tc = (mmax + DC_TN - 1) / DC_TN;
       const int ntiles = nodes * tr * tc;
-      const int ty = tid >> 4, tx = tid & 15;            // compute mapping: rows 2ty, 2ty+1; cols 4tx .. 4tx+3
+      const int wy = warp >> 2, wx = warp & 3;            // warp tile: rows 16 wy .., cols 16 wx ..
+      const int fg = lane >> 2, fq = lane & 3;            // fragment coordinates
       const int ii = tid & (DC_TM - 1), kq = tid >> 6;    // A-generation mapping: row ii, k-slots kq and kq + 8
       for (int T = rank; T < ntiles; T += DC_CLUSTER) {
         const int p = T / (tr * tc), rem = T - p * (tr * tc);
@@ -916,11 +926,11 @@ __global__ void __cluster_dims__(DC_CLUSTER, 1, 1) __launch_bounds__(DC_THREADS,
         const int org_i = vi ? S.org[a + i0 + ii] : 0;
         const double mu_i = vi ? S.mu[a + i0 + ii] : 1.0;
         double nrm_part = 0.0;
-        double acc[2][4];
+        double acc[2][2][2];
 #pragma unroll
         for (int h = 0; h < 2; ++h)
 #pragma unroll
-          for (int q = 0; q < 4; ++q) acc[h][q] = 0.0;
+          for (int q = 0; q < 2; ++q) acc[h][q][0] = acc[h][q][1] = 0.0;
         const int kend = (i0 < k) ? k : 0;                // tiles made of deflated rows only: no GEMM
         for (int j0 = 0; j0 < kend; j0 += DC_TK) {
 #pragma unroll
@@ -940,12 +950,17 @@ __global__ void __cluster_dims__(DC_CLUSTER, 1, 1) __launch_bounds__(DC_THREADS,
           }
           __syncthreads();
 #pragma unroll
-          for (int kk = 0; kk < DC_TK; ++kk) {
-            const double2 av = *reinterpret_cast<const double2*>(&S.As[kk][2 * ty]);
-            const double2 b0 = *reinterpret_cast<const double2*>(&S.Bs[kk][4 * tx]);
-            const double2 b1 = *reinterpret_cast<const double2*>(&S.Bs[kk][4 * tx + 2]);
-            acc[0][0] += av.x * b0.x; acc[0][1] += av.x * b0.y; acc[0][2] += av.x * b1.x; acc[0][3] += av.x * b1.y;
-            acc[1][0] += av.y * b0.x; acc[1][1] += av.y * b0.y; acc[1][2] += av.y * b1.x; acc[1][3] += av.y * b1.y;
+          for (int ks = 0; ks < DC_TK / 4; ++ks) {
+            double af[2], bf[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              af[h] = S.As[4 * ks + fq][16 * wy + 8 * h + fg];
+              bf[h] = S.Bs[4 * ks + fq][16 * wx + 8 * h + fg];
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+              for (int q = 0; q < 2; ++q) dmma884(acc[h][q][0], acc[h][q][1], af[h], bf[q]);
           }
           __syncthreads();
         }
@@ -960,15 +975,17 @@ __global__ void __cluster_dims__(DC_CLUSTER, 1, 1) __launch_bounds__(DC_THREADS,
         __syncthreads();
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const int r = i0 + 2 * ty + h;
+          const int rl = 16 * wy + 8 * h + fg, r = i0 + rl;
           if (r >= m) continue;
-          const double sc = S.inv[2 * ty + h];
+          const double sc = S.inv[rl];
           const long src = (long)S.row[a + r] * ldq + a;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int col = c0 + 4 * tx + q;
-            if (col < m) Qnew[(long)(a + r) * ldq + a + col] = (r < k) ? acc[h][q] * sc : __ldcg(Qold + src + col);
-          }
+          for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+              const int col = c0 + 16 * wx + 8 * q + 2 * fq + v;
+              if (col < m) Qnew[(long)(a + r) * ldq + a + col] = (r < k) ? acc[h][q][v] * sc : __ldcg(Qold + src + col);
+            }
         }
         __syncthreads();
       }
@@ -1255,6 +1272,10 @@ extern "C" {
 int gpcsd_dbg_prof(long long* out) {
   cudaDeviceSynchronize();
   return (int)cudaMemcpyFromSymbol(out, g_eig_prof, sizeof(long long) * 64);
+}
+int gpcsd_dbg_lp(long long* out) {
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(out, g_eig_lp, sizeof(long long) * 256);
 }
 int gpcsd_dbg_trace(long long* out) {
   cudaDeviceSynchronize();

@@ -20,3 +20,10 @@ for n in (24, 125, 250):
     v = np.array(list(out)[:32], dtype=float)
     print("n=%d cycles by phase:"%n, "  ".join("%s %.0f"%(a,b) for a,b in zip(names, v[:9])), " total %.0f"%v[:9].sum())
     print("     cycles by level:", " ".join("L%d %.0f"%(i, v[16+i]) for i in range(1, 9)))
+    lp = (ctypes.c_longlong*256)()
+    lib.gpcsd_dbg_lp(lp)
+    T = np.array(list(lp), dtype=float).reshape(16, 16)
+    print("     level x phase (cycles; columns: %s)" % " ".join(names[1:8]))
+    for Lv in range(1, 9):
+        if T[Lv, 1:8].sum() > 0:
+            print("     L%d: %s" % (Lv, " ".join("%7.0f" % x for x in T[Lv, 1:8])))
