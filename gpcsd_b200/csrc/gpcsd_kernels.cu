@@ -5,6 +5,8 @@
 
 #include <mutex>
 
+#include <stdlib.h>
+
 #include "common.h"
 #include "dmma_gemm.cuh"
 
@@ -28,6 +30,13 @@ int gp_num_sms() {
   if (sms[dev] == 0) {
     int v = 0;
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    // GPCSD_SM_BUDGET=n: size every full-GPU grid (persistent GEMM, split-K SYRK) for n SMs, leaving the rest to concurrent
+    // latency-bound kernels of ANOTHER model's evaluation (the 8-CTA eigensolver clusters): a persistent kernel that finds
+    // 16 SMs occupied runs its last 16 CTAs as a second wave and takes almost twice as long
+    if (const char* e = getenv("GPCSD_SM_BUDGET")) {
+      const int b = atoi(e);
+      if (b >= 8 && b < v) v = b;
+    }
     sms[dev] = v;
   }
   return sms[dev];
