@@ -1095,7 +1095,7 @@ constexpr int JAC_MAXN = 32;
 __global__ void __launch_bounds__(JAC_MAXN* JAC_MAXN / 2) jacobi_small_kernel(int n, const double* __restrict__ M, long ldm,
                                                                               double* __restrict__ QT, long ldq,
                                                                               double* __restrict__ W, int* __restrict__ info) {
-  __shared__ double A[JAC_MAXN][JAC_MAXN + 1], V[JAC_MAXN][JAC_MAXN + 1];
+  __shared__ double A[JAC_MAXN][JAC_MAXN + 1], V[JAC_MAXN][JAC_MAXN + 1], P[JAC_MAXN][JAC_MAXN + 1];
   __shared__ double cs[JAC_MAXN / 2], sn[JAC_MAXN / 2];
   __shared__ int pp[JAC_MAXN / 2], qq[JAC_MAXN / 2];
   __shared__ int rotated, bad;
@@ -1124,13 +1124,47 @@ __global__ void __launch_bounds__(JAC_MAXN* JAC_MAXN / 2) jacobi_small_kernel(in
   }
   __syncthreads();
   if (!bad && n >= 4) {
-    // Pre-rotation by the orthonormal DCT-II basis C (C[i][k] = sqrt((k ? 2 : 1) / n) cos(pi (2i+1) k / (2n))): it nearly
-    // diagonalises the (near-)Toeplitz covariance factors this solver is fed, so Jacobi starts close to diagonal
+    // Pre-rotation by an orthonormal cosine basis C (DCT-II: C[i][k] = sqrt((k ? 2 : 1) / n) cos(pi (2i+1) k / (2n))): it
+    // nearly diagonalises the (near-)Toeplitz covariance factors this solver is fed, so Jacobi starts close to diagonal
     // (5 sweeps instead of 9-12 on the GP spatial and temporal factors); for any other matrix it is a harmless orthogonal
-    // similarity.  A <- C^T A C, V <- C; T = A C goes through V's storage.
-    for (int e = tid; e < n * n; e += blockDim.x) {
-      const int i = e / n, c = e - i * n;
-      V[i][c] = sqrt((c ? 2.0 : 1.0) / n) * cospi((double)((2 * i + 1) * c) / (double)(2 * n));
+    // similarity.  A <- C^T A C, V <- C; T = A C goes through registers.
+    // Two candidates: DCT-II, and DCT-IV (C[i][k] = sqrt(2/n) cos(pi (2i+1)(2k+1) / (4n))).  The eigenvectors of a symmetric
+    // Toeplitz matrix of order 2n are close to the DCT-II basis of order 2n, whose even members restricted to the first half
+    // are the DCT-II basis of order n and whose odd members are the DCT-IV basis of order n: the symmetric half of the
+    // centrosymmetric split is pre-rotated best by the first, the skew half by the second.  The kernel is not told which
+    // matrix it holds; it keeps the candidate with the larger sum of squared diagonal entries of C^T A C (= the smaller
+    // off-diagonal norm), formed in a fixed order so the choice is reproducible.
+    double score[2];
+    for (int cand = 0; cand < 2; ++cand) {
+      for (int e = tid; e < n * n; e += blockDim.x) {
+        const int i = e / n, c = e - i * n;
+        V[i][c] = cand ? sqrt(2.0 / n) * cospi((double)((2 * i + 1) * (2 * c + 1)) / (double)(4 * n))
+                       : sqrt((c ? 2.0 : 1.0) / n) * cospi((double)((2 * i + 1) * c) / (double)(2 * n));
+      }
+      __syncthreads();
+      for (int e = tid; e < n * n; e += blockDim.x) {       // P[i][c] = C[i][c] * (A C)[i][c]
+        const int i = e / n, c = e - i * n;
+        double a0 = 0.0;
+        for (int l = 0; l < n; ++l) a0 += A[i][l] * V[l][c];
+        P[i][c] = a0 * V[i][c];
+      }
+      __syncthreads();
+      if (tid < n) {                                        // diagonal entry tid of C^T A C
+        double dg = 0.0;
+        for (int i = 0; i < n; ++i) dg += P[i][tid];
+        P[tid][JAC_MAXN] = dg * dg;                         // (padding column)
+      }
+      __syncthreads();
+      double sc = 0.0;
+      for (int i = 0; i < n; ++i) sc += P[i][JAC_MAXN];
+      score[cand] = sc;
+      __syncthreads();
+    }
+    if (!(score[1] > score[0])) {                           // keep DCT-II (V holds DCT-IV now)
+      for (int e = tid; e < n * n; e += blockDim.x) {
+        const int i = e / n, c = e - i * n;
+        V[i][c] = sqrt((c ? 2.0 : 1.0) / n) * cospi((double)((2 * i + 1) * c) / (double)(2 * n));
+      }
     }
     __syncthreads();
     double tacc[4];                                   // T[i][c] = sum_l A[i][l] C[l][c]; each thread owns <= 4 entries
