@@ -87,3 +87,55 @@ def test_channel_fold_identities():
     om2 = synth.perturbed(om, 3, scale=0.2)
     B2 = F.T @ om2.Ks(jitter=False) @ F
     assert np.max(np.abs(B2[:mh, mh:])) < 1e-12 * np.max(np.abs(B2))
+
+
+def _dct2(n):
+    i, k = np.arange(n)[:, None], np.arange(n)[None, :]
+    return np.sqrt(np.where(k == 0, 1.0, 2.0) / n) * np.cos(np.pi * (2 * i + 1) * k / (2 * n))
+
+
+def _dct4(n):
+    i, k = np.arange(n)[:, None], np.arange(n)[None, :]
+    return np.sqrt(2.0 / n) * np.cos(np.pi * (2 * i + 1) * (2 * k + 1) / (4 * n))
+
+
+@pytest.mark.parametrize("m", [12, 25])
+def test_cosine_prerotation_of_the_centrosymmetric_halves(m):
+    """jacobi_small_kernel (gpcsd_eig.cu) pre-rotates by DCT-II or DCT-IV, whichever leaves the larger squared diagonal.
+    Both are orthonormal; the even / odd members of the DCT-II basis of order 2m restricted to the first half ARE the DCT-II /
+    DCT-IV bases of order m (up to the fold's sqrt 2), so the symmetric half of a stationary kernel's centrosymmetric split is
+    closest to diagonal in the first basis and the skew half in the second -- the selection rule picks them that way."""
+    n = 2 * m
+    C2, C4, Cn = _dct2(m), _dct4(m), _dct2(n)
+    assert np.max(np.abs(C2.T @ C2 - np.eye(m))) < 1e-13 and np.max(np.abs(C4.T @ C4 - np.eye(m))) < 1e-13
+    assert np.max(np.abs(np.sqrt(2.0) * Cn[:m, 0::2] - C2)) < 1e-13
+    assert np.max(np.abs(np.sqrt(2.0) * Cn[:m, 1::2] - C4)) < 1e-13
+    t = np.arange(n, dtype=float)
+    dd = t[:, None] - t[None, :]
+    K = 0.5 * np.exp(-0.5 * dd ** 2 / 40.0) + 0.7 * np.exp(-np.abs(dd) / 5.0)
+    J = np.eye(m)[::-1]
+    S, A = K[:m, :m] + K[:m, m:] @ J, K[:m, :m] - K[:m, m:] @ J          # the two halves of F^T K F
+    score = lambda M, C: float(np.sum(np.diag(C.T @ M @ C) ** 2))
+    assert score(S, C2) > score(S, C4)
+    assert score(A, C4) > score(A, C2)
+    off = lambda M, C: np.linalg.norm(C.T @ M @ C - np.diag(np.diag(C.T @ M @ C))) / np.linalg.norm(M)
+    assert off(S, C2) < 0.25 * off(S, np.eye(m)) and off(A, C4) < 0.25 * off(A, np.eye(m))
+
+
+def test_transposed_eight_value_warp_reduction_model():
+    """warp_reduce8_transposed (gpcsd_eig.cu): every stage halves the values a lane carries; lane L ends with the warp total of
+    value L >> 2, and the four lanes of a group agree bit for bit (partners add the same two numbers)."""
+    rng = np.random.default_rng(0)
+    v = rng.standard_normal((32, 8))                       # v[lane][i]
+    lanes = np.arange(32)
+    shfl = lambda x, o: x[lanes ^ o]
+    b4, b3, b2 = (lanes & 16) != 0, (lanes & 8) != 0, (lanes & 4) != 0
+    u = np.stack([np.where(b4, v[:, i + 4], v[:, i]) + shfl(np.where(b4, v[:, i], v[:, i + 4]), 16) for i in range(4)], axis=1)
+    w = np.stack([np.where(b3, u[:, i + 2], u[:, i]) + shfl(np.where(b3, u[:, i], u[:, i + 2]), 8) for i in range(2)], axis=1)
+    r = np.where(b2, w[:, 1], w[:, 0]) + shfl(np.where(b2, w[:, 0], w[:, 1]), 4)
+    r = r + shfl(r, 2)
+    r = r + shfl(r, 1)
+    tot = v.sum(axis=0)
+    for L in range(32):
+        assert abs(r[L] - tot[L >> 2]) < 1e-13
+        assert r[L] == r[L & ~3]
