@@ -9,6 +9,7 @@
 int gp_fail(const char* msg);                 // records msg, returns 1
 int gp_fail_cuda(cudaError_t e, const char* what, int line);
 int gp_num_sms();
+void gp_set_sm_reserve(int n);   // thread-local: SMs left free when this thread sizes full-GPU grids
 
 #define GP_CUDA(expr)                                                  \
   do {                                                                 \

@@ -23,6 +23,12 @@ int gp_fail_cuda(cudaError_t e, const char* what, int line) {
   snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) in `%s` at line %d", (int)e, cudaGetErrorString(e), what, line);
   return 2;
 }
+// SMs the calling thread leaves free when it sizes full-GPU grids (set around the GEMM phase of an evaluation while other
+// models are in flight: their 8-CTA eigensolver clusters and small kernels then find SMs at once instead of at the next
+// kernel boundary of a persistent GEMM)
+static thread_local int tl_sm_reserve = 0;
+void gp_set_sm_reserve(int n) { tl_sm_reserve = n > 0 ? n : 0; }
+
 int gp_num_sms() {
   static int sms[GP_MAX_DEVICES];                  // per device (a process may drive more than one)
   int dev = 0;
@@ -39,7 +45,8 @@ int gp_num_sms() {
     }
     sms[dev] = v;
   }
-  return sms[dev];
+  const int v = sms[dev] - tl_sm_reserve;
+  return v >= 8 ? v : 8;
 }
 
 namespace gpcsd {

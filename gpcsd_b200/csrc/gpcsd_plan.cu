@@ -18,6 +18,7 @@
 
 #include <atomic>
 #include <chrono>
+#include <mutex>
 
 #include <unordered_map>
 #include <vector>
@@ -100,6 +101,15 @@ __global__ void kt_build_kernel(Dims d, const double* __restrict__ theta, const 
 }
 
 // per-block partials ws[r][block][16]; out via sum_cols_kernel
+// marks the end of an evaluation's GEMM phase for the host (gpcsd_plan_loglik_grad's token): counter on the device, copy in
+// host-mapped memory
+__global__ void gemm_done_kernel(unsigned long long* cnt, unsigned long long* host_flag) {
+  const unsigned long long v = *cnt + 1ull;
+  *cnt = v;
+  *reinterpret_cast<volatile unsigned long long*>(host_flag) = v;
+  __threadfence_system();
+}
+
 __global__ void kt_grad_kernel(Dims d, const double* __restrict__ theta, const double* __restrict__ t, const double* __restrict__ Gm,
                                long ldg, long sG, double* __restrict__ ws, long sW) {
   __shared__ double red[8];
@@ -486,6 +496,12 @@ struct Plan {
   cudaStream_t side[2];
   cudaStream_t own;                                   // every evaluation runs here (capturable whatever the caller's stream is)
   cudaEvent_t ev[8];
+  // GEMM-phase token: a one-thread kernel after the last full-GPU kernel bumps gemm_cnt (device) and writes it to a
+  // host-mapped word the host spins on (works inside a replayed graph, where an event-record node would not be seen by a
+  // host-side wait issued before the node has executed)
+  unsigned long long *gemm_flag_host, *gemm_flag_dev, *gemm_cnt;
+  unsigned long long gemm_seq_host;
+  cudaEvent_t ev_p1;                                  // end of phase 1 (recorded on `own` between the two launches)
   // host staging (pinned)
   double *h_theta, *h_out;
   // graphs
@@ -576,6 +592,16 @@ int gpcsd_plan_create(void** out_plan, int dim, int nx, int nt, const double* h_
   if (cudaStreamCreateWithFlags(&p->own, cudaStreamNonBlocking) != cudaSuccess) e = 1;
   for (int k = 0; k < 8; ++k)
     if (cudaEventCreateWithFlags(&p->ev[k], cudaEventDisableTiming) != cudaSuccess) e = 1;
+  p->gemm_flag_host = p->gemm_flag_dev = p->gemm_cnt = nullptr;
+  p->gemm_seq_host = 0;
+  if (cudaEventCreateWithFlags(&p->ev_p1, cudaEventDisableTiming) != cudaSuccess) e = 1;
+  if (cudaHostAlloc((void**)&p->gemm_flag_host, 64, cudaHostAllocMapped) != cudaSuccess) e = 1;
+  if (!e) {
+    *p->gemm_flag_host = 0ull;
+    if (cudaHostGetDevicePointer((void**)&p->gemm_flag_dev, p->gemm_flag_host, 0) != cudaSuccess) e = 1;
+    if (cudaMalloc((void**)&p->gemm_cnt, sizeof(unsigned long long)) != cudaSuccess) e = 1;
+    else if (cudaMemset(p->gemm_cnt, 0, sizeof(unsigned long long)) != cudaSuccess) e = 1;
+  }
   if (e) return fail_plan("plan_create: device / pinned allocation failed");
   *out_plan = p;
   return 0;
@@ -607,6 +633,9 @@ int gpcsd_plan_destroy(void* plan) {
   for (int k = 0; k < 2; ++k) cudaStreamDestroy(p->side[k]);
   cudaStreamDestroy(p->own);
   for (int k = 0; k < 8; ++k) cudaEventDestroy(p->ev[k]);
+  cudaEventDestroy(p->ev_p1);
+  if (p->gemm_flag_host) cudaFreeHost(p->gemm_flag_host);
+  if (p->gemm_cnt) cudaFree(p->gemm_cnt);
   delete p;
   return 0;
 }
@@ -811,8 +840,12 @@ struct Factors {          // caller-supplied eigen-factors (device, R == 1): QsT
   const double *QsT, *ls, *QtT, *lt;
 };
 
-// everything between "theta is on the device" and "out[r] is assembled", on `st` (+ the plan's side streams)
-int enqueue_body(Plan* p, int R, int want_grad, const Factors* fac, cudaStream_t st) {
+// everything between "theta is on the device" and "out[r] is assembled", on `st` (+ the plan's side streams).
+// phase 0: the whole evaluation.  phase 1: up to and including 1/D -- covariance build, eigendecompositions, Z = Qs^T Yf:
+// latency-bound work on a few SMs (plus one HBM-bound pass); phase 2: the rest -- projection, SYRKs, gradient assembly: the
+// kernels that fill the GPU.  The two phases are separate launches (separate CUDA graphs) only when several models are
+// evaluated concurrently, so that a host-side token can keep their GEMM phases from interleaving (gpcsd_plan_loglik_grad).
+int enqueue_body(Plan* p, int R, int want_grad, const Factors* fac, cudaStream_t st, int phase = 0) {
   const pl::Dims& d = p->d;
   const int nx = d.nx, nt = d.nt, G = d.G, N = p->N;
   const long ldx = p->ldx, ldt = p->ldt, ldn = p->ldn, row = (long)nt * ldn, slab = (long)nx * row;
@@ -820,8 +853,10 @@ int enqueue_body(Plan* p, int R, int want_grad, const Factors* fac, cudaStream_t
   const bool use_ssplit = p->s_split && !fac, use_tsplit = p->t_split && !fac, use_tfold = p->t_fold && !fac;
   cudaStream_t sS = p->side[0];
   const int sig_idx = 1 + d.nsp + 2 * d.ntc;
-  p->launches = 0;
+  const double *QsT = fac ? fac->QsT : p->QsT, *ls = fac ? fac->ls : p->ls, *QtT = fac ? fac->QtT : p->QtT, *lt = fac ? fac->lt : p->lt;
+  if (phase != 2) p->launches = 0;
 
+  auto prologue = [&]() -> int {
   pl::zero_kernel<<<1, 256, 0, st>>>(p->res, (long)R * pl::RESW);
   PL_LAUNCH(1);
 
@@ -849,10 +884,8 @@ int enqueue_body(Plan* p, int R, int want_grad, const Factors* fac, cudaStream_t
     PL_LAUNCH(1);
   }
 
-  const double *QsT = p->QsT, *ls = p->ls, *QtT = p->QtT, *lt = p->lt;
   int ninfo = 0;
   if (fac) {
-    QsT = fac->QsT; ls = fac->ls; QtT = fac->QtT; lt = fac->lt;
     if (N > 0) {
       PL_CHECK(gpcsd_dgemm(0, nx, (int)row, nx, QsT, ldx, 0, p->Y, row, 0, p->Z, row, 0, 1, st));
       p->launches += 1;
@@ -942,6 +975,17 @@ int enqueue_body(Plan* p, int R, int want_grad, const Factors* fac, cudaStream_t
   PL_LAUNCH(1);
   pl::eig_D_cols_kernel<<<dim3((nt + 31) / 32, R), 256, 0, st>>>(d, ls, p->rD, ldt, p->rowC, p->rowL, p->colB, p->res);
   PL_LAUNCH(1);
+  return 0;
+  };   // prologue
+  if (phase != 2) PL_CHECK(prologue());
+  if (phase == 1) return 0;
+  // (phase 2 only) a host-visible mark right after the last full-GPU kernel: the host releases the GEMM token there
+  auto mark_gemm_done = [&]() -> int {
+    if (phase != 2) return 0;
+    pl::gemm_done_kernel<<<1, 1, 0, st>>>(p->gemm_cnt, p->gemm_flag_dev);
+    PL_LAUNCH(1);
+    return 0;
+  };
 
   // ---------------- projection A_i = Qt^T Z_i with the fused /D + quadratic form (hot loop gpcsd1d.py:124-126)
   if (N > 0) {
@@ -961,6 +1005,7 @@ int enqueue_body(Plan* p, int R, int want_grad, const Factors* fac, cudaStream_t
     }
   }
 
+  if (!want_grad) PL_CHECK(mark_gemm_done());
   if (want_grad) {
     // The temporal branch (Mt SYRK -> core -> rotation -> <Gt, dKt>) and the spatial branch (Ms/Ns SYRKs -> core -> rotation
     // -> <Gs, dKs>) only share the projected data Bm: they run on two streams (two parallel branches of the captured graph).
@@ -988,6 +1033,7 @@ int enqueue_body(Plan* p, int R, int want_grad, const Factors* fac, cudaStream_t
         p->launches += 2;
       }
     }
+    PL_CHECK(mark_gemm_done());
     pl::grad_core_kernel<<<dim3(blocks256((long)nt * nt), R), 256, 0, st>>>(nt, p->Mt, ldt, nt * ldt, nullptr, lt, p->theta, d.P, sig_idx,
                                                                           p->colB, p->ntot, p->det_frac, p->Xt, ldt, nt * ldt);
     PL_LAUNCH(1);
@@ -1085,9 +1131,9 @@ static void stage_theta(Plan* p, int R, const double* h_theta) {
   }
 }
 
-static int enqueue_on_own(Plan* p, int R, int want_grad, size_t nb) {
+static int enqueue_on_own(Plan* p, int R, int want_grad, size_t nb, int phase = 0) {
   cudaStream_t st = p->own;
-  const long key = (long)R * 2 + (want_grad ? 1 : 0);
+  const long key = ((long)R * 2 + (want_grad ? 1 : 0)) * 4 + phase;
   // (the channel-folded copy Yf is rebuilt eagerly after every new upload; graphs are recorded without that step)
   const bool graphable = p->use_graph && !needs_cusolver(p) && (!(p->s_split || p->t_fold) || p->yf_valid || p->N == 0);
   if (graphable) {
@@ -1101,8 +1147,8 @@ static int enqueue_on_own(Plan* p, int R, int want_grad, size_t nb) {
       cudaGraph_t g = nullptr;
       GP_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
       int e = 0;
-      if (cudaMemcpyAsync(p->theta, p->h_theta, nb, cudaMemcpyHostToDevice, st) != cudaSuccess) e = 1;
-      if (!e) e = enqueue_body(p, R, want_grad, nullptr, st);
+      if (phase != 2 && cudaMemcpyAsync(p->theta, p->h_theta, nb, cudaMemcpyHostToDevice, st) != cudaSuccess) e = 1;
+      if (!e) e = enqueue_body(p, R, want_grad, nullptr, st, phase);
       cudaError_t ce = cudaStreamEndCapture(st, &g);
       if (e || ce != cudaSuccess || !g) {
         if (g) cudaGraphDestroy(g);
@@ -1123,12 +1169,12 @@ static int enqueue_on_own(Plan* p, int R, int want_grad, size_t nb) {
       }
     }
   }
-  GP_CUDA(cudaMemcpyAsync(p->theta, p->h_theta, nb, cudaMemcpyHostToDevice, st));
+  if (phase != 2) GP_CUDA(cudaMemcpyAsync(p->theta, p->h_theta, nb, cudaMemcpyHostToDevice, st));
   static const bool trace = getenv("GPCSD_PLAN_TRACE") != nullptr;
   if (trace) {
     cudaStreamSynchronize(st);
     auto t0 = std::chrono::steady_clock::now();
-    int e = enqueue_body(p, R, want_grad, nullptr, st);
+    int e = enqueue_body(p, R, want_grad, nullptr, st, phase);
     auto t1 = std::chrono::steady_clock::now();
     cudaStreamSynchronize(st);
     auto t2 = std::chrono::steady_clock::now();
@@ -1136,7 +1182,7 @@ static int enqueue_on_own(Plan* p, int R, int want_grad, size_t nb) {
             std::chrono::duration<double, std::micro>(t1 - t0).count(), std::chrono::duration<double, std::micro>(t2 - t1).count());
     if (e) return e;
   } else {
-    PL_CHECK(enqueue_body(p, R, want_grad, nullptr, st));
+    PL_CHECK(enqueue_body(p, R, want_grad, nullptr, st, phase));
   }
   p->warmed[key] += 1;
   return 0;
@@ -1232,8 +1278,137 @@ int gpcsd_plan_set_mailbox(void* plan, void* h_shared, long bytes, int world, in
 }
 
 // One call per evaluation: h_out[r] = [loglik, d loglik / d theta (P), solver flag (0 = ok), checksum pair] for r < R.
+// GEMM-phase token.  An evaluation is a latency-bound prologue on a few SMs (eigendecompositions, ~0.5 ms at configs[1])
+// followed by kernels that fill the GPU (~1 ms).  Two models evaluated concurrently from two host threads should interleave
+// as  A-GEMMs | B-GEMMs | A-GEMMs ...  with each prologue underneath the other model's GEMM phase; left to the hardware
+// scheduler they drift into lock step instead (both GEMM phases share the SMs and finish together, then both prologues run
+// together on an idle GPU: measured period = sum of everything).  So when calls overlap in time, the evaluation is issued
+// as two launches and the second one -- the GEMM phase -- is taken under a process-wide mutex that is released as soon as
+// the phase's last full-GPU kernel has finished (a host-mapped flag written from inside the graph).  Same kernels, same grids:
+// results are bit-identical to the one-launch path.  Single-model processes never see an overlap and keep the one-launch
+// path (the policy lapses four calls after the last overlap).  GPCSD_GEMM_TOKEN=0 / 1 forces the policy.
+static std::mutex g_gemm_token;
+static std::atomic<int> g_inflight{0};
+static std::atomic<long> g_call_seq{0}, g_last_overlap{-(1L << 40)};
+
+// GPCSD_GEMM_RESERVE=n (default 0): SMs the two-phase path leaves free when it sizes full-GPU grids.  With n = 16 a
+// concurrent model's eigensolver clusters and small kernels find SMs at once instead of at the next kernel boundary of a
+// persistent GEMM (+5 % throughput with two models in flight), but grid sizes -- hence the grouping of partial sums --
+// then differ between overlapped and non-overlapped calls, so results are reproducible only to rounding (1e-15), not bit
+// for bit, across concurrency patterns.  Off by default: n_workers = 2 and n_workers = 1 fits stay bit-identical.
+static int gemm_reserve_sms() {
+  static const int v = [] {
+    const char* e = getenv("GPCSD_GEMM_RESERVE");
+    const int n = e ? atoi(e) : 0;
+    return n > 0 && n <= 64 ? n : 0;
+  }();
+  return v;
+}
+
+static int gemm_token_policy() {
+  static const int v = [] {
+    const char* e = getenv("GPCSD_GEMM_TOKEN");
+    return e ? (atoi(e) != 0 ? 1 : 0) : -1;
+  }();
+  return v;
+}
+
+// GPCSD_TOKEN_STATS=1: mean host-side durations of the two-phase path, printed to stderr every 64 calls (developer aid)
+struct TokenStats {
+  std::atomic<long> n{0};
+  std::atomic<long long> enq1{0}, wait_token{0}, enq2{0}, gemm{0}, finish{0};
+};
+static TokenStats g_tstats;
+static bool token_stats_on() {
+  static const bool v = getenv("GPCSD_TOKEN_STATS") != nullptr;
+  return v;
+}
+static inline long long now_ns() {
+  return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+static int loglik_grad_two_phase(Plan* p, int R, const double* h_theta, int want_grad, void* stream) {
+  if (!p->ws) return fail_plan("plan: no LFP / workspace bound (gpcsd_plan_set_lfp)");
+  if (R < 1 || R > p->Rmax) return fail_plan("plan: restart count out of range");
+  cudaStream_t caller = (cudaStream_t)stream;
+  const size_t nb = (size_t)R * (p->d.P + 2) * sizeof(double);
+  stage_theta(p, R, h_theta);
+  GP_CUDA(cudaEventRecord(p->ev[6], caller));
+  GP_CUDA(cudaStreamWaitEvent(p->own, p->ev[6], 0));
+  const bool stats = token_stats_on();
+  const long long t0s = stats ? now_ns() : 0;
+  gp_set_sm_reserve(gemm_reserve_sms());              // (see below; the prologue's one full-GPU pass, Z = Qs^T Yf, included)
+  const int e1 = enqueue_on_own(p, R, want_grad, nb, 1);
+  gp_set_sm_reserve(0);
+  if (e1) return e1;
+  // the token is only asked for once this model's own prologue is off the GPU: holding it while the GEMM phase still
+  // waits (in stream order) for the eigendecompositions would keep the other model's GEMMs out for nothing
+  GP_CUDA(cudaEventRecord(p->ev_p1, p->own));
+  GP_CUDA(cudaEventSynchronize(p->ev_p1));
+  const long long t1s = stats ? now_ns() : 0;
+  std::lock_guard<std::mutex> token(g_gemm_token);
+  const long long t2s = stats ? now_ns() : 0;
+  // optionally the GEMM phase leaves SMs (16 = two 8-CTA clusters) to the other models' prologues: a persistent GEMM on all
+  // SMs makes every kernel of a concurrent eigensolve wait for its next kernel boundary (measured: prologue 0.57 -> 0.84 ms)
+  gp_set_sm_reserve(gemm_reserve_sms());
+  const int e2 = enqueue_on_own(p, R, want_grad, nb, 2);
+  gp_set_sm_reserve(0);
+  if (e2) return e2;
+  const long long t3s = stats ? now_ns() : 0;
+  GP_CUDA(cudaEventRecord(p->ev[7], p->own));
+  GP_CUDA(cudaStreamWaitEvent(caller, p->ev[7], 0));
+  // wait until the GEMM phase is off the GPU: then the next model may start its own
+  const unsigned long long want = ++p->gemm_seq_host;
+  const volatile unsigned long long* flag = p->gemm_flag_host;
+  const auto t0 = std::chrono::steady_clock::now();
+  unsigned long spins = 0;
+  while (*flag < want) {
+    if ((++spins & 0xFFFF) == 0) {
+      const cudaError_t qe = cudaStreamQuery(p->own);
+      if (qe == cudaSuccess && *flag < want) return fail_plan("plan: the evaluation finished without marking its GEMM phase");
+      if (qe != cudaSuccess && qe != cudaErrorNotReady) return gp_fail_cuda(qe, "waiting for the GEMM phase", __LINE__);
+      if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 120.0)
+        return fail_plan("plan: timed out waiting for the GEMM phase");
+    }
+  }
+  if (stats) {
+    const long long t4s = now_ns();
+    g_tstats.enq1 += t1s - t0s;
+    g_tstats.wait_token += t2s - t1s;
+    g_tstats.enq2 += t3s - t2s;
+    g_tstats.gemm += t4s - t3s;
+  }
+  return 0;
+}
+
 int gpcsd_plan_loglik_grad(void* plan, int R, const double* h_theta, int want_grad, double* h_out, void* stream) {
-  PL_CHECK(gpcsd_plan_enqueue(plan, R, h_theta, want_grad, stream));
+  if (!plan) return fail_plan("null plan");
+  const long seq = ++g_call_seq;
+  struct Inflight {
+    Inflight() { n = ++g_inflight; }
+    ~Inflight() { --g_inflight; }
+    int n;
+  } guard;
+  if (guard.n > 1) g_last_overlap.store(seq);
+  const int policy = gemm_token_policy();
+  const bool two_phase = policy == 1 || (policy < 0 && seq - g_last_overlap.load() < 4);
+  if (two_phase) {
+    PL_CHECK(loglik_grad_two_phase((Plan*)plan, R, h_theta, want_grad, stream));
+  } else {
+    PL_CHECK(gpcsd_plan_enqueue(plan, R, h_theta, want_grad, stream));
+  }
+  if (two_phase && token_stats_on()) {
+    const long long t0f = now_ns();
+    const int e = gpcsd_plan_finish(plan, R, h_out, stream);
+    g_tstats.finish += now_ns() - t0f;
+    const long n = ++g_tstats.n;
+    if (n % 64 == 0) {
+      fprintf(stderr, "[token stats] %ld calls: enqueue-1 %.1f us, wait for token %.1f us, enqueue-2 %.1f us, until GEMM phase done %.1f us, until result %.1f us\n",
+              n, 1e-3 * g_tstats.enq1 / n, 1e-3 * g_tstats.wait_token / n, 1e-3 * g_tstats.enq2 / n, 1e-3 * g_tstats.gemm / n,
+              1e-3 * g_tstats.finish / n);
+    }
+    return e;
+  }
   return gpcsd_plan_finish(plan, R, h_out, stream);
 }
 

@@ -107,3 +107,57 @@ def test_plan_eigensolver_failure_flag(cuda_lib):
     assert np.isfinite(ll[0]) and ll[0] == ll[2]
     with pytest.raises(np.linalg.LinAlgError):
         eng.loglik_grad(bad)
+
+
+_TWO_PHASE_SCRIPT = r"""
+import json, os, sys
+sys.path.insert(0, os.path.join(%(root)r, "tests")); sys.path.insert(0, %(root)r)
+import numpy as np
+from helpers import engine_from_oracle, hp_from_oracle
+from oracle import gpcsd_oracle as O, synth
+x, t = synth.geometry_1d(24, 130)
+om = synth.model_1d(x, t, sig2n=1e-2 * np.exp(0.3 * np.random.default_rng(0).standard_normal(24)))
+lfp = synth.matched_lfp(om, 40, 7)
+eng, _ = engine_from_oracle(om, lfp)
+rng = np.random.default_rng(3)
+tp = O.pack_tparams(om)
+hps = [hp_from_oracle(O.unpack_tparams(om, tp + 0.1 * rng.standard_normal(tp.shape))) for _ in range(3)]
+out = []
+for rep in range(4):                                     # eager, capture, replay of whichever path the policy selects
+    ll, g = eng.loglik_grad(hps[0])
+    llb, gb, flag = eng.loglik_grad_batch(hps)
+    out.append({"ll": float(ll), "g": np.asarray(g).tolist(), "llb": np.asarray(llb).tolist(), "gb": np.asarray(gb).tolist()})
+print("RESULT " + json.dumps(out))
+"""
+
+
+def test_two_phase_token_path_matches_single_launch(cuda_lib, tmp_path):
+    """gpcsd_plan_loglik_grad issues the evaluation as two launches (prologue | GEMM phase under the process-wide token) when
+    calls from several host threads overlap; GPCSD_GEMM_TOKEN=1 forces that path.  Same kernels, same grids: bit-identical to
+    the single-launch path.  With GPCSD_GEMM_RESERVE=16 the GEMM phase is sized for all SMs but 16 (partial sums are grouped
+    differently): equal to rounding.  Eager / captured / replayed launches of every path agree bit for bit."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "two_phase.py"
+    script.write_text(_TWO_PHASE_SCRIPT % {"root": root})
+    res = {}
+    for mode in ("0", "1", "reserve"):
+        env = dict(os.environ, GPCSD_GEMM_TOKEN="0" if mode == "0" else "1", GPCSD_GEMM_RESERVE="16" if mode == "reserve" else "0")
+        p = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stderr[-2000:]
+        line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")][-1]
+        res[mode] = json.loads(line[len("RESULT "):])
+    for mode in ("0", "1", "reserve"):
+        for rep in res[mode][1:]:
+            assert rep == res[mode][0]                    # eager == captured == replayed, bit for bit
+    assert res["1"][0] == res["0"][0]                     # two launches, same grids: bit-identical
+    a, b = res["0"][0], res["reserve"][0]
+    assert abs(a["ll"] - b["ll"]) <= 1e-13 * abs(a["ll"])
+    ga, gb = np.array(a["g"]), np.array(b["g"])
+    # (per-electrode noise: the (R, ell) components amplify rounding ~1e5 x, DESIGN.md section 6)
+    assert np.max(np.abs(ga - gb) / np.maximum(np.abs(ga), 1e-300)) < 1e-8
+    assert np.max(np.abs(np.array(a["llb"]) - np.array(b["llb"])) / np.abs(np.array(a["llb"]))) <= 1e-13
+    assert np.max(np.abs(np.array(a["gb"]) - np.array(b["gb"])) / np.maximum(np.abs(np.array(a["gb"])), 1e-300)) < 1e-8
