@@ -856,6 +856,40 @@ int enqueue_body(Plan* p, int R, int want_grad, const Factors* fac, cudaStream_t
   const double *QsT = fac ? fac->QsT : p->QsT, *ls = fac ? fac->ls : p->ls, *QtT = fac ? fac->QtT : p->QtT, *lt = fac ? fac->lt : p->lt;
   if (phase != 2) p->launches = 0;
 
+  // Z = Qs^T Yf for all trials (the one HBM-bound full-GPU pass that does not need Qt).  One-launch evaluations issue it on
+  // the spatial side stream underneath the temporal eigensolve; two-phase evaluations (concurrent models) issue it at the
+  // head of the GEMM phase instead: squeezed onto the SMs a concurrent model's persistent GEMM leaves free it took ~0.4 ms.
+  auto enqueue_Z = [&](cudaStream_t zs) -> int {
+    if (N > 0) {
+      // The symmetry folds act on the DATA axes and commute with the projections: the LFP is moved to the evaluation basis
+      // (channel fold for reflection-symmetric geometries, centrosymmetric time fold on uniform grids) ONCE per upload, so
+      // Z = Qs^T Y comes out directly in the folded time basis -- no per-evaluation fold pass over the trial data.
+      if ((p->s_split || p->t_fold) && !p->yf_valid) {
+        if (p->s_split && p->t_fold) {
+          PL_CHECK(gpcsd_pairsym_fold(nx, p->ra, p->rb, row, p->Y, p->Z, zs));       // Z (restart 0) is free here: scratch
+          PL_CHECK(gpcsd_centro_fold(nx, nt, ldn, p->Z, p->Yf, zs));
+          p->launches += 2;
+        } else if (p->s_split) {
+          PL_CHECK(gpcsd_pairsym_fold(nx, p->ra, p->rb, row, p->Y, p->Yf, zs));
+          p->launches += 1;
+        } else {
+          PL_CHECK(gpcsd_centro_fold(nx, nt, ldn, p->Y, p->Yf, zs));
+          p->launches += 1;
+        }
+      }
+      const double* Ysrc = (p->s_split || p->t_fold) ? p->Yf : p->Y;
+      if (use_ssplit) {
+        const int m = p->sm;
+        const long ldm = p->sldm, sM = (long)m * ldm;
+        PL_CHECK(gemm_shared_b(p, R, m, (int)row, m, p->uS, ldm, sM, Ysrc, row, p->Z, row, slab, zs));
+        PL_CHECK(gemm_shared_b(p, R, m, (int)row, m, p->uS + R * sM, ldm, sM, Ysrc + (long)m * row, row, p->Z + (long)m * row, row, slab, zs));
+      } else {
+        PL_CHECK(gemm_shared_b(p, R, nx, (int)row, nx, p->QsT, ldx, nx * ldx, Ysrc, row, p->Z, row, slab, zs));
+      }
+    }
+    return 0;
+  };
+
   auto prologue = [&]() -> int {
   pl::zero_kernel<<<1, 256, 0, st>>>(p->res, (long)R * pl::RESW);
   PL_LAUNCH(1);
@@ -910,33 +944,7 @@ int enqueue_body(Plan* p, int R, int want_grad, const Factors* fac, cudaStream_t
       PL_CHECK(eigh_stack(p, nx, R, p->Ks, ldx, p->QsT, p->ls, p->eigws, p->info + ninfo, sS));
       ninfo += R;
     }
-    if (N > 0) {
-      // The symmetry folds act on the DATA axes and commute with the projections: the LFP is moved to the evaluation basis
-      // (channel fold for reflection-symmetric geometries, centrosymmetric time fold on uniform grids) ONCE per upload, so
-      // Z = Qs^T Y comes out directly in the folded time basis -- no per-evaluation fold pass over the trial data.
-      if ((p->s_split || p->t_fold) && !p->yf_valid) {
-        if (p->s_split && p->t_fold) {
-          PL_CHECK(gpcsd_pairsym_fold(nx, p->ra, p->rb, row, p->Y, p->Z, sS));       // Z (restart 0) is free here: scratch
-          PL_CHECK(gpcsd_centro_fold(nx, nt, ldn, p->Z, p->Yf, sS));
-          p->launches += 2;
-        } else if (p->s_split) {
-          PL_CHECK(gpcsd_pairsym_fold(nx, p->ra, p->rb, row, p->Y, p->Yf, sS));
-          p->launches += 1;
-        } else {
-          PL_CHECK(gpcsd_centro_fold(nx, nt, ldn, p->Y, p->Yf, sS));
-          p->launches += 1;
-        }
-      }
-      const double* Ysrc = (p->s_split || p->t_fold) ? p->Yf : p->Y;
-      if (use_ssplit) {
-        const int m = p->sm;
-        const long ldm = p->sldm, sM = (long)m * ldm;
-        PL_CHECK(gemm_shared_b(p, R, m, (int)row, m, p->uS, ldm, sM, Ysrc, row, p->Z, row, slab, sS));
-        PL_CHECK(gemm_shared_b(p, R, m, (int)row, m, p->uS + R * sM, ldm, sM, Ysrc + (long)m * row, row, p->Z + (long)m * row, row, slab, sS));
-      } else {
-        PL_CHECK(gemm_shared_b(p, R, nx, (int)row, nx, p->QsT, ldx, nx * ldx, Ysrc, row, p->Z, row, slab, sS));
-      }
-    }
+    if (phase == 0) PL_CHECK(enqueue_Z(sS));
     GP_CUDA(cudaEventRecord(p->ev[1], sS));
 
     // ---------------- temporal covariance + eigen-factors (main stream)
@@ -979,6 +987,7 @@ int enqueue_body(Plan* p, int R, int want_grad, const Factors* fac, cudaStream_t
   };   // prologue
   if (phase != 2) PL_CHECK(prologue());
   if (phase == 1) return 0;
+  if (phase == 2) PL_CHECK(enqueue_Z(st));
   // (phase 2 only) a host-visible mark right after the last full-GPU kernel: the host releases the GEMM token there
   auto mark_gemm_done = [&]() -> int {
     if (phase != 2) return 0;
