@@ -1047,21 +1047,47 @@ __global__ void __launch_bounds__(32 * BT_WARPS) backtransform_kernel(int n, con
     const int j = lane + 32 * m;
     x[m] = (j < n) ? XT[(long)vec * ldx + j] : 0.0;
   }
-  for (int k = n - 3; k >= 0; --k) {
-    const double t = __ldg(tau + k);
-    if (t == 0.0) continue;
+  // The reflector rows are read two steps ahead of their use (registers): one step is a dot product, a 5-stage warp
+  // reduction and an axpy (~300 cycles), an L2 round trip for the row is longer than that, and nothing but the loads is
+  // independent of the previous step.  (Entries j <= k+1 of row k hold no reflector data: masked at use.)
+  constexpr int NRB = TRD_MAXN / 32;
+  auto load_row = [&](int k, double (&r)[NRB], double& t) {
+    if (k < 0) return;
     const double* vk = V + (long)k * ldv;
-    double vv[TRD_MAXN / 32];
-    double dot = 0.0;
+    t = __ldg(tau + k);
 #pragma unroll
-    for (int m = 0; m < TRD_MAXN / 32; ++m) {
+    for (int m = 0; m < NRB; ++m) {
       const int j = lane + 32 * m;
-      vv[m] = (j > k + 1 && j < n) ? __ldg(vk + j) : ((j == k + 1) ? 1.0 : 0.0);
-      dot += vv[m] * x[m];
+      r[m] = (j < n) ? __ldg(vk + j) : 0.0;
     }
-    dot = warp_sum(dot) * t;
+  };
+  double ra[NRB], rb[NRB], rc[NRB], ta = 0.0, tb = 0.0, tc = 0.0;
 #pragma unroll
-    for (int m = 0; m < TRD_MAXN / 32; ++m) x[m] -= dot * vv[m];
+  for (int m = 0; m < NRB; ++m) ra[m] = rb[m] = rc[m] = 0.0;
+  load_row(n - 3, ra, ta);
+  load_row(n - 4, rb, tb);
+  for (int k = n - 3; k >= 0; --k) {
+    load_row(k - 2, rc, tc);
+    if (ta != 0.0) {
+      double vv[NRB];
+      double dot0 = 0.0, dot1 = 0.0;
+#pragma unroll
+      for (int m = 0; m < NRB; ++m) {
+        const int j = lane + 32 * m;
+        vv[m] = (j > k + 1) ? ra[m] : ((j == k + 1) ? 1.0 : 0.0);
+        if (m & 1) dot1 += vv[m] * x[m]; else dot0 += vv[m] * x[m];
+      }
+      const double dot = warp_sum(dot0 + dot1) * ta;
+#pragma unroll
+      for (int m = 0; m < NRB; ++m) x[m] -= dot * vv[m];
+    }
+#pragma unroll
+    for (int m = 0; m < NRB; ++m) {
+      ra[m] = rb[m];
+      rb[m] = rc[m];
+    }
+    ta = tb;
+    tb = tc;
   }
 #pragma unroll
   for (int m = 0; m < TRD_MAXN / 32; ++m) {
