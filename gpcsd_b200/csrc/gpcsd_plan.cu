@@ -1400,7 +1400,11 @@ int gpcsd_plan_loglik_grad(void* plan, int R, const double* h_theta, int want_gr
   } guard;
   if (guard.n > 1) g_last_overlap.store(seq);
   const int policy = gemm_token_policy();
-  const bool two_phase = policy == 1 || (policy < 0 && seq - g_last_overlap.load() < 4);
+  // (not right after a new upload: that evaluation refolds the LFP and is issued kernel by kernel, not as a graph -- its
+  //  ~50 launches are best queued in one go behind the upload it waits for anyway)
+  const Plan* pp = (const Plan*)plan;
+  const bool fresh_upload = (pp->s_split || pp->t_fold) && !pp->yf_valid && pp->N > 0;
+  const bool two_phase = !fresh_upload && (policy == 1 || (policy < 0 && seq - g_last_overlap.load() < 4));
   if (two_phase) {
     PL_CHECK(loglik_grad_two_phase((Plan*)plan, R, h_theta, want_grad, stream));
   } else {
