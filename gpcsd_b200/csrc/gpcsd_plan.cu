@@ -502,6 +502,11 @@ struct Plan {
   unsigned long long *gemm_flag_host, *gemm_flag_dev, *gemm_cnt;
   unsigned long long gemm_seq_host;
   cudaEvent_t ev_p1;                                  // end of phase 1 (recorded on `own` between the two launches)
+  // token ordering (two-phase path): creation index of the plan, evaluations issued, "prologue in flight, token not yet taken"
+  // (plain fields, read and written under g_registry_mutex)
+  long model_index;
+  long eval_count;
+  int in_prologue;
   // host staging (pinned)
   double *h_theta, *h_out;
   // graphs
@@ -516,6 +521,51 @@ struct Plan {
   unsigned long long* seq_dev;
   unsigned long long seq_host;
 };
+
+// Registry of live plans for the token's grant order.  Ranks of a trial-sharded job must take the token in the SAME order
+// (an evaluation only completes when every rank has finished it: if rank X runs model A's GEMM phase first and rank Y model
+// B's, both models complete only after both phases everywhere and their next prologues start together -- the lock step the
+// token exists to break).  Arrival order is timing; (evaluations issued, creation index) is the same on every rank of an
+// SPMD job.  So a requester defers to any other plan whose prologue is in flight and whose (count, index) is smaller: that
+// plan is certain to ask for the token within its prologue's duration, and it will not defer back.
+static std::mutex g_registry_mutex;
+static Plan* g_registry[64];
+static long g_plans_created = 0;
+static void registry_add(Plan* p) {
+  std::lock_guard<std::mutex> lk(g_registry_mutex);
+  p->model_index = g_plans_created++;
+  p->eval_count = 0;
+  p->in_prologue = 0;
+  for (auto& slot : g_registry)
+    if (!slot) {
+      slot = p;
+      return;
+    }
+}
+static void registry_remove(Plan* p) {
+  std::lock_guard<std::mutex> lk(g_registry_mutex);
+  for (auto& slot : g_registry)
+    if (slot == p) slot = nullptr;
+}
+static void set_token_state(Plan* p, int v) {
+  std::lock_guard<std::mutex> lk(g_registry_mutex);
+  p->in_prologue = v;
+}
+static long next_eval_count(Plan* p) {
+  std::lock_guard<std::mutex> lk(g_registry_mutex);
+  return ++p->eval_count;
+}
+// true while some other plan with a smaller (evaluations issued, creation index) has its prologue in flight
+static bool must_defer(const Plan* p, long my_count) {
+  std::lock_guard<std::mutex> lk(g_registry_mutex);
+  for (Plan* q : g_registry) {
+    if (!q || q == p || !q->in_prologue) continue;
+    const long qc = q->eval_count;
+    if (qc < my_count || (qc == my_count && q->model_index < p->model_index)) return true;
+  }
+  return false;
+}
+
 
 int fail_plan(const char* m) { return gp_fail(m); }
 
@@ -536,6 +586,7 @@ int gpcsd_plan_create(void** out_plan, int dim, int nx, int nt, const double* h_
   const int Gtot = dim == 1 ? G1 : G1 * G2;
   if (Gtot & 1) return fail_plan("plan_create: the (last) quadrature axis must be padded to an even length");
   Plan* p = new Plan();
+  registry_add(p);
   memset(&p->d, 0, sizeof(p->d));
   p->d.dim = dim; p->d.nx = nx; p->d.nt = nt; p->d.G = Gtot; p->d.G1 = G1; p->d.G2 = dim == 2 ? G2 : 0;
   p->d.ntc = ntc; p->d.nsig = n_sig2n; p->d.nsp = dim == 1 ? 1 : 2;
@@ -624,6 +675,7 @@ static void drop_graphs(Plan* p) {
 int gpcsd_plan_destroy(void* plan) {
   if (!plan) return 0;
   Plan* p = (Plan*)plan;
+  registry_remove(p);
   drop_graphs(p);
   cudaFree(p->x); cudaFree(p->t); cudaFree(p->g1); cudaFree(p->w1); cudaFree(p->g2); cudaFree(p->w2);
   cudaFree(p->ra); cudaFree(p->rb);
@@ -1336,7 +1388,7 @@ static inline long long now_ns() {
   return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-static int loglik_grad_two_phase(Plan* p, int R, const double* h_theta, int want_grad, void* stream) {
+static int loglik_grad_two_phase(Plan* p, int R, const double* h_theta, int want_grad, void* stream, long my_count) {
   if (!p->ws) return fail_plan("plan: no LFP / workspace bound (gpcsd_plan_set_lfp)");
   if (R < 1 || R > p->Rmax) return fail_plan("plan: restart count out of range");
   cudaStream_t caller = (cudaStream_t)stream;
@@ -1346,6 +1398,11 @@ static int loglik_grad_two_phase(Plan* p, int R, const double* h_theta, int want
   GP_CUDA(cudaStreamWaitEvent(p->own, p->ev[6], 0));
   const bool stats = token_stats_on();
   const long long t0s = stats ? now_ns() : 0;
+  struct Prologue {                                   // "in flight, token not yet taken" (cleared on every exit path)
+    explicit Prologue(Plan* p_) : p(p_) { set_token_state(p, 1); }
+    ~Prologue() { set_token_state(p, 0); }
+    Plan* p;
+  } prologue_mark(p);
   gp_set_sm_reserve(gemm_reserve_sms());              // (see below; the prologue's one full-GPU pass, Z = Qs^T Yf, included)
   const int e1 = enqueue_on_own(p, R, want_grad, nb, 1);
   gp_set_sm_reserve(0);
@@ -1355,7 +1412,15 @@ static int loglik_grad_two_phase(Plan* p, int R, const double* h_theta, int want
   GP_CUDA(cudaEventRecord(p->ev_p1, p->own));
   GP_CUDA(cudaEventSynchronize(p->ev_p1));
   const long long t1s = stats ? now_ns() : 0;
+  {   // rank-consistent grant order (bounded: a prologue lasts ~1 ms; 20 ms means the other thread is not coming)
+    const auto td = std::chrono::steady_clock::now();
+    unsigned long spins = 0;
+    while (must_defer(p, my_count)) {
+      if ((++spins & 0x3FF) == 0 && std::chrono::duration<double>(std::chrono::steady_clock::now() - td).count() > 0.02) break;
+    }
+  }
   std::lock_guard<std::mutex> token(g_gemm_token);
+  set_token_state(p, 0);
   const long long t2s = stats ? now_ns() : 0;
   // optionally the GEMM phase leaves SMs (16 = two 8-CTA clusters) to the other models' prologues: a persistent GEMM on all
   // SMs makes every kernel of a concurrent eigensolve wait for its next kernel boundary (measured: prologue 0.57 -> 0.84 ms)
@@ -1405,8 +1470,9 @@ int gpcsd_plan_loglik_grad(void* plan, int R, const double* h_theta, int want_gr
   const Plan* pp = (const Plan*)plan;
   const bool fresh_upload = (pp->s_split || pp->t_fold) && !pp->yf_valid && pp->N > 0;
   const bool two_phase = !fresh_upload && (policy == 1 || (policy < 0 && seq - g_last_overlap.load() < 4));
+  const long my_count = next_eval_count((Plan*)plan);       // every call, whichever path: the same on every rank of an SPMD job
   if (two_phase) {
-    PL_CHECK(loglik_grad_two_phase((Plan*)plan, R, h_theta, want_grad, stream));
+    PL_CHECK(loglik_grad_two_phase((Plan*)plan, R, h_theta, want_grad, stream, my_count));
   } else {
     PL_CHECK(gpcsd_plan_enqueue(plan, R, h_theta, want_grad, stream));
   }
