@@ -279,7 +279,11 @@ int gpcsd_plan_set_graph(void* plan, int enable);               /* CUDA-graph re
 /* h_theta [R][P] host -> h_out [R][P+4] host: loglik, d loglik / d theta (P entries; zeros when want_grad == 0), eigensolver
  * flag (0 = ok; numpy raises LinAlgError otherwise), and a hyperparameter checksum pair (c*f, c^2*f) for rank-consistency
  * checks after an all-reduce.  gpcsd_plan_loglik_grad = gpcsd_plan_enqueue + gpcsd_plan_finish; trial-sharded callers
- * all-reduce gpcsd_plan_device_result() ([R][P+4], on `stream`) between the two.  One evaluation in flight per plan. */
+ * all-reduce gpcsd_plan_device_result() ([R][P+4], on `stream`) between the two.  One evaluation in flight per plan.
+ * When calls for DIFFERENT plans overlap in time (several models evaluated from several host threads) gpcsd_plan_loglik_grad
+ * issues the evaluation as two launches -- covariances + eigendecompositions, then the kernels that fill the GPU under a
+ * process-wide token -- so that one model's latency-bound prologue runs underneath another model's GEMMs; results are
+ * bit-identical to the one-launch form (GPCSD_GEMM_TOKEN, GPCSD_GEMM_RESERVE). */
 int gpcsd_plan_loglik_grad(void* plan, int R, const double* h_theta, int want_grad, double* h_out, void* stream);
 int gpcsd_plan_enqueue(void* plan, int R, const double* h_theta, int want_grad, void* stream);
 int gpcsd_plan_finish(void* plan, int R, double* h_out, void* stream);
