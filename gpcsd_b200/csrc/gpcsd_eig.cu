@@ -1,22 +1,31 @@
-// In-house symmetric eigensolver for orders 3..256 (FP64, full eigen-decomposition with vectors), one 8-CTA thread-block
-// cluster per matrix, batched over matrices.
+// In-house symmetric eigensolvers for orders 1..256 (FP64, full eigen-decomposition with vectors), batched over matrices.
 //
 // cuSOLVER syevd spends ~1.2 ms + 8 us per column in a latency-bound tridiagonalisation (profiles/r01_eigh_options.md) and
 // it is the Amdahl term of every GPCSD evaluation (the 250-order halves of a 500-point temporal factor, the 192-order halves
-// of a Neuropixels spatial factor, comp_eig_D utility_functions.py:44-64).  Three kernels replace it:
+// of a Neuropixels spatial factor, comp_eig_D utility_functions.py:44-64).
 //
-//   1. tridiag_cluster_kernel   Householder tridiagonalisation M = H T H^T.  Every matrix row lives in the registers of one
-//                               warp (row i in CTA i mod 8); ONE exchange per column through distributed shared memory
-//                               (st.async / bulk copies that complete transaction bytes on an mbarrier of the receiver):
-//                               no cluster barrier in the loop.  ~2.1 us per column.
+// Orders <= 32: jacobi_small_kernel, one CTA per matrix -- parallel cyclic Jacobi in shared memory after a pre-rotation by
+// the DCT-II or DCT-IV basis (whichever leaves the smaller off-diagonal norm: the two halves of a centrosymmetric Toeplitz
+// factor are nearly diagonal in exactly these bases).  ~80-140 us whatever the batch (profiles/r02i_small_eigh.md).
+//
+// Orders 33..256: one 8-CTA thread-block cluster per matrix, three kernels (profiles/r02n_eigensolver.md):
+//
+//   1. tridiag_cluster_kernel<NR>  Householder tridiagonalisation M = H T H^T.  Every matrix row lives in the registers of
+//                               one warp (row i in CTA i mod 8, up to 4 rows per warp); ONE exchange per column through
+//                               distributed shared memory in which no warp is special: every row warp sends the raw pair
+//                               ((A x)_i, a_{i,k+1}) with 16-byte st.async stores that complete transaction bytes on an
+//                               mbarrier of the receiver -- no cluster barrier in the loop.  The reflector stays
+//                               unnormalised, so its rsqrt / reciprocal chain runs next to the next column's reduction;
+//                               the body is specialised on the register-block count and the first live block.
+//                               ~1.08 us per column at n = 250, 0.8 us at n <= 64.
 //   2. dc_cluster_kernel        Cuppen divide and conquer on T down to 1x1 leaves (ceil(log2 n) merge levels): per merge
 //                               LAPACK-style deflation, secular roots by a bracketed two-pole rational iteration (1 to 32
 //                               lanes per root depending on the merge size), Gu-Eisenstat recomputation of z for numerically
-//                               orthogonal eigenvectors, eigenvector update as a shared-memory tiled GEMM whose A operand
-//                               (z_j / (d_j - lambda_i)) is generated on the fly.  Bottom levels (at least one merge node
-//                               per CTA) run CTA-locally; above, small per-merge vectors are broadcast through distributed
-//                               shared memory and the eigenvector matrices ping-pong through L2.  The numerical core
-//                               (dc_core.h) also compiles for the host: tests/test_dc_host.py checks it against LAPACK
+//                               orthogonal eigenvectors, eigenvector update as a shared-memory tiled DMMA GEMM whose A
+//                               operand (z_j / (d_j - lambda_i)) is generated on the fly.  Bottom levels (at least one
+//                               merge node per CTA) run CTA-locally; above, small per-merge vectors are broadcast through
+//                               distributed shared memory and the eigenvector matrices ping-pong through L2.  The numerical
+//                               core (dc_core.h) also compiles for the host: tests/test_dc_host.py checks it against LAPACK
 //                               without a GPU.
 //   3. back-transformation      n < 97: backtransform_kernel applies the reflectors to every eigenvector (one warp per
 //                               vector).  n >= 97: the top-level merge and the back-transformation are two full-GPU DMMA
