@@ -586,7 +586,6 @@ int gpcsd_plan_create(void** out_plan, int dim, int nx, int nt, const double* h_
   const int Gtot = dim == 1 ? G1 : G1 * G2;
   if (Gtot & 1) return fail_plan("plan_create: the (last) quadrature axis must be padded to an even length");
   Plan* p = new Plan();
-  registry_add(p);
   memset(&p->d, 0, sizeof(p->d));
   p->d.dim = dim; p->d.nx = nx; p->d.nt = nt; p->d.G = Gtot; p->d.G1 = G1; p->d.G2 = dim == 2 ? G2 : 0;
   p->d.ntc = ntc; p->d.nsig = n_sig2n; p->d.nsp = dim == 1 ? 1 : 2;
@@ -654,6 +653,7 @@ int gpcsd_plan_create(void** out_plan, int dim, int nx, int nt, const double* h_
     else if (cudaMemset(p->gemm_cnt, 0, sizeof(unsigned long long)) != cudaSuccess) e = 1;
   }
   if (e) return fail_plan("plan_create: device / pinned allocation failed");
+  registry_add(p);                    // (only plans handed to the caller take part in the token's grant order)
   *out_plan = p;
   return 0;
 }
