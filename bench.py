@@ -215,7 +215,7 @@ def workload_config(n_gpus):
     return {"workload": "BASELINE.json configs[1]: GPCSD1D auditory-shaped, 2 probes x 24 ch x 500 t x 2000 trials per GPU, "
                         "per-electrode noise (P=30), a=-200 b=2600 ngl=100, loglik+grad",
             "eval_unit": "one loglik+grad over a 24x500x2000 trial block", "trials_per_gpu_per_probe": NTRIALS,
-            "global_trials_per_probe": NTRIALS * n_gpus, "parallelism": "trial-shard x%d, 1 allreduce of the raw result vector (~70 f64) per eval; the 2 probes run concurrently on 2 host threads / streams, started half an evaluation apart" % n_gpus,
+            "global_trials_per_probe": NTRIALS * n_gpus, "parallelism": "trial-shard x%d, 1 allreduce of the raw result vector (~70 f64) per eval; the 2 probes run concurrently on 2 host threads / streams; their GEMM phases alternate under the library's token (DESIGN.md 4.1)" % n_gpus,
             "cache": "working set per step 2 x (Y+Z+Zf+B) = 1.5 GB >> 126 MB L2 (inputs larger than L2)",
             "library_env": {"GPCSD_GEMM_RESERVE": os.environ.get("GPCSD_GEMM_RESERVE", "0")}}
 
@@ -498,10 +498,9 @@ def run_gpu(args):
             return
 
         def worker(p):
-            # Phase offset between the probes: an evaluation is a latency-bound eigensolve on 16 SMs followed by GEMMs that
-            # fill the GPU.  Started together, the two probes stay in lock step (both eigensolves, then both GEMM phases
-            # fighting for the SMs); started half an evaluation apart, one probe's eigensolve runs underneath the other's
-            # GEMMs for the whole region.  The offset is inside the timed region.
+            # Optional phase offset between the probes (--stagger; round 1 needed it to keep the probes out of lock step).
+            # The library now alternates the probes' GEMM phases itself (gpcsd_plan_loglik_grad's token), so the default is
+            # to start together.  When used, the offset is inside the timed region.
             if p > 0 and stagger_s[0] > 0.0:
                 time.sleep(p * stagger_s[0] / len(models))
             r = None
@@ -657,7 +656,7 @@ def run_gpu(args):
     t0 = time.perf_counter()
     predict_probe(0, False)
     torch.cuda.synchronize()
-    t_pred = (time.perf_counter() - t0) if not args.no_stagger else 0.0
+    t_pred = time.perf_counter() - t0          # (predict does not go through the plan's token: the phase offset stays)
 
     def timed_predict(nsteps):
         def worker(p):
@@ -810,7 +809,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the configs[0]/[2] secondary lines (N = 1)")
     ap.add_argument("--serial", action="store_true", help="evaluate the two probes one after the other")
-    ap.add_argument("--no-stagger", action="store_true", help="start the probes' evaluation loops together (no phase offset)")
+    ap.add_argument("--stagger", dest="no_stagger", action="store_false",
+                    help="start the probes' evaluation loops half an evaluation apart (round-1 behaviour; the library's GEMM token "
+                         "now alternates the probes by itself: 850 evals/s without the offset, 812-855 with it)")
+    ap.add_argument("--no-stagger", dest="no_stagger", action="store_true", help="(default) start the probes' evaluation loops together")
+    ap.set_defaults(no_stagger=True)
     ap.add_argument("--profile-step", action="store_true", help="run warm-up then ONE step inside cudaProfilerStart/Stop")
     args = ap.parse_args()
     # watchdog: a hang (e.g. a collective one rank never enters) becomes a stack dump of every thread and a non-zero exit
